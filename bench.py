@@ -1,0 +1,305 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark of the ToyCrystals VP-SDE sampling hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Metric (BASELINE.json): 64x64 samples/sec, 300 reverse-SDE (Euler-Maruyama) steps, CFG 1.5, EMA
+weights, t_end 0.005.  One bench "step" = ONE complete sampling job of `--n` samples per GPU
+(configs[1]: n=1024 on 1 B200; weak scaling for N>1, final images all-gathered over NCCL inside the
+timed region).  `value` = device-resident throughput (conditions already in HBM, Philox noise
+in-kernel); `e2e` = the same job through the public Python API with HOST condition buffers and a
+device->host read of the images, copies inside the timed region.
+
+`--impl reference` times the reference algorithm's CPU implementation (the oracle port, which is
+bit-identical to the reference module in fp32) on the host cores, on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "vae-diffusion-toy-crystals_b200"))
+
+CONV_GFLOP_PER_FORWARD = 7.092          # per sample per network forward
+SDE_STEPS, CFG, T_END = 300, 1.5, 0.005
+PEAKS_FALLBACK = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def shard_range(n_total: int, rank: int, world: int):
+    """Contiguous block of global sample indices owned by `rank`."""
+    base, rem = divmod(n_total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_images(local, n_total: int, world: int):
+    """All-gather of the per-rank image blocks -> [n_total,1,H,W] on every rank (the path's only collective)."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return local
+    sizes = [shard_range(n_total, r, world) for r in range(world)]
+    if len({hi - lo for lo, hi in sizes}) == 1:
+        out = local.new_empty((n_total,) + tuple(local.shape[1:]))
+        dist.all_gather_into_tensor(out, local.contiguous())
+        return out
+    parts = [local.new_empty((hi - lo,) + tuple(local.shape[1:])) for lo, hi in sizes]
+    dist.all_gather(parts, local.contiguous())
+    return torch.cat(parts)
+
+
+def max_over_ranks(value: float, device) -> float:
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        d["_source"] = "measured"
+        return d
+    d = dict(PEAKS_FALLBACK)
+    d["_source"] = "fallback"
+    return d
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 8 and r[4 + k].lower() == "active" for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (oracle port) on the host cores, bounded sample
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_samples_per_sec(n: int = 16, steps: int = 3, repeats: int = 1):
+    """Time `steps` reverse-SDE steps (+ final projection) of the reference algorithm on n samples and
+    extrapolate linearly to 300 steps (per-step cost is constant).  Returns (samples/s, description)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import toycrystals_oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = orc.default_init_state_dict(1)
+    y_cat, y_cont = orc.condition_grid(n, 4, 4)
+    g = torch.Generator().manual_seed(1234)
+    x0 = torch.randn((n, 1, 64, 64), generator=g)
+    noise = [torch.randn((n, 1, 64, 64), generator=g) for _ in range(steps)]
+    sch = orc.Schedule(0.1, 30.0)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        orc.sample(sd, orc.DEFAULT_CFG, sch, y_cat, y_cont, x0, "sde", steps, CFG, T_END, noise, keep_trace=False)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    per_eval = best / (steps + 1)
+    sps = n / (per_eval * (SDE_STEPS + 1))
+    desc = (f"reference algorithm (oracle port, torch {torch.__version__} CPU fp32, {torch.get_num_threads()} threads): "
+            f"n={n}, {steps} reverse-SDE steps + projection = {steps + 1} CFG evaluations in {best:.2f}s, "
+            f"extrapolated linearly to {SDE_STEPS + 1} evaluations")
+    return sps, cores, desc
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    vals = []
+    for i in range(args.warmup + args.steps):
+        sps, cores, desc = cpu_reference_samples_per_sec(n=args.cpu_n, steps=args.cpu_steps)
+        if i >= args.warmup:
+            vals.append(sps)
+    v = statistics.mean(vals)
+    line = {
+        "impl": "reference", "metric": "samples_per_sec_64x64_sde300_cfg1.5", "value": v, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * args.cpu_n / v if v else None, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, n_per_gpu=args.n, world=args.gpus),
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args, n_per_gpu, world):
+    return {"workload": f"VP-SDE reverse-SDE Euler-Maruyama sampling, EMA weights (random-init seed 1), CFG {CFG}, "
+                        f"{SDE_STEPS} steps, t_end {T_END}, 64x64x1, n={n_per_gpu} per GPU (BASELINE configs[1])",
+            "n_per_gpu": n_per_gpu, "n_total": n_per_gpu * world, "sde_steps": SDE_STEPS, "cfg": CFG, "t_end": T_END,
+            "sampler": "sde", "precision": args.precision, "parallelism": f"dp{world} (batch sharded, all-gather of images)",
+            "l2_policy": "inputs larger than L2: per-step activation working set >> 126 MB; no explicit flush"}
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from toycrystals_b200.models import sde_score_model as shim
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.n
+    n_total = n * world
+    lo, hi = shard_range(n_total, rank, world)
+
+    # weights: default init, seed 0 = model, seed 1 = EMA (the sampled one); built without the oracle
+    torch.manual_seed(1)
+    model = shim.CondUNetTiny(4, 4, 96, 128, 8, 8, precision=args.precision, chunk=args.chunk).to(dev).eval()
+    sde = shim.VPSDE(0.1, 30.0)
+    y_cat, y_cont = shim.condition_grid(model, n, 3.141592653589793 / 3.0, dev, offset=lo, n_total=n_total)
+    h_cat, h_cont = y_cat.cpu().pin_memory(), y_cont.cpu().pin_memory()
+    h_img = torch.empty((n, 1, 64, 64), dtype=torch.float32).pin_memory()
+    seed = 1234
+
+    def job_device():
+        x = shim.sample_reverse_sde_euler_maruyama(model, sde, y_cat, y_cont, (n, 1, 64, 64), n_steps=SDE_STEPS,
+                                                   guidance_scale=CFG, t_end=T_END, seed=seed, global_index_offset=lo)
+        return gather_images(x, n_total, world)
+
+    def job_e2e():
+        yc = h_cat.to(dev, non_blocking=True)
+        yk = h_cont.to(dev, non_blocking=True)
+        x = shim.sample_reverse_sde_euler_maruyama(model, sde, yc, yk, (n, 1, 64, 64), n_steps=SDE_STEPS,
+                                                   guidance_scale=CFG, t_end=T_END, seed=seed, global_index_offset=lo)
+        full = gather_images(x, n_total, world)
+        h_img.copy_(full[lo:hi], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(h_img[0, 0, 0, 0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1), dev)  # ms, max over ranks
+
+    for _ in range(args.warmup):
+        job_device()
+    launches0 = model.launch_count()
+    with ClockSampler(local_rank) as clk:
+        ms = timed(job_device, args.steps)
+    launches = model.launch_count() - launches0
+    job_e2e()
+    ms_e2e = timed(job_e2e, args.steps)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sps, cores, desc = cpu_reference_samples_per_sec(n=args.cpu_n, steps=args.cpu_steps)
+        cpu = {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port", "sample": desc}
+    if rank == 0:
+        peaks = load_peaks()
+        value = n_total * args.steps / (ms / 1e3)
+        e2e = n_total * args.steps / (ms_e2e / 1e3)
+        tflop_per_sample = 2 * (SDE_STEPS + 1) * CONV_GFLOP_PER_FORWARD / 1e3
+        achieved = value / world * tflop_per_sample
+        peak = peaks.get("bf16_tflops_sustained", PEAKS_FALLBACK["bf16_tflops_sustained"])
+        line = {
+            "metric": "samples_per_sec_64x64_sde300_cfg1.5", "value": value, "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": workload_config(args, n, world),
+            "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": int(h_cat.numel() * 8 + h_cont.numel() * 4),
+                    "d2h_bytes_per_step": int(h_img.numel() * 4)},
+            "gpu_launches": int(launches),
+            "clocks": clk.summary(),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "traffic": None,
+                         "note": f"whole-job conv FLOPs ({tflop_per_sample:.3f} TFLOP/sample) / wall time per GPU, "
+                                 f"vs bf16 sustained peak ({peaks['_source']})"},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=1024, help="samples per GPU per job")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--cpu-n", type=int, default=16)
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

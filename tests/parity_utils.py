@@ -1,0 +1,89 @@
+"""Shared helpers of the parity tests (CUDA path vs oracle)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+import torch.nn.functional as F
+
+import toycrystals_oracle as orc
+from toycrystals_b200 import _cabi
+from toycrystals_b200.models.sde_score_model import CondUNetTiny, VPSDE
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CFG = dict(orc.DEFAULT_CFG)
+_models = {}
+
+
+def rel_l2(a, b):
+    return orc.rel_l2(a, b)
+
+
+def model(precision: str, engine: str = "auto", seed: int = 0, chunk: int = 0, use_graph: bool = True) -> CondUNetTiny:
+    key = (precision, engine, seed, chunk, use_graph)
+    if key not in _models:
+        m = CondUNetTiny(**CFG, precision=precision, engine=engine, chunk=chunk, use_graph=use_graph)
+        m.load_state_dict(orc.default_init_state_dict(seed))
+        _models[key] = m.to("cuda").eval()
+    return _models[key]
+
+
+def golden(name):
+    return torch.load(os.path.join(GOLDEN, name), weights_only=False)
+
+
+def conv_reference(in0, in1, w, b, ksize, stride, round_bf16=False):
+    """torch circular conv on NHWC fp32 inputs; returns NHWC fp32."""
+    x = in0 if in1 is None else torch.cat([in0, in1], dim=-1)
+    if round_bf16:
+        x = x.bfloat16().float()
+        w = w.bfloat16().float()
+    x = x.permute(0, 3, 1, 2).double()
+    if ksize > 1:
+        x = F.pad(x, (1, 1, 1, 1), mode="circular")
+    y = F.conv2d(x, w.double(), b.double(), stride=stride)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+def debug_conv(engine, precision, in0, in1, w, b, ksize, stride, epi):
+    """in0/in1 NHWC fp32 CUDA tensors.  Returns (out NHWC fp32, stats [B,8,2] or None)."""
+    L = _cabi.lib()
+    B, Hin, Win, c0 = in0.shape
+    c1 = 0 if in1 is None else in1.shape[-1]
+    Ho, Wo = Hin // stride, Win // stride
+    cout = w.shape[0]
+    out = torch.full((B, Ho, Wo, cout), float("nan"), device="cuda")
+    stats = torch.zeros((B, 8, 2), device="cuda") if epi == 0 else None
+    torch.cuda.synchronize()
+    _cabi.check(L.tcs_debug_conv(_cabi.__dict__["ENGINE_" + engine.upper()], _cabi.__dict__[precision.upper()], B, Ho, Wo,
+                                 c0, c1, cout, ksize, stride, in0.data_ptr(), None if in1 is None else in1.data_ptr(),
+                                 w.contiguous().data_ptr(), b.data_ptr(), out.data_ptr(),
+                                 None if stats is None else stats.data_ptr(), epi, None))
+    torch.cuda.synchronize()
+    return out, stats
+
+
+def debug_layer(m: CondUNetTiny, name, x, t, y_cat, y_cont, C_out, res):
+    h = m.engine_handle()
+    n = x.shape[0]
+    out = torch.full((n, res, res, C_out), float("nan"), device="cuda")
+    got = _cabi.lib().tcs_debug_layer(h, name.encode(), x.data_ptr(), t.data_ptr(), y_cat.data_ptr(), y_cont.data_ptr(),
+                                      n, 0, out.data_ptr(), out.numel(), None)
+    if got < 0:
+        _cabi.check(int(got))
+    torch.cuda.synchronize()
+    assert got == out.numel(), (name, got, out.numel())
+    return out
+
+
+# layer name -> (channels, resolution, is post-activation tap)
+LAYERS = [
+    ("down1.net.0.raw", 96, 64), ("down1.net.0.act", 96, 64), ("down1.net.3.raw", 96, 64), ("down1.net.3.act", 96, 64),
+    ("ds1", 96, 32), ("down2.net.0.raw", 192, 32), ("down2.net.0.act", 192, 32), ("down2.net.3.raw", 192, 32),
+    ("down2.net.3.act", 192, 32), ("ds2", 192, 16), ("mid.net.0.raw", 192, 16), ("mid.net.0.act", 192, 16),
+    ("mid.net.3.raw", 192, 16), ("mid.net.3.act", 192, 16), ("attn", 192, 16), ("us2_conv", 192, 32),
+    ("up2.net.0.raw", 96, 32), ("up2.net.0.act", 96, 32), ("up2.net.3.raw", 96, 32), ("up2.net.3.act", 96, 32),
+    ("us1_conv", 96, 64), ("up1.net.0.raw", 96, 64), ("up1.net.0.act", 96, 64), ("up1.net.3.raw", 96, 64),
+    ("up1.net.3.act", 96, 64),
+]

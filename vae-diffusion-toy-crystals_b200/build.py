@@ -1,0 +1,65 @@
+#!/usr/bin/env python3
+"""Build libtcs.so (sm_100a only) in-tree with nvcc.  No torch headers are involved: the library
+is a plain C-ABI shared object that the Python shim loads with ctypes.
+
+    python vae-diffusion-toy-crystals_b200/build.py [--force]
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT_DIR = os.path.join(HERE, "toycrystals_b200")
+LIB = os.path.join(OUT_DIR, "libtcs.so")
+OBJ_DIR = os.path.join(HERE, "build")
+SOURCES = ["tcs_api.cu", "conv_tc.cu", "kernels_simt.cu", "kernels_embed.cu", "kernels_step.cu"]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+
+
+def _newer(target: str, deps) -> bool:
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(d) <= t for d in deps)
+
+
+def build_lib(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers.append(os.path.join(HERE, "..", "include", "tcs.h"))
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    if not force and _newer(LIB, srcs + headers + [os.path.abspath(__file__)]):
+        return LIB
+
+    def compile_one(src):
+        obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
+        if not force and _newer(obj, [src] + headers):
+            return obj, ""
+        r = subprocess.run([NVCC, *FLAGS, "-c", src, "-o", obj], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        return obj, r.stderr
+
+    with ThreadPoolExecutor(max_workers=len(srcs)) as ex:
+        res = list(ex.map(compile_one, srcs))
+    with open(os.path.join(OBJ_DIR, "ptxas.log"), "a") as f:
+        for _, log in res:
+            f.write(log)
+            if verbose:
+                sys.stderr.write(log)
+    objs = [o for o, _ in res]
+    r = subprocess.run([NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,71 @@
+// common.cuh — shared declarations for libtcs (B200 / sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/tcs.h"
+
+namespace tcs {
+
+constexpr int IMG = 64;            // the sampler hard-codes 64x64 (sde_score_model.py:329,340)
+constexpr int IMG_PIX = IMG * IMG;
+constexpr int GN_GROUPS = 8;       // _gn_groups(96) == _gn_groups(192) == 8 (sde_score_model.py:89-94)
+constexpr float GN_EPS = 1e-5f;
+constexpr int N_HEADS = 4;
+
+// thread-local error plumbing (tcs_api.cu)
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+
+#define TCS_CUDA(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      return ::tcs::fail(TCS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));     \
+  } while (0)
+
+#define TCS_CHECK(expr)                    \
+  do {                                     \
+    int _s = (expr);                       \
+    if (_s != TCS_OK) return _s;           \
+  } while (0)
+
+// --------------------------------------------------------------------------------------
+// tensor geometry: activations are NHWC.  "padded" tensors carry a 1-pixel circular halo:
+// [B, H+2, W+2, C]; padded (py,px) holds image ((py-1) mod H, (px-1) mod W).
+// --------------------------------------------------------------------------------------
+enum Epilogue : int {
+  EPI_RAW_STATS = 0,  // fp32 [B,H,W,N] + bias, plus GroupNorm partial sums
+  EPI_PADDED = 1,     // T [B,H+2,W+2,ldo] + bias (+ residual), halo written
+  EPI_PLAIN = 2       // T [M, ldo] + bias
+};
+
+struct ConvGeom {
+  int B;          // images in this pass
+  int H, W;       // OUTPUT spatial size
+  int ksize;      // 1, 3 or 4
+  int stride;     // 1 or 2
+  int nsrc;       // 1 or 2 (skip-concat as split-K)
+  int csrc[2];    // channels per source (multiples of 32)
+  int in_pad[2];  // 1 = source is a padded tensor, 0 = plain
+  int ntot;       // total output channels
+};
+
+struct EpiArgs {
+  const float* bias;      // [ntot]
+  void* out;              // see Epilogue
+  float* partials;        // EPI_RAW_STATS: [B][slots][8][2]
+  const void* residual;   // EPI_PADDED optional: padded T [B,H+2,W+2,ntot]
+  int ldo;                // channel pitch of `out`
+  int slots;              // partial slots per image
+};
+
+// GroupNorm partial-sum slots per image written by each conv engine
+inline int tc_slots(int H, int W) { return (H * W / 128) * 4; }
+inline int simt_slots(int H, int W) { return H * W / 64; }
+
+}  // namespace tcs

@@ -1,0 +1,47 @@
+// conv_tc.cuh — host interface of the tcgen05 implicit-GEMM convolution (conv_tc.cu).
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+namespace tcs {
+
+struct ConvTcParams {
+  int n_mtiles, n_ntiles;   // tiles = n_mtiles * n_ntiles
+  int tiles_per_img;        // M tiles per image
+  int H, W;                 // output spatial size
+  int Rt;                   // image rows per 128-pixel sub-tile (= 128 / W)
+  int T, KYG, KW;           // taps per stage, ky groups, kx count
+  int stride, WR;           // conv stride; window rows per stage
+  int nsrc, cblk[2], base_off[2];
+  int ntot;                 // total output channels
+  int kstages;              // pipeline stages (K iterations) per tile
+  int nstage;               // smem ring depth
+  uint32_t a_bytes, stage_bytes;
+  EpiArgs epi;
+};
+
+struct ConvTcPlan {
+  CUtensorMap mapA[2];
+  CUtensorMap mapW;
+  ConvTcParams p;
+  int N;       // N tile (96 or 192)
+  int epi;     // Epilogue
+  int msub;    // 128-row sub-tiles per CTA tile
+  int grid;
+  size_t smem;
+  bool valid = false;
+};
+
+// number of K stages and packed weight element count for a geometry
+int conv_tc_kstages(const ConvGeom& g);
+size_t conv_tc_packed_elems(const ConvGeom& g);
+// weight [ntot][cin_total][k][k] fp32 (PyTorch layout) -> bf16 [kstage][T][ntot][32]
+void conv_tc_pack_weights(const ConvGeom& g, const float* w, __nv_bfloat16* out_host);
+
+// src0/src1: bf16 NHWC device tensors (padded or plain as g.in_pad says); wpacked: device bf16
+int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, const void* src1,
+                      const __nv_bfloat16* wpacked, int epi, const EpiArgs& ea, int sm_count);
+int conv_tc_launch(const ConvTcPlan& plan, cudaStream_t stream);
+
+}  // namespace tcs

@@ -1,0 +1,699 @@
+// kernels_simt.cu — CUDA-core kernels of the score network (everything that is not a
+// tensor-core GEMM): first 1->96 conv, GroupNorm(+SiLU), bilinear x2, attention, 96->1 out conv
+// with the CFG combine, and a generic fp32-accumulate SIMT convolution that is the whole conv
+// engine of the fp32 mode (and the on-GPU cross-check of the tcgen05 engine in bf16 mode).
+//
+// Reference: CondUNetTiny.forward, src/toycrystals/models/sde_score_model.py:243-266 and the
+// modules it calls (_ConvBlock :97-111, SelfAttention2d :114-167, nn.Upsample :217,221).
+#include "kernels.cuh"
+
+namespace tcs {
+
+// ------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------
+template <typename T> struct Vec8;  // 8 consecutive channels
+template <> struct Vec8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) { a = *reinterpret_cast<const float4*>(p); b = *reinterpret_cast<const float4*>(p + 4); }
+  __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = a; *reinterpret_cast<float4*>(p + 4) = b; }
+  __device__ __forceinline__ void get(float* f) const { f[0]=a.x; f[1]=a.y; f[2]=a.z; f[3]=a.w; f[4]=b.x; f[5]=b.y; f[6]=b.z; f[7]=b.w; }
+  __device__ __forceinline__ void set(const float* f) { a = make_float4(f[0],f[1],f[2],f[3]); b = make_float4(f[4],f[5],f[6],f[7]); }
+};
+template <> struct Vec8<__nv_bfloat16> {
+  uint4 u;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { u = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void store(__nv_bfloat16* p) const { *reinterpret_cast<uint4*>(p) = u; }
+  __device__ __forceinline__ void get(float* f) const {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2*i] = t.x; f[2*i+1] = t.y; }
+  }
+  __device__ __forceinline__ void set(const float* f) {
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2*i], f[2*i+1]);
+  }
+};
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16(v); }
+
+// padded-tensor halo bookkeeping: image (y,x) lives at padded (y+1,x+1); rows/cols on the border
+// are duplicated on the opposite halo.  wrap offset in padded rows/cols (0 = interior only).
+__device__ __forceinline__ int halo_wrap(int v, int n) { return v == 0 ? n : (v == n - 1 ? -n : 0); }
+
+// ------------------------------------------------------------------------------------------
+// first conv: x[n,64,64] (*) w9[96][9], circular, + tvec[row] + cvec[b]   -> raw fp32 + GN partials
+// block = 2 image rows (128 px) of one sample, 192 threads: oc = t%96, pixel parity = t/96
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(192) first_conv_kernel(const float* __restrict__ x, const float* __restrict__ w9,
+                                                        const float* __restrict__ tvec, int tvec_stride,
+                                                        const int* __restrict__ step_ptr, int trow_off,
+                                                        const float* __restrict__ cvec, int dup,
+                                                        float* __restrict__ raw, float* __restrict__ partials) {
+  __shared__ float xs[4][IMG + 2];
+  __shared__ float red[2][96][2][2];  // [half][oc][u][sum,sumsq]
+  const int i = blockIdx.x >> 5, rp = blockIdx.x & 31, y0 = rp * 2;
+  const int t = threadIdx.x, oc = t % 96, half = t / 96;
+  for (int e = t; e < 4 * (IMG + 2); e += 192) {
+    const int r = e / (IMG + 2), c = e % (IMG + 2);
+    const int yy = (y0 - 1 + r + IMG) & (IMG - 1), xx = (c - 1 + IMG) & (IMG - 1);
+    xs[r][c] = x[(static_cast<size_t>(i) * IMG + yy) * IMG + xx];
+  }
+  float w[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) w[k] = w9[oc * 9 + k];
+  const int trow = (step_ptr ? *step_ptr : 0) + trow_off + i * tvec_stride;
+  const float tb = tvec[static_cast<size_t>(trow) * 96 + oc];
+  float bias[2], s[2] = {0.f, 0.f}, q[2] = {0.f, 0.f};
+  for (int u = 0; u < dup; ++u) bias[u] = tb + cvec[(static_cast<size_t>(i) * dup + u) * 96 + oc];
+  __syncthreads();
+  for (int p = half; p < 128; p += 2) {
+    const int r = p >> 6, c = p & 63;
+    float acc = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) acc = fmaf(w[ky * 3 + kx], xs[r + ky][c + kx], acc);
+    for (int u = 0; u < dup; ++u) {
+      const float v = acc + bias[u];
+      raw[((static_cast<size_t>(i) * dup + u) * IMG_PIX + (y0 + r) * IMG + c) * 96 + oc] = v;
+      s[u] += v;
+      q[u] += v * v;
+    }
+  }
+  for (int u = 0; u < dup; ++u) { red[half][oc][u][0] = s[u]; red[half][oc][u][1] = q[u]; }
+  __syncthreads();
+  if (t < 8 * dup) {
+    const int g = t % 8, u = t / 8;
+    float ss = 0.f, qq = 0.f;
+    for (int h = 0; h < 2; ++h)
+      for (int c = 0; c < 12; ++c) { ss += red[h][g * 12 + c][u][0]; qq += red[h][g * 12 + c][u][1]; }
+    float* dst = partials + ((static_cast<size_t>(i) * dup + u) * FIRST_CONV_SLOTS + rp) * 16 + 2 * g;
+    dst[0] = ss;
+    dst[1] = qq;
+  }
+}
+
+int launch_first_conv(const float* x, const float* w9, const float* tvec, int tvec_stride, const int* step_ptr,
+                      int trow_off, const float* cvec, int n, int dup, float* raw, float* partials,
+                      cudaStream_t st) {
+  if (n <= 0) return TCS_OK;
+  first_conv_kernel<<<n * 32, 192, 0, st>>>(x, w9, tvec, tvec_stride, step_ptr, trow_off, cvec, dup, raw, partials);
+  TCS_CUDA(cudaGetLastError());
+  return TCS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// GroupNorm statistics from partial sums (fp64 combine, fixed order -> deterministic)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void gn_finalize(const float* __restrict__ part, int slots, double count, float* s_mean,
+                                            float* s_rstd) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp < GN_GROUPS) {
+    double s = 0.0, q = 0.0;
+    for (int k = lane; k < slots; k += 32) {
+      s += static_cast<double>(part[k * 16 + 2 * warp]);
+      q += static_cast<double>(part[k * 16 + 2 * warp + 1]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (lane == 0) {
+      const double mean = s / count;
+      double var = q / count - mean * mean;
+      var = var < 0.0 ? 0.0 : var;
+      s_mean[warp] = static_cast<float>(mean);
+      s_rstd[warp] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(GN_EPS)));
+    }
+  }
+  __syncthreads();
+}
+
+template <typename T, bool IN_PADDED, bool SILU>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ in_, const float* __restrict__ partials,
+                                                      int slots, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, int H, int W, int C,
+                                                      T* __restrict__ out) {
+  __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
+  const int b = blockIdx.y;
+  gn_finalize(partials + static_cast<size_t>(b) * slots * 16, slots, static_cast<double>(H) * W * (C / GN_GROUPS),
+              s_mean, s_rstd);
+  const int cv = C / 8, cpg = C / GN_GROUPS;
+  const int nvec = H * W * cv;
+  const int Wp = W + 2, Hp = H + 2;
+  for (int e = blockIdx.x * 256 + threadIdx.x; e < nvec; e += gridDim.x * 256) {
+    const int pix = e / cv, c = (e - pix * cv) * 8;
+    const int y = pix / W, x = pix - y * W;
+    float v[8];
+    if constexpr (IN_PADDED) {
+      Vec8<T> iv;
+      iv.load(static_cast<const T*>(in_) + ((static_cast<size_t>(b) * Hp + y + 1) * Wp + x + 1) * C + c);
+      iv.get(v);
+    } else {
+      Vec8<float> iv;
+      iv.load(static_cast<const float*>(in_) + (static_cast<size_t>(b) * H * W + pix) * C + c);
+      iv.get(v);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int g = (c + k) / cpg;
+      float yv = (v[k] - s_mean[g]) * s_rstd[g] * __ldg(gamma + c + k) + __ldg(beta + c + k);
+      if constexpr (SILU) yv = yv / (1.0f + expf(-yv));
+      v[k] = yv;
+    }
+    Vec8<T> ov;
+    ov.set(v);
+    const int wy = halo_wrap(y, H), wx = halo_wrap(x, W);
+    const size_t base = (static_cast<size_t>(b) * Hp + y + 1) * Wp + x + 1;
+    ov.store(out + base * C + c);
+    if (wy) ov.store(out + (base + static_cast<long long>(wy) * Wp) * C + c);
+    if (wx) ov.store(out + (base + wx) * C + c);
+    if (wy && wx) ov.store(out + (base + static_cast<long long>(wy) * Wp + wx) * C + c);
+  }
+}
+
+template <typename T>
+int launch_gn_apply(const void* in, int in_padded, const float* partials, int slots, const float* gamma,
+                    const float* beta, int B, int H, int W, int C, int silu, T* out, cudaStream_t st) {
+  if (B <= 0) return TCS_OK;
+  const int nvec = H * W * (C / 8);
+  int gx = (nvec + 256 * 4 - 1) / (256 * 4);
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, B);
+  if (in_padded && !silu)
+    gn_apply_kernel<T, true, false><<<grid, 256, 0, st>>>(in, partials, slots, gamma, beta, H, W, C, out);
+  else if (!in_padded && silu)
+    gn_apply_kernel<T, false, true><<<grid, 256, 0, st>>>(in, partials, slots, gamma, beta, H, W, C, out);
+  else if (!in_padded && !silu)
+    gn_apply_kernel<T, false, false><<<grid, 256, 0, st>>>(in, partials, slots, gamma, beta, H, W, C, out);
+  else
+    gn_apply_kernel<T, true, true><<<grid, 256, 0, st>>>(in, partials, slots, gamma, beta, H, W, C, out);
+  TCS_CUDA(cudaGetLastError());
+  return TCS_OK;
+}
+template int launch_gn_apply<float>(const void*, int, const float*, int, const float*, const float*, int, int, int, int, int, float*, cudaStream_t);
+template int launch_gn_apply<__nv_bfloat16>(const void*, int, const float*, int, const float*, const float*, int, int, int, int, int, __nv_bfloat16*, cudaStream_t);
+
+// statistics of a padded T tensor (one block per image; thread = channel) -> one partial slot
+template <typename T>
+__global__ void __launch_bounds__(192) gn_stats_kernel(const T* __restrict__ in, int H, int W, int C,
+                                                      float* __restrict__ partials) {
+  __shared__ float red[192][2];
+  const int b = blockIdx.x, c = threadIdx.x;
+  const int Wp = W + 2, Hp = H + 2;
+  float s = 0.f, q = 0.f;
+  if (c < C)
+    for (int y = 0; y < H; ++y)
+      for (int x = 0; x < W; ++x) {
+        const float v = to_f<T>(in[((static_cast<size_t>(b) * Hp + y + 1) * Wp + x + 1) * C + c]);
+        s += v;
+        q += v * v;
+      }
+  red[c][0] = s;
+  red[c][1] = q;
+  __syncthreads();
+  if (c < GN_GROUPS) {
+    const int cpg = C / GN_GROUPS;
+    float ss = 0.f, qq = 0.f;
+    for (int k = 0; k < cpg; ++k) { ss += red[c * cpg + k][0]; qq += red[c * cpg + k][1]; }
+    partials[static_cast<size_t>(b) * 16 + 2 * c] = ss;
+    partials[static_cast<size_t>(b) * 16 + 2 * c + 1] = qq;
+  }
+}
+template <typename T>
+int launch_gn_stats(const T* in, int B, int H, int W, int C, float* partials, cudaStream_t st) {
+  if (B <= 0) return TCS_OK;
+  if (C > 192) return fail(TCS_ERR_UNSUPPORTED, "gn_stats: C > 192");
+  gn_stats_kernel<T><<<B, 192, 0, st>>>(in, H, W, C, partials);
+  TCS_CUDA(cudaGetLastError());
+  return TCS_OK;
+}
+template int launch_gn_stats<float>(const float*, int, int, int, int, float*, cudaStream_t);
+template int launch_gn_stats<__nv_bfloat16>(const __nv_bfloat16*, int, int, int, int, float*, cudaStream_t);
+
+// ------------------------------------------------------------------------------------------
+// bilinear x2, align_corners=False, edge clamp (nn.Upsample, sde_score_model.py:217,221)
+// value = wy0*(wx0*a + wx1*b) + wy1*(wx0*c + wx1*d)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) upsample2x_kernel(const T* __restrict__ in, int h, int w, int C,
+                                                        T* __restrict__ out, long long total) {
+  const long long e = blockIdx.x * 256LL + threadIdx.x;
+  if (e >= total) return;
+  const int cv = C / 8;
+  const int c = static_cast<int>(e % cv) * 8;
+  long long r = e / cv;
+  const int H = 2 * h, W = 2 * w;
+  const int x = static_cast<int>(r % W); r /= W;
+  const int y = static_cast<int>(r % H);
+  const int b = static_cast<int>(r / H);
+  const float sy = fmaxf(0.5f * (y + 0.5f) - 0.5f, 0.f), sx = fmaxf(0.5f * (x + 0.5f) - 0.5f, 0.f);
+  const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
+  const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+  const float ly = sy - y0, lx = sx - x0;
+  const float wy0 = 1.f - ly, wx0 = 1.f - lx;
+  const int wp = w + 2, hp = h + 2;
+  const T* ib = in + static_cast<size_t>(b) * hp * wp * C + c;
+  Vec8<T> va, vb, vc, vd;
+  va.load(ib + (static_cast<size_t>(y0 + 1) * wp + x0 + 1) * C);
+  vb.load(ib + (static_cast<size_t>(y0 + 1) * wp + x1 + 1) * C);
+  vc.load(ib + (static_cast<size_t>(y1 + 1) * wp + x0 + 1) * C);
+  vd.load(ib + (static_cast<size_t>(y1 + 1) * wp + x1 + 1) * C);
+  float fa[8], fb[8], fc[8], fd[8], o[8];
+  va.get(fa); vb.get(fb); vc.get(fc); vd.get(fd);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) o[k] = wy0 * (wx0 * fa[k] + lx * fb[k]) + ly * (wx0 * fc[k] + lx * fd[k]);
+  Vec8<T> ov;
+  ov.set(o);
+  const int Wp = W + 2, Hp = H + 2;
+  const int wy = halo_wrap(y, H), wx = halo_wrap(x, W);
+  const size_t base = (static_cast<size_t>(b) * Hp + y + 1) * Wp + x + 1;
+  ov.store(out + base * C + c);
+  if (wy) ov.store(out + (base + static_cast<long long>(wy) * Wp) * C + c);
+  if (wx) ov.store(out + (base + wx) * C + c);
+  if (wy && wx) ov.store(out + (base + static_cast<long long>(wy) * Wp + wx) * C + c);
+}
+template <typename T>
+int launch_upsample2x(const T* in, int B, int h, int w, int C, T* out, cudaStream_t st) {
+  if (B <= 0) return TCS_OK;
+  const long long total = static_cast<long long>(B) * 4 * h * w * (C / 8);
+  upsample2x_kernel<T><<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(in, h, w, C, out, total);
+  TCS_CUDA(cudaGetLastError());
+  return TCS_OK;
+}
+template int launch_upsample2x<float>(const float*, int, int, int, int, float*, cudaStream_t);
+template int launch_upsample2x<__nv_bfloat16>(const __nv_bfloat16*, int, int, int, int, __nv_bfloat16*, cudaStream_t);
+
+// ------------------------------------------------------------------------------------------
+// attention: 4 heads x 256 tokens x d=48 (SelfAttention2d, sde_score_model.py:146-164)
+// block = (image, head); thread = query token; K,V in shared memory; online softmax
+// ------------------------------------------------------------------------------------------
+constexpr int ATT_TOK = 256, ATT_D = 48, ATT_C = 192;
+template <typename T>
+__global__ void __launch_bounds__(ATT_TOK) attention_kernel(const T* __restrict__ qkv, T* __restrict__ yout) {
+  extern __shared__ float att_smem[];
+  float* Ks = att_smem;
+  float* Vs = att_smem + ATT_TOK * ATT_D;
+  const int b = blockIdx.x >> 2, head = blockIdx.x & 3, t = threadIdx.x;
+  const T* base = qkv + static_cast<size_t>(b) * ATT_TOK * (3 * ATT_C);
+  for (int e = t; e < ATT_TOK * (ATT_D / 8); e += ATT_TOK) {
+    const int tok = e / (ATT_D / 8), d8 = (e % (ATT_D / 8)) * 8;
+    Vec8<T> kv, vv;
+    kv.load(base + static_cast<size_t>(tok) * (3 * ATT_C) + ATT_C + head * ATT_D + d8);
+    vv.load(base + static_cast<size_t>(tok) * (3 * ATT_C) + 2 * ATT_C + head * ATT_D + d8);
+    kv.get(Ks + tok * ATT_D + d8);
+    vv.get(Vs + tok * ATT_D + d8);
+  }
+  float q[ATT_D], acc[ATT_D];
+  const float scale = 0.14433756729740643f;  // 1/sqrt(48)
+#pragma unroll
+  for (int d8 = 0; d8 < ATT_D; d8 += 8) {
+    Vec8<T> qv;
+    qv.load(base + static_cast<size_t>(t) * (3 * ATT_C) + head * ATT_D + d8);
+    qv.get(q + d8);
+  }
+#pragma unroll
+  for (int d = 0; d < ATT_D; ++d) { q[d] *= scale; acc[d] = 0.f; }
+  __syncthreads();
+  float m = -INFINITY, l = 0.f;
+  for (int j0 = 0; j0 < ATT_TOK; j0 += 8) {
+    float s[8];
+    float mx = m;
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      const float4* kr = reinterpret_cast<const float4*>(Ks + (j0 + jj) * ATT_D);
+      float a = 0.f;
+#pragma unroll
+      for (int d4 = 0; d4 < ATT_D / 4; ++d4) {
+        const float4 k4 = kr[d4];
+        a = fmaf(q[4 * d4], k4.x, a); a = fmaf(q[4 * d4 + 1], k4.y, a);
+        a = fmaf(q[4 * d4 + 2], k4.z, a); a = fmaf(q[4 * d4 + 3], k4.w, a);
+      }
+      s[jj] = a;
+      mx = fmaxf(mx, a);
+    }
+    const float corr = expf(m - mx);
+    m = mx;
+    l *= corr;
+#pragma unroll
+    for (int d = 0; d < ATT_D; ++d) acc[d] *= corr;
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      const float pj = expf(s[jj] - m);
+      l += pj;
+      const float4* vr = reinterpret_cast<const float4*>(Vs + (j0 + jj) * ATT_D);
+#pragma unroll
+      for (int d4 = 0; d4 < ATT_D / 4; ++d4) {
+        const float4 v4 = vr[d4];
+        acc[4 * d4] = fmaf(pj, v4.x, acc[4 * d4]); acc[4 * d4 + 1] = fmaf(pj, v4.y, acc[4 * d4 + 1]);
+        acc[4 * d4 + 2] = fmaf(pj, v4.z, acc[4 * d4 + 2]); acc[4 * d4 + 3] = fmaf(pj, v4.w, acc[4 * d4 + 3]);
+      }
+    }
+  }
+  const float inv = 1.0f / l;
+  T* orow = yout + (static_cast<size_t>(b) * ATT_TOK + t) * ATT_C + head * ATT_D;
+#pragma unroll
+  for (int d8 = 0; d8 < ATT_D; d8 += 8) {
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = acc[d8 + k] * inv;
+    Vec8<T> ov;
+    ov.set(o);
+    ov.store(orow + d8);
+  }
+}
+template <typename T>
+int launch_attention(const T* qkv, int B, T* y, cudaStream_t st) {
+  if (B <= 0) return TCS_OK;
+  const size_t smem = 2 * ATT_TOK * ATT_D * sizeof(float);
+  static bool done = false;
+  if (!done) {
+    TCS_CUDA(cudaFuncSetAttribute(attention_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    done = true;
+  }
+  attention_kernel<T><<<B * N_HEADS, ATT_TOK, smem, st>>>(qkv, y);
+  TCS_CUDA(cudaGetLastError());
+  return TCS_OK;
+}
+template int launch_attention<float>(const float*, int, float*, cudaStream_t);
+template int launch_attention<__nv_bfloat16>(const __nv_bfloat16*, int, __nv_bfloat16*, cudaStream_t);
+
+// ------------------------------------------------------------------------------------------
+// generic SIMT convolution: tile = 64 pixels x 96 output channels, 256 threads (4 px x 6 oc each)
+// ------------------------------------------------------------------------------------------
+struct SimtConvParams {
+  int B, H, W, HW;            // output
+  int ksize, stride, nsrc;
+  int csrc[2], Hin[2], Win[2], base_off[2];
+  int cin_tot, ntot;
+  EpiArgs epi;
+};
+
+template <typename T, int EPI>
+__global__ void __launch_bounds__(256) conv_simt_kernel(const T* __restrict__ src0, const T* __restrict__ src1,
+                                                       const float* __restrict__ wp, const SimtConvParams p) {
+  __shared__ __align__(16) float As[32][68];
+  __shared__ __align__(16) float Bs[32][96];
+  __shared__ float red[256][2];
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  const int m0 = blockIdx.x * 64, n_off = blockIdx.y * 96;
+  const int b = m0 / p.HW;
+  // A-load role: pixel lp = t/4, 8 channels at (t%4)*8
+  const int lp = t >> 2, lc = (t & 3) * 8;
+  const int lrem = m0 + lp - b * p.HW;
+  const int ly = lrem / p.W, lx = lrem - ly * p.W;
+  float acc[4][6];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 6; ++j) acc[i][j] = 0.f;
+
+  for (int tap = 0; tap < p.ksize * p.ksize; ++tap) {
+    const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
+    int coff = 0;
+    for (int s = 0; s < p.nsrc; ++s) {
+      const T* src = s == 0 ? src0 : src1;
+      const int C = p.csrc[s];
+      const int iy = ly * p.stride + ky + p.base_off[s], ix = lx * p.stride + kx + p.base_off[s];
+      const T* arow = src + ((static_cast<size_t>(b) * p.Hin[s] + iy) * p.Win[s] + ix) * C + lc;
+      for (int cb = 0; cb < C; cb += 32) {
+        Vec8<T> av;
+        av.load(arow + cb);
+        float f[8];
+        av.get(f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) As[lc + k][lp] = f[k];
+        const float* wrow = wp + (static_cast<size_t>(tap) * p.cin_tot + coff + cb) * p.ntot + n_off;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const int e = t + r * 256;           // 768 float4 = 32 rows x 24
+          const int kk = e / 24, c4 = (e - kk * 24) * 4;
+          *reinterpret_cast<float4*>(&Bs[kk][c4]) = __ldg(reinterpret_cast<const float4*>(wrow + static_cast<size_t>(kk) * p.ntot + c4));
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int kk = 0; kk < 32; ++kk) {
+          const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+          const float2 b0 = *reinterpret_cast<const float2*>(&Bs[kk][tx * 6]);
+          const float2 b1 = *reinterpret_cast<const float2*>(&Bs[kk][tx * 6 + 2]);
+          const float2 b2 = *reinterpret_cast<const float2*>(&Bs[kk][tx * 6 + 4]);
+          const float av4[4] = {a4.x, a4.y, a4.z, a4.w};
+          const float bv[6] = {b0.x, b0.y, b1.x, b1.y, b2.x, b2.y};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 6; ++j) acc[i][j] = fmaf(av4[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+      }
+      coff += C;
+    }
+  }
+
+  // ---- epilogue -------------------------------------------------------------------------
+  const int oc0 = n_off + tx * 6;
+  float bias[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) bias[j] = __ldg(p.epi.bias + oc0 + j);
+  if constexpr (EPI == EPI_RAW_STATS) {
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + ty * 4 + i;
+      float* o = static_cast<float*>(p.epi.out) + static_cast<size_t>(m) * p.epi.ldo + oc0;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const float v = acc[i][j] + bias[j];
+        o[j] = v;
+        s += v;
+        q += v * v;
+      }
+    }
+    red[t][0] = s;
+    red[t][1] = q;
+    __syncthreads();
+    const int cpg = p.ntot / GN_GROUPS;      // 12 or 24
+    const int gpt = 96 / cpg;                // groups in this n-tile: 8 or 4
+    if (t < gpt) {
+      const int txpg = cpg / 6;              // tx values per group: 2 or 4
+      float ss = 0.f, qq = 0.f;
+      for (int yy = 0; yy < 16; ++yy)
+        for (int xx = 0; xx < txpg; ++xx) { ss += red[yy * 16 + t * txpg + xx][0]; qq += red[yy * 16 + t * txpg + xx][1]; }
+      const int slot = (m0 - b * p.HW) / 64;
+      const int g = n_off / cpg + t;
+      float* dst = p.epi.partials + (static_cast<size_t>(b) * p.epi.slots + slot) * 16 + 2 * g;
+      dst[0] = ss;
+      dst[1] = qq;
+    }
+  } else if constexpr (EPI == EPI_PADDED) {
+    const int Wp = p.W + 2, Hp = p.H + 2;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rem = m0 + ty * 4 + i - b * p.HW;
+      const int y = rem / p.W, x = rem - y * p.W;
+      const size_t pix = (static_cast<size_t>(b) * Hp + y + 1) * Wp + x + 1;
+      T ov[6];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        float v = acc[i][j] + bias[j];
+        if (p.epi.residual) v += to_f<T>(static_cast<const T*>(p.epi.residual)[pix * p.ntot + oc0 + j]);
+        ov[j] = from_f<T>(v);
+      }
+      const int wy = halo_wrap(y, p.H), wx = halo_wrap(x, p.W);
+      T* ob = static_cast<T*>(p.epi.out);
+#pragma unroll
+      for (int cy = 0; cy < 2; ++cy) {
+        if (cy && !wy) continue;
+#pragma unroll
+        for (int cx = 0; cx < 2; ++cx) {
+          if (cx && !wx) continue;
+          T* o = ob + (pix + static_cast<long long>(cy ? wy : 0) * Wp + (cx ? wx : 0)) * p.epi.ldo + oc0;
+#pragma unroll
+          for (int j = 0; j < 6; ++j) o[j] = ov[j];
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + ty * 4 + i;
+      T* o = static_cast<T*>(p.epi.out) + static_cast<size_t>(m) * p.epi.ldo + oc0;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) o[j] = from_f<T>(acc[i][j] + bias[j]);
+    }
+  }
+}
+
+void conv_simt_pack_weights(const ConvGeom& g, const float* w, float* out, bool round_bf16) {
+  const int k = g.ksize;
+  int cin = 0;
+  for (int s = 0; s < g.nsrc; ++s) cin += g.csrc[s];
+  for (int ky = 0; ky < k; ++ky)
+    for (int kx = 0; kx < k; ++kx)
+      for (int c = 0; c < cin; ++c)
+        for (int n = 0; n < g.ntot; ++n) {
+          float v = w[((static_cast<size_t>(n) * cin + c) * k + ky) * k + kx];
+          if (round_bf16) v = __bfloat162float(__float2bfloat16(v));
+          out[((static_cast<size_t>(ky) * k + kx) * cin + c) * g.ntot + n] = v;
+        }
+}
+
+template <typename T>
+int launch_conv_simt(const ConvGeom& g, const T* src0, const T* src1, const float* wpacked, int epi, const EpiArgs& ea,
+                     cudaStream_t st) {
+  if (g.B <= 0) return TCS_OK;
+  SimtConvParams p;
+  p.B = g.B; p.H = g.H; p.W = g.W; p.HW = g.H * g.W;
+  p.ksize = g.ksize; p.stride = g.stride; p.nsrc = g.nsrc;
+  p.cin_tot = 0;
+  const int conv_pad = g.ksize == 1 ? 0 : 1;
+  for (int s = 0; s < 2; ++s) {
+    const int si = s < g.nsrc ? s : 0;
+    p.csrc[s] = g.csrc[si];
+    p.Hin[s] = g.H * g.stride + 2 * g.in_pad[si];
+    p.Win[s] = g.W * g.stride + 2 * g.in_pad[si];
+    p.base_off[s] = g.in_pad[si] - conv_pad;
+    if (p.base_off[s] < 0) return fail(TCS_ERR_BAD_ARGUMENT, "conv_simt: a 3x3/4x4 conv needs a padded source");
+    if (s < g.nsrc) p.cin_tot += g.csrc[s];
+    if (g.csrc[si] % 32) return fail(TCS_ERR_UNSUPPORTED, "conv_simt: C_in must be a multiple of 32");
+  }
+  p.ntot = g.ntot;
+  p.epi = ea;
+  if (p.HW % 64 || g.ntot % 96) return fail(TCS_ERR_UNSUPPORTED, "conv_simt: needs HW%64==0 and C_out%96==0");
+  dim3 grid(g.B * p.HW / 64, g.ntot / 96);
+  switch (epi) {
+    case EPI_RAW_STATS: conv_simt_kernel<T, EPI_RAW_STATS><<<grid, 256, 0, st>>>(src0, src1, wpacked, p); break;
+    case EPI_PADDED: conv_simt_kernel<T, EPI_PADDED><<<grid, 256, 0, st>>>(src0, src1, wpacked, p); break;
+    case EPI_PLAIN: conv_simt_kernel<T, EPI_PLAIN><<<grid, 256, 0, st>>>(src0, src1, wpacked, p); break;
+    default: return fail(TCS_ERR_BAD_ARGUMENT, "conv_simt: bad epilogue");
+  }
+  TCS_CUDA(cudaGetLastError());
+  return TCS_OK;
+}
+template int launch_conv_simt<float>(const ConvGeom&, const float*, const float*, const float*, int, const EpiArgs&, cudaStream_t);
+template int launch_conv_simt<__nv_bfloat16>(const ConvGeom&, const __nv_bfloat16*, const __nv_bfloat16*, const float*, int, const EpiArgs&, cudaStream_t);
+
+// ------------------------------------------------------------------------------------------
+// out conv 96 -> 1 (3x3 circular) + CFG combine  (sde_score_model.py:225,266 and :418-423)
+// 8 lanes per output pixel, 12 channels per lane; 32 pixels per 256-thread block
+// ------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ void load12(const T* p, float* f);
+template <> __device__ __forceinline__ void load12<float>(const float* p, float* f) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float4 v = *reinterpret_cast<const float4*>(p + 4 * i);
+    f[4 * i] = v.x; f[4 * i + 1] = v.y; f[4 * i + 2] = v.z; f[4 * i + 3] = v.w;
+  }
+}
+template <> __device__ __forceinline__ void load12<__nv_bfloat16>(const __nv_bfloat16* p, float* f) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p + 4 * i);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+    const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+    f[4 * i] = a.x; f[4 * i + 1] = a.y; f[4 * i + 2] = c.x; f[4 * i + 3] = c.y;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) out_conv_kernel(const T* __restrict__ act, const float* __restrict__ w, float bias,
+                                                      int dup, float guidance, float* __restrict__ eps) {
+  __shared__ float ws[9 * 96];
+  for (int e = threadIdx.x; e < 9 * 96; e += 256) ws[e] = w[e];
+  __syncthreads();
+  const int sl = threadIdx.x & 7;                       // channel slice
+  const int pix = blockIdx.x * 32 + (threadIdx.x >> 3); // pixel within the whole launch
+  const int i = pix >> 12, rem = pix & 4095, y = rem >> 6, x = rem & 63;
+  constexpr int Wp = IMG + 2;
+  float e[2] = {0.f, 0.f};
+  for (int u = 0; u < dup; ++u) {
+    const T* img = act + static_cast<size_t>(i * dup + u) * Wp * Wp * 96 + sl * 12;
+    float a = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        float f[12];
+        load12<T>(img + (static_cast<size_t>(y + ky) * Wp + x + kx) * 96, f);
+        const float* wk = ws + (ky * 3 + kx) * 96 + sl * 12;
+#pragma unroll
+        for (int c = 0; c < 12; ++c) a = fmaf(f[c], wk[c], a);
+      }
+    a += __shfl_xor_sync(0xffffffffu, a, 4);
+    a += __shfl_xor_sync(0xffffffffu, a, 2);
+    a += __shfl_xor_sync(0xffffffffu, a, 1);
+    e[u] = a + bias;
+  }
+  if (sl == 0) eps[pix] = dup == 2 ? e[1] + guidance * (e[0] - e[1]) : e[0];
+}
+template <typename T>
+int launch_out_conv(const T* act, const float* w, float bias, int n, int dup, float guidance, float* eps,
+                    cudaStream_t st) {
+  if (n <= 0) return TCS_OK;
+  out_conv_kernel<T><<<n * (IMG_PIX / 32), 256, 0, st>>>(act, w, bias, dup, guidance, eps);
+  TCS_CUDA(cudaGetLastError());
+  return TCS_OK;
+}
+template int launch_out_conv<float>(const float*, const float*, float, int, int, float, float*, cudaStream_t);
+template int launch_out_conv<__nv_bfloat16>(const __nv_bfloat16*, const float*, float, int, int, float, float*, cudaStream_t);
+
+// ------------------------------------------------------------------------------------------
+// layout helpers
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) pad_from_plain_kernel(const float* __restrict__ in, int H, int W, int C, int pad,
+                                                            T* __restrict__ out, long long total) {
+  const long long e = blockIdx.x * 256LL + threadIdx.x;
+  if (e >= total) return;
+  const int c = static_cast<int>(e % C);
+  long long r = e / C;
+  const int Wp = W + 2 * pad, Hp = H + 2 * pad;
+  const int px = static_cast<int>(r % Wp); r /= Wp;
+  const int py = static_cast<int>(r % Hp);
+  const long long b = r / Hp;
+  const int y = (py - pad + H) % H, x = (px - pad + W) % W;
+  out[e] = from_f<T>(in[((b * H + y) * W + x) * C + c]);
+}
+template <typename T>
+int launch_pad_from_plain(const float* in, int B, int H, int W, int C, int pad, T* out, cudaStream_t st) {
+  const long long total = static_cast<long long>(B) * (H + 2 * pad) * (W + 2 * pad) * C;
+  if (total <= 0) return TCS_OK;
+  pad_from_plain_kernel<T><<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(in, H, W, C, pad, out, total);
+  TCS_CUDA(cudaGetLastError());
+  return TCS_OK;
+}
+template int launch_pad_from_plain<float>(const float*, int, int, int, int, int, float*, cudaStream_t);
+template int launch_pad_from_plain<__nv_bfloat16>(const float*, int, int, int, int, int, __nv_bfloat16*, cudaStream_t);
+
+template <typename T>
+__global__ void __launch_bounds__(256) unpad_kernel(const T* __restrict__ in, int H, int W, int C, int pad,
+                                                   float* __restrict__ out, long long total) {
+  const long long e = blockIdx.x * 256LL + threadIdx.x;
+  if (e >= total) return;
+  const int c = static_cast<int>(e % C);
+  long long r = e / C;
+  const int x = static_cast<int>(r % W); r /= W;
+  const int y = static_cast<int>(r % H);
+  const long long b = r / H;
+  out[e] = to_f<T>(in[((b * (H + 2 * pad) + y + pad) * (W + 2 * pad) + x + pad) * C + c]);
+}
+template <typename T>
+int launch_unpad_to_f32(const T* in, int B, int H, int W, int C, int pad, float* out, cudaStream_t st) {
+  const long long total = static_cast<long long>(B) * H * W * C;
+  if (total <= 0) return TCS_OK;
+  unpad_kernel<T><<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(in, H, W, C, pad, out, total);
+  TCS_CUDA(cudaGetLastError());
+  return TCS_OK;
+}
+template int launch_unpad_to_f32<float>(const float*, int, int, int, int, int, float*, cudaStream_t);
+template int launch_unpad_to_f32<__nv_bfloat16>(const __nv_bfloat16*, int, int, int, int, int, float*, cudaStream_t);
+
+}  // namespace tcs
