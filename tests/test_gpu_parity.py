@@ -44,7 +44,7 @@ def test_conv_layer(case, precision, engine):
         tol = 2e-5 if (precision == "fp32" or epi == 0) else 6e-3  # epi 1/2 round the output to bf16
         err = pu.rel_l2(out, ref)
         assert err < tol, (case, precision, engine, epi, err)
-        if epi == 0:
+        if epi == 0 and cout in (96, 192):  # GroupNorm only ever follows 96/192-channel convs
             cpg = cout // 8
             r = ref.reshape(B, -1, 8, cpg)
             want = torch.stack([r.sum(dim=(1, 3)), (r * r).sum(dim=(1, 3))], dim=-1)

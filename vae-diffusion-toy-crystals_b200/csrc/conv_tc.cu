@@ -18,6 +18,7 @@
 // * persistent grid: one CTA per SM looping over M tiles.
 #include "conv_tc.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -464,6 +465,7 @@ int conv_tc_launch(const ConvTcPlan& pl, cudaStream_t st) {
   if (pl.N == NN && pl.epi == EE && pl.msub == MM) return launch_t<NN, EE, MM>(pl, st);
   TCS_TC_CASE(96, EPI_RAW_STATS, 1)
   TCS_TC_CASE(96, EPI_PADDED, 1)
+  TCS_TC_CASE(96, EPI_PLAIN, 1)
   TCS_TC_CASE(192, EPI_RAW_STATS, 1)
   TCS_TC_CASE(192, EPI_PADDED, 1)
   TCS_TC_CASE(192, EPI_PLAIN, 1)
@@ -485,7 +487,13 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, con
   pl.N = (g.ntot % 192 == 0) ? 192 : 96;
   if (g.ntot % pl.N) return fail(TCS_ERR_UNSUPPORTED, "conv_tc: C_out must be a multiple of 96");
   pl.epi = epi;
-  pl.msub = 1;
+  {
+    // two 128-pixel sub-tiles per CTA tile share every weight (B) stage: halves the B traffic per MAC.
+    // Only where two fp32 accumulator sets of MSUB*N columns still double-buffer in TMEM (N = 96).
+    const char* e = getenv("TCS_MSUB");
+    const int want = e ? atoi(e) : 2;
+    pl.msub = (want == 2 && pl.N == 96 && epi != EPI_PLAIN && (g.H % (2 * (128 / g.W)) == 0)) ? 2 : 1;
+  }
   stage_shape(g, &p.T, &p.KYG, &p.KW);
   p.H = g.H; p.W = g.W; p.Rt = 128 / g.W;
   p.stride = g.stride;

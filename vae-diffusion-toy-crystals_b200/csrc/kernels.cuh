@@ -37,7 +37,8 @@ constexpr int FIRST_CONV_SLOTS = 32;
 // in: fp32 raw plain [B,H,W,C] (in_padded=0) or padded T (in_padded=1); partials [B][slots][8][2]
 template <typename T>
 int launch_gn_apply(const void* in, int in_padded, const float* partials, int slots, const float* gamma,
-                    const float* beta, int B, int H, int W, int C, int silu, T* out_padded, cudaStream_t st);
+                    const float* beta, int B, int H, int W, int C, int silu, T* out_padded, float2* stats_scratch /*[B][8]*/,
+                    cudaStream_t st);
 // statistics of a padded T tensor -> partials [B][1][8][2]
 template <typename T>
 int launch_gn_stats(const T* in_padded, int B, int H, int W, int C, float* partials, cudaStream_t st);

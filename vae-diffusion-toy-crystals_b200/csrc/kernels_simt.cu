@@ -111,66 +111,91 @@ int launch_first_conv(const float* x, const float* w9, const float* tvec, int tv
 
 // ------------------------------------------------------------------------------------------
 // GroupNorm statistics from partial sums (fp64 combine, fixed order -> deterministic)
+// one block per image: stats[b][g] = (mean, rstd)
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void gn_finalize(const float* __restrict__ part, int slots, double count, float* s_mean,
-                                            float* s_rstd) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp < GN_GROUPS) {
-    double s = 0.0, q = 0.0;
-    for (int k = lane; k < slots; k += 32) {
-      s += static_cast<double>(part[k * 16 + 2 * warp]);
-      q += static_cast<double>(part[k * 16 + 2 * warp + 1]);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      s += __shfl_xor_sync(0xffffffffu, s, o);
-      q += __shfl_xor_sync(0xffffffffu, q, o);
-    }
-    if (lane == 0) {
-      const double mean = s / count;
-      double var = q / count - mean * mean;
-      var = var < 0.0 ? 0.0 : var;
-      s_mean[warp] = static_cast<float>(mean);
-      s_rstd[warp] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(GN_EPS)));
-    }
+__global__ void __launch_bounds__(256) gn_finalize_kernel(const float* __restrict__ partials, int slots, double count,
+                                                         float2* __restrict__ stats) {
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* part = partials + static_cast<size_t>(b) * slots * 16;
+  double s = 0.0, q = 0.0;
+  for (int k = lane; k < slots; k += 32) {
+    s += static_cast<double>(part[k * 16 + 2 * warp]);
+    q += static_cast<double>(part[k * 16 + 2 * warp + 1]);
   }
-  __syncthreads();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (lane == 0) {
+    const double mean = s / count;
+    double var = q / count - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    stats[b * GN_GROUPS + warp] = make_float2(static_cast<float>(mean),
+                                              static_cast<float>(1.0 / sqrt(var + static_cast<double>(GN_EPS))));
+  }
 }
 
+template <bool FAST> __device__ __forceinline__ float silu_f(float v) {
+  if constexpr (FAST) return __fdividef(v, 1.0f + __expf(-v));
+  return v / (1.0f + expf(-v));
+}
+
+// y = (x - mean) * rstd * gamma + beta (+SiLU) -> padded T with circular halo.  4 x 8 channels per thread,
+// all loads issued before the math.
 template <typename T, bool IN_PADDED, bool SILU>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ in_, const float* __restrict__ partials,
-                                                      int slots, const float* __restrict__ gamma,
-                                                      const float* __restrict__ beta, int H, int W, int C,
-                                                      T* __restrict__ out) {
+__global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ in_, const float2* __restrict__ stats,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      int H, int W, int C, T* __restrict__ out) {
+  constexpr bool FAST = sizeof(T) == 2;
   __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
   const int b = blockIdx.y;
-  gn_finalize(partials + static_cast<size_t>(b) * slots * 16, slots, static_cast<double>(H) * W * (C / GN_GROUPS),
-              s_mean, s_rstd);
+  if (threadIdx.x < GN_GROUPS) {
+    const float2 st = stats[b * GN_GROUPS + threadIdx.x];
+    s_mean[threadIdx.x] = st.x;
+    s_rstd[threadIdx.x] = st.y;
+  }
+  __syncthreads();
   const int cv = C / 8, cpg = C / GN_GROUPS;
   const int nvec = H * W * cv;
   const int Wp = W + 2, Hp = H + 2;
-  for (int e = blockIdx.x * 256 + threadIdx.x; e < nvec; e += gridDim.x * 256) {
+  const int e0 = blockIdx.x * 1024 + threadIdx.x;
+  float v[4][8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int e = e0 + k * 256;
+    if (e >= nvec) continue;
     const int pix = e / cv, c = (e - pix * cv) * 8;
-    const int y = pix / W, x = pix - y * W;
-    float v[8];
     if constexpr (IN_PADDED) {
+      const int y = pix / W, x = pix - y * W;
       Vec8<T> iv;
       iv.load(static_cast<const T*>(in_) + ((static_cast<size_t>(b) * Hp + y + 1) * Wp + x + 1) * C + c);
-      iv.get(v);
+      iv.get(v[k]);
     } else {
       Vec8<float> iv;
       iv.load(static_cast<const float*>(in_) + (static_cast<size_t>(b) * H * W + pix) * C + c);
-      iv.get(v);
+      iv.get(v[k]);
     }
+  }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int g = (c + k) / cpg;
-      float yv = (v[k] - s_mean[g]) * s_rstd[g] * __ldg(gamma + c + k) + __ldg(beta + c + k);
-      if constexpr (SILU) yv = yv / (1.0f + expf(-yv));
-      v[k] = yv;
+  for (int k = 0; k < 4; ++k) {
+    const int e = e0 + k * 256;
+    if (e >= nvec) continue;
+    const int pix = e / cv, c = (e - pix * cv) * 8;
+    const int y = pix / W, x = pix - y * W;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+    const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (c + j) / cpg;
+      float yv = (v[k][j] - s_mean[g]) * s_rstd[g] * gm[j] + bt[j];
+      if constexpr (SILU) yv = silu_f<FAST>(yv);
+      v[k][j] = yv;
     }
     Vec8<T> ov;
-    ov.set(v);
+    ov.set(v[k]);
     const int wy = halo_wrap(y, H), wx = halo_wrap(x, W);
     const size_t base = (static_cast<size_t>(b) * Hp + y + 1) * Wp + x + 1;
     ov.store(out + base * C + c);
@@ -182,25 +207,24 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ 
 
 template <typename T>
 int launch_gn_apply(const void* in, int in_padded, const float* partials, int slots, const float* gamma,
-                    const float* beta, int B, int H, int W, int C, int silu, T* out, cudaStream_t st) {
+                    const float* beta, int B, int H, int W, int C, int silu, T* out, float2* stats, cudaStream_t st) {
   if (B <= 0) return TCS_OK;
+  gn_finalize_kernel<<<B, 256, 0, st>>>(partials, slots, static_cast<double>(H) * W * (C / GN_GROUPS), stats);
   const int nvec = H * W * (C / 8);
-  int gx = (nvec + 256 * 4 - 1) / (256 * 4);
-  if (gx < 1) gx = 1;
-  dim3 grid(gx, B);
+  dim3 grid((nvec + 1023) / 1024, B);
   if (in_padded && !silu)
-    gn_apply_kernel<T, true, false><<<grid, 256, 0, st>>>(in, partials, slots, gamma, beta, H, W, C, out);
+    gn_apply_kernel<T, true, false><<<grid, 256, 0, st>>>(in, stats, gamma, beta, H, W, C, out);
   else if (!in_padded && silu)
-    gn_apply_kernel<T, false, true><<<grid, 256, 0, st>>>(in, partials, slots, gamma, beta, H, W, C, out);
+    gn_apply_kernel<T, false, true><<<grid, 256, 0, st>>>(in, stats, gamma, beta, H, W, C, out);
   else if (!in_padded && !silu)
-    gn_apply_kernel<T, false, false><<<grid, 256, 0, st>>>(in, partials, slots, gamma, beta, H, W, C, out);
+    gn_apply_kernel<T, false, false><<<grid, 256, 0, st>>>(in, stats, gamma, beta, H, W, C, out);
   else
-    gn_apply_kernel<T, true, true><<<grid, 256, 0, st>>>(in, partials, slots, gamma, beta, H, W, C, out);
+    gn_apply_kernel<T, true, true><<<grid, 256, 0, st>>>(in, stats, gamma, beta, H, W, C, out);
   TCS_CUDA(cudaGetLastError());
   return TCS_OK;
 }
-template int launch_gn_apply<float>(const void*, int, const float*, int, const float*, const float*, int, int, int, int, int, float*, cudaStream_t);
-template int launch_gn_apply<__nv_bfloat16>(const void*, int, const float*, int, const float*, const float*, int, int, int, int, int, __nv_bfloat16*, cudaStream_t);
+template int launch_gn_apply<float>(const void*, int, const float*, int, const float*, const float*, int, int, int, int, int, float*, float2*, cudaStream_t);
+template int launch_gn_apply<__nv_bfloat16>(const void*, int, const float*, int, const float*, const float*, int, int, int, int, int, __nv_bfloat16*, float2*, cudaStream_t);
 
 // statistics of a padded T tensor (one block per image; thread = channel) -> one partial slot
 template <typename T>

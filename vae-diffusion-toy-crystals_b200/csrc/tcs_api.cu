@@ -131,7 +131,7 @@ struct tcs_handle {
 
   // workspace (sized for `chunk` images)
   int chunk = 0;
-  DevBuf raw64, raw32, raw16, partials;
+  DevBuf raw64, raw32, raw16, partials, gnstats;
   DevBuf p64_h1, p64_a, p64_b;
   DevBuf p32_96a, p32_96b, p32_192a, p32_192h2, p32_192b;
   DevBuf p16_a, p16_b, p16_c, qkv, atty;
@@ -212,6 +212,7 @@ static int alloc_workspace(tcs_handle* h) {
   TCS_CHECK(h->raw32.ensure(MB * 1024 * 192 * 4));
   TCS_CHECK(h->raw16.ensure(MB * 256 * 192 * 4));
   TCS_CHECK(h->partials.ensure(MB * 128 * 16 * 4));
+  TCS_CHECK(h->gnstats.ensure(MB * 8 * 8));
   const size_t P64 = MB * 66 * 66 * 96 * e, P32a = MB * 34 * 34 * 96 * e, P32b = MB * 34 * 34 * 192 * e,
                P16 = MB * 18 * 18 * 192 * e;
   TCS_CHECK(h->p64_h1.ensure(P64)); TCS_CHECK(h->p64_a.ensure(P64)); TCS_CHECK(h->p64_b.ensure(P64));
@@ -319,7 +320,7 @@ static int forward_chunk(tcs_handle* h, const PassArgs& a, cudaStream_t st, TapR
   };
 #define TAP(kind, p, H, W, C) { int _r = tapout(kind, p, H, W, C); if (_r != 0) return _r < 0 ? _r : TCS_OK; }
 #define GN(key, raw, slots, res, C, out) \
-  { ++h->launches; TCS_CHECK(launch_gn_apply<T>(raw, 0, part, slots, gnw(key), gnb(key), B, res, res, C, 1, out, st)); }
+  { h->launches += 2; TCS_CHECK(launch_gn_apply<T>(raw, 0, part, slots, gnw(key), gnb(key), B, res, res, C, 1, out, h->gnstats.as<float2>(), st)); }
 
   // ---- down1 -------------------------------------------------------------------------------
   ++h->launches;
@@ -356,9 +357,9 @@ static int forward_chunk(tcs_handle* h, const PassArgs& a, cudaStream_t st, TapR
   TAP(1, h->p16_a.p, 16, 16, 192);
   ++h->launches;
   TCS_CHECK(launch_gn_stats<T>(h->p16_a.as<T>(), B, 16, 16, 192, part, st));
-  ++h->launches;
+  h->launches += 2;
   TCS_CHECK(launch_gn_apply<T>(h->p16_a.p, 1, part, 1, gnw("attn.norm"), gnb("attn.norm"), B, 16, 16, 192, 0,
-                               h->p16_b.as<T>(), st));
+                               h->p16_b.as<T>(), h->gnstats.as<float2>(), st));
   TCS_CHECK(run_conv<T>(h, C_QKV, B, st));
   TAP(2, h->qkv.p, 16, 16, 576);
   ++h->launches;
