@@ -80,6 +80,18 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N_) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -143,6 +155,8 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 
 constexpr int TC_THREADS = 192;
 constexpr int MAX_STAGES = 8;
+constexpr uint32_t EPI_SLAB_BYTES = 4 * 2 * 4096;   // per-warp double-buffered 32x32 fp32 slabs
+constexpr uint32_t EPI_BIAS_BYTES = 576 * 4;
 
 struct __align__(8) TcBarriers {
   uint64_t full[MAX_STAGES];
@@ -155,7 +169,8 @@ struct __align__(8) TcBarriers {
 template <int N, int EPI, int MSUB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-               const __grid_constant__ CUtensorMap mapW, const ConvTcParams p) {
+               const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapO,
+               const ConvTcParams p) {
   constexpr int ACC_STRIDE = (N * MSUB <= 128) ? 128 : 256;  // TMEM columns per accumulator stage
   static_assert(N * MSUB <= 256, "accumulator does not fit a double-buffered TMEM stage");
   constexpr int CPG = 0;  // (placeholder to keep the template list short)
@@ -168,11 +183,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const int n_tiles = p.n_mtiles * p.n_ntiles;
+  // after the operand ring: 4 epilogue warps x 2 x 4 KB output slabs (TMA-store staging), then the bias
+  const uint32_t slab_base = smem_base + p.nstage * p.stage_bytes;
+  float* bias_s = reinterpret_cast<float*>(smem_raw + (slab_base - ptx::smem_u32(smem_raw)) + EPI_SLAB_BYTES);
+  for (int i = threadIdx.x; i < p.ntot; i += TC_THREADS) bias_s[i] = p.epi.bias[i];
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&mapA0);
     ptx::prefetch_tmap(&mapA1);
     ptx::prefetch_tmap(&mapW);
+    if (EPI == EPI_RAW_STATS) ptx::prefetch_tmap(&mapO);
     for (int s = 0; s < p.nstage; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bars.full[s]), 1);
       ptx::mbar_init(ptx::smem_u32(&bars.empty[s]), 1);
@@ -257,7 +277,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;
     const int HW = p.H * p.W;
-    uint32_t acc = 0, acc_phase = 0;
+    uint32_t acc = 0, acc_phase = 0, slab_buf = 0;
+    (void)slab_buf;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int mt = tile / p.n_ntiles, nt = tile - mt * p.n_ntiles;
       const int n_off = nt * N;
@@ -272,21 +293,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           float gs[8], gq[8];
 #pragma unroll
           for (int g = 0; g < 8; ++g) gs[g] = gq[g] = 0.f;
-          float* orow = static_cast<float*>(p.epi.out) + static_cast<size_t>(m) * p.epi.ldo + n_off;
+          // fp32 tile -> swizzled 32x32 slab in shared memory -> TMA store (full 128 B lines, no LSU)
+          const uint32_t slab = slab_base + static_cast<uint32_t>(warp - 2) * 8192;
+          const int m_base = (mt * MSUB + sub) * 128 + q * 32;
 #pragma unroll
           for (int c0 = 0; c0 < N; c0 += 32) {
             float v[32];
             ptx::tmem_ld32(taddr + c0, v);
             ptx::tmem_ld_wait();
 #pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n_off + c0 + i);
+              v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+            }
+#pragma unroll
             for (int i = 0; i < 32; ++i) {
-              v[i] += __ldg(p.epi.bias + n_off + c0 + i);
               gs[(c0 + i) / CPGN] += v[i];
               gq[(c0 + i) / CPGN] += v[i] * v[i];
             }
+            if (lane == 0) ptx::bulk_wait_read<1>();   // the slab written two chunks ago has been read
+            __syncwarp();
+            const uint32_t dst = slab + slab_buf * 4096 + lane * 128;
 #pragma unroll
-            for (int i = 0; i < 32; i += 4)
-              *reinterpret_cast<float4*>(orow + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            for (int j = 0; j < 8; ++j)
+              ptx::st_shared_v4(dst + ((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              ptx::tma_store_2d(&mapO, slab + slab_buf * 4096, n_off + c0, m_base);
+              ptx::bulk_commit();
+            }
+            slab_buf ^= 1;
           }
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
@@ -334,8 +371,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             }
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-              h2[i] = __floats2bfloat162_rn(v[2 * i] + __ldg(p.epi.bias + n_off + c0 + 2 * i),
-                                            v[2 * i + 1] + __ldg(p.epi.bias + n_off + c0 + 2 * i + 1));
+              h2[i] = __floats2bfloat162_rn(v[2 * i] + bias_s[n_off + c0 + 2 * i],
+                                            v[2 * i + 1] + bias_s[n_off + c0 + 2 * i + 1]);
 #pragma unroll
             for (int cy = 0; cy < 2; ++cy) {
               if (cy == 1 && wy == 0) continue;
@@ -360,8 +397,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(pk);
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-              h2[i] = __floats2bfloat162_rn(v[2 * i] + __ldg(p.epi.bias + n_off + c0 + 2 * i),
-                                            v[2 * i + 1] + __ldg(p.epi.bias + n_off + c0 + 2 * i + 1));
+              h2[i] = __floats2bfloat162_rn(v[2 * i] + bias_s[n_off + c0 + 2 * i],
+                                            v[2 * i + 1] + bias_s[n_off + c0 + 2 * i + 1]);
             uint4* dst = reinterpret_cast<uint4*>(orow + c0);
 #pragma unroll
             for (int i = 0; i < 4; ++i) dst[i] = pk[i];
@@ -373,6 +410,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars.tmem_empty[acc]));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (EPI == EPI_RAW_STATS && lane == 0) ptx::bulk_wait_all();   // staged stores have left shared memory
   }
 
   ptx::tc_fence_before();
@@ -454,7 +492,7 @@ static int launch_t(const ConvTcPlan& pl, cudaStream_t st) {
     TCS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
     attr_done = true;
   }
-  kern<<<pl.grid, TC_THREADS, pl.smem, st>>>(pl.mapA[0], pl.mapA[1], pl.mapW, pl.p);
+  kern<<<pl.grid, TC_THREADS, pl.smem, st>>>(pl.mapA[0], pl.mapA[1], pl.mapW, pl.mapO, pl.p);
   TCS_CUDA(cudaGetLastError());
   return TCS_OK;
 }
@@ -506,11 +544,11 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, con
   p.kstages = conv_tc_kstages(g);
   p.a_bytes = static_cast<uint32_t>(p.WR) * g.W * 64;
   p.stage_bytes = (p.a_bytes + p.T * pl.N * 64 + 1023u) & ~1023u;
-  const size_t budget = 227 * 1024 - 2048 - 1024;
+  const size_t budget = 227 * 1024 - 2048 - 1024 - EPI_SLAB_BYTES - EPI_BIAS_BYTES;
   p.nstage = static_cast<int>(budget / p.stage_bytes);
   if (p.nstage > MAX_STAGES) p.nstage = MAX_STAGES;
   if (p.nstage < 2) return fail(TCS_ERR_UNSUPPORTED, "conv_tc: stage does not fit shared memory twice");
-  pl.smem = static_cast<size_t>(p.nstage) * p.stage_bytes + 1024;
+  pl.smem = static_cast<size_t>(p.nstage) * p.stage_bytes + 1024 + EPI_SLAB_BYTES + EPI_BIAS_BYTES;
   p.epi = ea;
   const int tiles = p.n_mtiles * p.n_ntiles;
   pl.grid = tiles < sm_count ? tiles : sm_count;
@@ -544,6 +582,17 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, con
                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(TCS_ERR_CUDA, "cuTensorMapEncodeTiled(W) failed: " + std::to_string(r));
+  }
+  pl.mapO = pl.mapW;
+  if (epi == EPI_RAW_STATS) {   // fp32 [M, ldo] output written by TMA store in 32x32 boxes
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(ea.ldo), static_cast<cuuint64_t>(g.B) * g.H * g.W};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(ea.ldo) * 4};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&pl.mapO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ea.out, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(TCS_ERR_CUDA, "cuTensorMapEncodeTiled(O) failed: " + std::to_string(r));
   }
   pl.valid = true;
   return TCS_OK;

@@ -24,6 +24,7 @@ struct ConvTcParams {
 struct ConvTcPlan {
   CUtensorMap mapA[2];
   CUtensorMap mapW;
+  CUtensorMap mapO;   // EPI_RAW_STATS: fp32 output, TMA-stored
   ConvTcParams p;
   int N;       // N tile (96 or 192)
   int epi;     // Epilogue

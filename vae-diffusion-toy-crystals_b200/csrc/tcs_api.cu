@@ -528,7 +528,7 @@ int tcs_create(tcs_handle** out, const tcs_config* cfg) {
   if (eng == TCS_ENGINE_AUTO) eng = h->bf16 ? TCS_ENGINE_TCGEN05 : TCS_ENGINE_SIMT;
   if (eng == TCS_ENGINE_TCGEN05 && !h->bf16) return fail(TCS_ERR_UNSUPPORTED, "the tcgen05 engine needs precision = bf16");
   h->use_tc = eng == TCS_ENGINE_TCGEN05;
-  h->chunk = cfg->chunk > 0 ? cfg->chunk : 64;
+  h->chunk = cfg->chunk > 0 ? cfg->chunk : 256;
   if (h->chunk % 2) h->chunk += 1;
   TCS_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   TCS_CUDA(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
