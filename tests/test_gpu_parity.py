@@ -65,7 +65,12 @@ def test_layers_against_oracle(precision, engine):
         orc.score_net(sd, pu.CFG, x.double(), t.double(), g["y_cat"], g["y_cont"].double(), taps)
     worst = 0.0
     for name, C, res in pu.LAYERS:
-        got = pu.debug_layer(m, name, x.cuda(), t.cuda(), g["y_cat"].cuda(), g["y_cont"].cuda(), C, res)
+        try:
+            got = pu.debug_layer(m, name, x.cuda(), t.cuda(), g["y_cat"].cuda(), g["y_cont"].cuda(), C, res)
+        except NotImplementedError:
+            # the tcgen05 engine fuses GroupNorm+SiLU into the conv: the raw conv output never exists
+            assert engine == "tcgen05" and name.endswith(".raw") and name != "down1.net.0.raw", name
+            continue
         want = taps[name].permute(0, 2, 3, 1)
         err = pu.rel_l2(got, want)
         worst = max(worst, err)

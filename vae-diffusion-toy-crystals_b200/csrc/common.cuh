@@ -41,7 +41,8 @@ int fail(int code, const std::string& msg);
 enum Epilogue : int {
   EPI_RAW_STATS = 0,  // fp32 [B,H,W,N] + bias, plus GroupNorm partial sums
   EPI_PADDED = 1,     // T [B,H+2,W+2,ldo] + bias (+ residual), halo written
-  EPI_PLAIN = 2       // T [M, ldo] + bias
+  EPI_PLAIN = 2,      // T [M, ldo] + bias
+  EPI_GN_FUSED = 3    // tcgen05 engine only: bias + GroupNorm + SiLU from TMEM -> padded bf16 (halo written)
 };
 
 struct ConvGeom {
@@ -62,6 +63,9 @@ struct EpiArgs {
   const void* residual;   // EPI_PADDED optional: padded T [B,H+2,W+2,ntot]
   int ldo;                // channel pitch of `out`
   int slots;              // partial slots per image
+  const float* gamma;     // EPI_GN_FUSED: GroupNorm affine [ntot]
+  const float* beta;
+  int* counters;          // EPI_GN_FUSED: per-image arrival counters [B], zeroed before the launch
 };
 
 // GroupNorm partial-sum slots per image written by each conv engine

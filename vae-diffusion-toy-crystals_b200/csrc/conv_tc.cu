@@ -157,6 +157,22 @@ constexpr int TC_THREADS = 192;
 constexpr int MAX_STAGES = 8;
 constexpr uint32_t EPI_SLAB_BYTES = 4 * 2 * 4096;   // per-warp double-buffered 32x32 fp32 slabs
 constexpr uint32_t EPI_BIAS_BYTES = 576 * 4;
+struct EpiFusedSmem {          // EPI_GN_FUSED scratch (lives right after the bias)
+  float gamma[192], beta[192], scale[192], shift[192];
+  float red[4][16];
+  float mean[8], rstd[8];
+};
+constexpr uint32_t EPI_FUSED_BYTES = sizeof(EpiFusedSmem);
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 struct __align__(8) TcBarriers {
   uint64_t full[MAX_STAGES];
@@ -187,6 +203,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   const uint32_t slab_base = smem_base + p.nstage * p.stage_bytes;
   float* bias_s = reinterpret_cast<float*>(smem_raw + (slab_base - ptx::smem_u32(smem_raw)) + EPI_SLAB_BYTES);
   for (int i = threadIdx.x; i < p.ntot; i += TC_THREADS) bias_s[i] = p.epi.bias[i];
+  EpiFusedSmem* fs = reinterpret_cast<EpiFusedSmem*>(reinterpret_cast<uint8_t*>(bias_s) + EPI_BIAS_BYTES);
+  if constexpr (EPI == EPI_GN_FUSED)
+    for (int i = threadIdx.x; i < N; i += TC_THREADS) { fs->gamma[i] = p.epi.gamma[i]; fs->beta[i] = p.epi.beta[i]; }
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&mapA0);
@@ -284,6 +303,129 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       const int n_off = nt * N;
       ptx::mbar_wait(ptx::smem_u32(&bars.tmem_full[acc]), acc_phase);
       ptx::tc_fence_after();
+      if constexpr (EPI == EPI_GN_FUSED) {
+        // ---- conv + bias + GroupNorm + SiLU without leaving TMEM --------------------------------------
+        // The G = tiles_per_img CTAs blockIdx % G == 0..G-1 of a group hold one image between them.
+        // pass 1: per-group sums of this CTA's pixels -> global; arrive on the image counter; wait for
+        // the other G-1 CTAs (they run the same image in lock step); pass 2: normalise from TMEM.
+        constexpr int CPGN = N / 8;
+        const int G = p.tiles_per_img;
+        const int img = mt / G;
+        float gs[8], gq[8];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) gs[g] = gq[g] = 0.f;
+#pragma unroll
+        for (int sub = 0; sub < MSUB; ++sub) {
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_STRIDE + sub * N;
+#pragma unroll
+          for (int c0 = 0; c0 < N; c0 += 32) {
+            float v[32];
+            ptx::tmem_ld32(taddr + c0, v);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float t = v[i] + bias_s[c0 + i];
+              gs[(c0 + i) / CPGN] += t;
+              gq[(c0 + i) / CPGN] += t * t;
+            }
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            gs[g] += __shfl_xor_sync(0xffffffffu, gs[g], o);
+            gq[g] += __shfl_xor_sync(0xffffffffu, gq[g], o);
+          }
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) { fs->red[warp - 2][2 * g] = gs[g]; fs->red[warp - 2][2 * g + 1] = gq[g]; }
+        }
+        epi_bar_sync();
+        if (warp == 2) {
+          float* gpart = p.epi.partials + static_cast<size_t>(mt) * 16;
+          if (lane < 16) {
+            __stcg(gpart + lane, (fs->red[0][lane] + fs->red[1][lane]) + (fs->red[2][lane] + fs->red[3][lane]));
+            __threadfence();
+          }
+          __syncwarp();
+          if (lane == 0) {
+            red_release_gpu_add(p.epi.counters + img, 1);
+            const long long t0 = clock64();
+            while (ld_acquire_gpu(p.epi.counters + img) < G) {
+              if (clock64() - t0 > 4000000000LL) __trap();
+            }
+          }
+          __syncwarp();
+          __threadfence();
+          if (lane < 8) {
+            const float* ip = p.epi.partials + static_cast<size_t>(img) * G * 16;
+            double sd = 0.0, qd = 0.0;
+            for (int k = 0; k < G; ++k) {
+              sd += static_cast<double>(__ldcg(ip + k * 16 + 2 * lane));
+              qd += static_cast<double>(__ldcg(ip + k * 16 + 2 * lane + 1));
+            }
+            const double cnt = static_cast<double>(HW) * CPGN;
+            const double mean = sd / cnt;
+            double var = qd / cnt - mean * mean;
+            var = var < 0.0 ? 0.0 : var;
+            fs->mean[lane] = static_cast<float>(mean);
+            fs->rstd[lane] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(GN_EPS)));
+          }
+        }
+        epi_bar_sync();
+        for (int c = threadIdx.x - 64; c < N; c += 128) {
+          const int g = c / CPGN;
+          const float sc = fs->rstd[g] * fs->gamma[c];
+          fs->scale[c] = sc;
+          fs->shift[c] = (bias_s[c] - fs->mean[g]) * sc + fs->beta[c];
+        }
+        epi_bar_sync();
+        const int Wp = p.W + 2, Hp = p.H + 2;
+        __nv_bfloat16* obase = static_cast<__nv_bfloat16*>(p.epi.out);
+#pragma unroll
+        for (int sub = 0; sub < MSUB; ++sub) {
+          const int m = (mt * MSUB + sub) * 128 + row;
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_STRIDE + sub * N;
+          const int rem = m - img * HW;
+          const int y = rem / p.W, x = rem - y * p.W;
+          const int wy = (y == 0) ? p.H : ((y == p.H - 1) ? -p.H : 0);
+          const int wx = (x == 0) ? p.W : ((x == p.W - 1) ? -p.W : 0);
+          const size_t pix = (static_cast<size_t>(img) * Hp + (y + 1)) * Wp + (x + 1);
+#pragma unroll
+          for (int c0 = 0; c0 < N; c0 += 32) {
+            float v[32];
+            ptx::tmem_ld32(taddr + c0, v);
+            ptx::tmem_ld_wait();
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 s4 = *reinterpret_cast<const float4*>(fs->scale + c0 + i);
+              const float4 h4 = *reinterpret_cast<const float4*>(fs->shift + c0 + i);
+              float y0 = fmaf(v[i], s4.x, h4.x), y1 = fmaf(v[i + 1], s4.y, h4.y);
+              float y2 = fmaf(v[i + 2], s4.z, h4.z), y3 = fmaf(v[i + 3], s4.w, h4.w);
+              y0 = __fdividef(y0, 1.0f + __expf(-y0)); y1 = __fdividef(y1, 1.0f + __expf(-y1));
+              y2 = __fdividef(y2, 1.0f + __expf(-y2)); y3 = __fdividef(y3, 1.0f + __expf(-y3));
+              const __nv_bfloat162 a = __floats2bfloat162_rn(y0, y1), b2 = __floats2bfloat162_rn(y2, y3);
+              pk[i / 2] = *reinterpret_cast<const uint32_t*>(&a);
+              pk[i / 2 + 1] = *reinterpret_cast<const uint32_t*>(&b2);
+            }
+#pragma unroll
+            for (int cy = 0; cy < 2; ++cy) {
+              if (cy == 1 && wy == 0) continue;
+#pragma unroll
+              for (int cx = 0; cx < 2; ++cx) {
+                if (cx == 1 && wx == 0) continue;
+                const size_t dp = pix + static_cast<size_t>(cy ? wy : 0) * Wp + (cx ? wx : 0);
+                uint4* dst = reinterpret_cast<uint4*>(obase + dp * p.epi.ldo + c0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+              }
+            }
+          }
+        }
+      } else {
 #pragma unroll
       for (int sub = 0; sub < MSUB; ++sub) {
         const int m = (mt * MSUB + sub) * 128 + row;  // global pixel index (b, y, x)
@@ -405,6 +547,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           }
         }
       }
+      }  // !EPI_GN_FUSED
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars.tmem_empty[acc]));
@@ -484,6 +627,13 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
+int conv_tc_grid(const ConvTcPlan& pl, int B, int sm_count) {
+  const int tiles = B * pl.p.tiles_per_img * pl.p.n_ntiles;
+  int grid = tiles < sm_count ? tiles : sm_count;
+  if (pl.epi == EPI_GN_FUSED) grid = grid / pl.p.tiles_per_img * pl.p.tiles_per_img;  // whole image groups only
+  return grid;
+}
+
 template <int N, int EPI, int MSUB>
 static int launch_t(const ConvTcPlan& pl, cudaStream_t st) {
   auto kern = conv_tc_kernel<N, EPI, MSUB>;
@@ -492,7 +642,19 @@ static int launch_t(const ConvTcPlan& pl, cudaStream_t st) {
     TCS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
     attr_done = true;
   }
-  kern<<<pl.grid, TC_THREADS, pl.smem, st>>>(pl.mapA[0], pl.mapA[1], pl.mapW, pl.mapO, pl.p);
+  if (EPI == EPI_GN_FUSED) {
+    // the CTAs of an image group wait on one another: zero the arrival counters, launch co-resident
+    TCS_CUDA(cudaMemsetAsync(pl.p.epi.counters, 0, sizeof(int) * (pl.p.n_mtiles / pl.p.tiles_per_img), st));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(pl.grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = pl.smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    TCS_CUDA(cudaLaunchKernelEx(&cfg, kern, pl.mapA[0], pl.mapA[1], pl.mapW, pl.mapO, pl.p));
+  } else {
+    kern<<<pl.grid, TC_THREADS, pl.smem, st>>>(pl.mapA[0], pl.mapA[1], pl.mapW, pl.mapO, pl.p);
+  }
   TCS_CUDA(cudaGetLastError());
   return TCS_OK;
 }
@@ -509,6 +671,9 @@ int conv_tc_launch(const ConvTcPlan& pl, cudaStream_t st) {
   TCS_TC_CASE(192, EPI_PLAIN, 1)
   TCS_TC_CASE(96, EPI_RAW_STATS, 2)
   TCS_TC_CASE(96, EPI_PADDED, 2)
+  TCS_TC_CASE(96, EPI_GN_FUSED, 1)
+  TCS_TC_CASE(96, EPI_GN_FUSED, 2)
+  TCS_TC_CASE(192, EPI_GN_FUSED, 1)
 #undef TCS_TC_CASE
   return fail(TCS_ERR_UNSUPPORTED, "conv_tc_launch: no kernel instance for this (N, epilogue, msub)");
 }
@@ -544,14 +709,17 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, con
   p.kstages = conv_tc_kstages(g);
   p.a_bytes = static_cast<uint32_t>(p.WR) * g.W * 64;
   p.stage_bytes = (p.a_bytes + p.T * pl.N * 64 + 1023u) & ~1023u;
-  const size_t budget = 227 * 1024 - 2048 - 1024 - EPI_SLAB_BYTES - EPI_BIAS_BYTES;
+  const size_t budget = 227 * 1024 - 2048 - 1024 - EPI_SLAB_BYTES - EPI_BIAS_BYTES - EPI_FUSED_BYTES;
   p.nstage = static_cast<int>(budget / p.stage_bytes);
   if (p.nstage > MAX_STAGES) p.nstage = MAX_STAGES;
   if (p.nstage < 2) return fail(TCS_ERR_UNSUPPORTED, "conv_tc: stage does not fit shared memory twice");
-  pl.smem = static_cast<size_t>(p.nstage) * p.stage_bytes + 1024 + EPI_SLAB_BYTES + EPI_BIAS_BYTES;
+  pl.smem = static_cast<size_t>(p.nstage) * p.stage_bytes + 1024 + EPI_SLAB_BYTES + EPI_BIAS_BYTES + EPI_FUSED_BYTES;
   p.epi = ea;
   const int tiles = p.n_mtiles * p.n_ntiles;
-  pl.grid = tiles < sm_count ? tiles : sm_count;
+  pl.grid = conv_tc_grid(pl, g.B, sm_count);
+  if (epi == EPI_GN_FUSED && (p.n_ntiles != 1 || pl.grid < p.tiles_per_img))
+    return fail(TCS_ERR_UNSUPPORTED, "conv_tc: fused GroupNorm needs one N tile and a whole image group on the GPU");
+  (void)tiles;
 
   const void* srcs[2] = {src0, src1};
   for (int s = 0; s < 2; ++s) {

@@ -44,5 +44,7 @@ void conv_tc_pack_weights(const ConvGeom& g, const float* w, __nv_bfloat16* out_
 int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, const void* src1,
                       const __nv_bfloat16* wpacked, int epi, const EpiArgs& ea, int sm_count);
 int conv_tc_launch(const ConvTcPlan& plan, cudaStream_t stream);
+// grid for B images (persistent: <= one CTA per SM; whole image groups for EPI_GN_FUSED)
+int conv_tc_grid(const ConvTcPlan& plan, int B, int sm_count);
 
 }  // namespace tcs

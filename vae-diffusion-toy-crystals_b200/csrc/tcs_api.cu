@@ -2,6 +2,7 @@
 // the two samplers and their CUDA-graph replay.  No PyTorch types, no CPU fallback.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -114,7 +115,7 @@ using namespace tcs;
 struct tcs_handle {
   tcs_config cfg;
   int sm_count = 148;
-  bool bf16 = false, use_tc = false;
+  bool bf16 = false, use_tc = false, fuse_gn = false;
   size_t esz = 4;
   cudaStream_t stream = nullptr;   // internal stream all work runs on
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
@@ -131,7 +132,7 @@ struct tcs_handle {
 
   // workspace (sized for `chunk` images)
   int chunk = 0;
-  DevBuf raw64, raw32, raw16, partials, gnstats;
+  DevBuf raw64, raw32, raw16, partials, gnstats, counters;
   DevBuf p64_h1, p64_a, p64_b;
   DevBuf p32_96a, p32_96b, p32_192a, p32_192h2, p32_192b;
   DevBuf p16_a, p16_b, p16_c, qkv, atty;
@@ -213,6 +214,7 @@ static int alloc_workspace(tcs_handle* h) {
   TCS_CHECK(h->raw16.ensure(MB * 256 * 192 * 4));
   TCS_CHECK(h->partials.ensure(MB * 128 * 16 * 4));
   TCS_CHECK(h->gnstats.ensure(MB * 8 * 8));
+  TCS_CHECK(h->counters.ensure(MB * 4));
   const size_t P64 = MB * 66 * 66 * 96 * e, P32a = MB * 34 * 34 * 96 * e, P32b = MB * 34 * 34 * 192 * e,
                P16 = MB * 18 * 18 * 192 * e;
   TCS_CHECK(h->p64_h1.ensure(P64)); TCS_CHECK(h->p64_a.ensure(P64)); TCS_CHECK(h->p64_b.ensure(P64));
@@ -225,25 +227,32 @@ static int alloc_workspace(tcs_handle* h) {
 }
 
 // (source buffers, destination, epilogue) of every GEMM conv, shared by both engines
-struct ConvWiring { const void *s0, *s1; void* out; int epi; const void* residual; int ldo; int in_pad; };
+struct ConvWiring { const void *s0, *s1; void* out; int epi; const void* residual; int ldo; int in_pad;
+                    const char* gn; void* act; };  // gn: GroupNorm that follows (or null); act: its padded output
 static ConvWiring wiring(tcs_handle* h, int id) {
+  ConvWiring w{};
   switch (id) {
-    case C_D1B: return {h->p64_a.p, nullptr, h->raw64.p, EPI_RAW_STATS, nullptr, 96, 1};
-    case C_DS1: return {h->p64_h1.p, nullptr, h->p32_96a.p, EPI_PADDED, nullptr, 96, 1};
-    case C_D2A: return {h->p32_96a.p, nullptr, h->raw32.p, EPI_RAW_STATS, nullptr, 192, 1};
-    case C_D2B: return {h->p32_192a.p, nullptr, h->raw32.p, EPI_RAW_STATS, nullptr, 192, 1};
-    case C_DS2: return {h->p32_192h2.p, nullptr, h->p16_a.p, EPI_PADDED, nullptr, 192, 1};
-    case C_MA: return {h->p16_a.p, nullptr, h->raw16.p, EPI_RAW_STATS, nullptr, 192, 1};
-    case C_MB: return {h->p16_b.p, nullptr, h->raw16.p, EPI_RAW_STATS, nullptr, 192, 1};
-    case C_QKV: return {h->p16_b.p, nullptr, h->qkv.p, EPI_PLAIN, nullptr, 576, 1};
-    case C_PROJ: return {h->atty.p, nullptr, h->p16_c.p, EPI_PADDED, h->p16_a.p, 192, 0};
-    case C_US2: return {h->p32_192a.p, nullptr, h->p32_192b.p, EPI_PADDED, nullptr, 192, 1};
-    case C_U2A: return {h->p32_192b.p, h->p32_192h2.p, h->raw32.p, EPI_RAW_STATS, nullptr, 96, 1};
-    case C_U2B: return {h->p32_96a.p, nullptr, h->raw32.p, EPI_RAW_STATS, nullptr, 96, 1};
-    case C_US1: return {h->p64_a.p, nullptr, h->p64_b.p, EPI_PADDED, nullptr, 96, 1};
-    case C_U1A: return {h->p64_b.p, h->p64_h1.p, h->raw64.p, EPI_RAW_STATS, nullptr, 96, 1};
-    default: return {h->p64_a.p, nullptr, h->raw64.p, EPI_RAW_STATS, nullptr, 96, 1};  // C_U1B
+    case C_D1B: w = {h->p64_a.p, nullptr, h->raw64.p, EPI_RAW_STATS, nullptr, 96, 1, "down1.net.4", h->p64_h1.p}; break;
+    case C_DS1: w = {h->p64_h1.p, nullptr, h->p32_96a.p, EPI_PADDED, nullptr, 96, 1, nullptr, nullptr}; break;
+    case C_D2A: w = {h->p32_96a.p, nullptr, h->raw32.p, EPI_RAW_STATS, nullptr, 192, 1, "down2.net.1", h->p32_192a.p}; break;
+    case C_D2B: w = {h->p32_192a.p, nullptr, h->raw32.p, EPI_RAW_STATS, nullptr, 192, 1, "down2.net.4", h->p32_192h2.p}; break;
+    case C_DS2: w = {h->p32_192h2.p, nullptr, h->p16_a.p, EPI_PADDED, nullptr, 192, 1, nullptr, nullptr}; break;
+    case C_MA: w = {h->p16_a.p, nullptr, h->raw16.p, EPI_RAW_STATS, nullptr, 192, 1, "mid.net.1", h->p16_b.p}; break;
+    case C_MB: w = {h->p16_b.p, nullptr, h->raw16.p, EPI_RAW_STATS, nullptr, 192, 1, "mid.net.4", h->p16_a.p}; break;
+    case C_QKV: w = {h->p16_b.p, nullptr, h->qkv.p, EPI_PLAIN, nullptr, 576, 1, nullptr, nullptr}; break;
+    case C_PROJ: w = {h->atty.p, nullptr, h->p16_c.p, EPI_PADDED, h->p16_a.p, 192, 0, nullptr, nullptr}; break;
+    case C_US2: w = {h->p32_192a.p, nullptr, h->p32_192b.p, EPI_PADDED, nullptr, 192, 1, nullptr, nullptr}; break;
+    case C_U2A: w = {h->p32_192b.p, h->p32_192h2.p, h->raw32.p, EPI_RAW_STATS, nullptr, 96, 1, "up2.net.1", h->p32_96a.p}; break;
+    case C_U2B: w = {h->p32_96a.p, nullptr, h->raw32.p, EPI_RAW_STATS, nullptr, 96, 1, "up2.net.4", h->p32_96b.p}; break;
+    case C_US1: w = {h->p64_a.p, nullptr, h->p64_b.p, EPI_PADDED, nullptr, 96, 1, nullptr, nullptr}; break;
+    case C_U1A: w = {h->p64_b.p, h->p64_h1.p, h->raw64.p, EPI_RAW_STATS, nullptr, 96, 1, "up1.net.1", h->p64_a.p}; break;
+    default: w = {h->p64_a.p, nullptr, h->raw64.p, EPI_RAW_STATS, nullptr, 96, 1, "up1.net.4", h->p64_b.p}; break;  // C_U1B
   }
+  if (h->fuse_gn && w.gn) {   // conv + GroupNorm + SiLU in one kernel: the padded activation is the output
+    w.out = w.act;
+    w.epi = EPI_GN_FUSED;
+  }
+  return w;
 }
 
 static int slots_of(tcs_handle* h, int id) {
@@ -260,6 +269,11 @@ static int build_plans(tcs_handle* h) {
     ea.bias = h->dw.at(std::string(kConv[id].key) + ".bias");
     ea.out = w.out; ea.partials = h->partials.as<float>(); ea.residual = w.residual; ea.ldo = w.ldo;
     ea.slots = slots_of(h, id);
+    if (w.epi == EPI_GN_FUSED) {
+      ea.gamma = h->dw.at(std::string(w.gn) + ".weight");
+      ea.beta = h->dw.at(std::string(w.gn) + ".bias");
+      ea.counters = h->counters.as<int>();
+    }
     TCS_CHECK(conv_tc_make_plan(&h->plan[id], g, w.s0, w.s1, h->wpack[id].as<__nv_bfloat16>(), w.epi, ea, h->sm_count));
   }
   return TCS_OK;
@@ -271,8 +285,7 @@ static int run_conv(tcs_handle* h, int id, int B, cudaStream_t st) {
   if (h->use_tc) {
     ConvTcPlan pl = h->plan[id];
     pl.p.n_mtiles = B * pl.p.tiles_per_img;
-    const int tiles = pl.p.n_mtiles * pl.p.n_ntiles;
-    pl.grid = tiles < h->sm_count ? tiles : h->sm_count;
+    pl.grid = conv_tc_grid(pl, B, h->sm_count);
     return conv_tc_launch(pl, st);
   }
   const ConvWiring w = wiring(h, id);
@@ -319,6 +332,20 @@ static int forward_chunk(tcs_handle* h, const PassArgs& a, cudaStream_t st, TapR
     return 1;
   };
 #define TAP(kind, p, H, W, C) { int _r = tapout(kind, p, H, W, C); if (_r != 0) return _r < 0 ? _r : TCS_OK; }
+// conv followed by GroupNorm+SiLU: one fused kernel (tcgen05) or conv -> raw fp32 -> gn_apply
+#define CONV_GN(cid, raw, res, C)                                                                         \
+  {                                                                                                      \
+    const ConvWiring _w = wiring(h, cid);                                                                 \
+    TCS_CHECK(run_conv<T>(h, cid, B, st));                                                                \
+    if (_w.epi == EPI_GN_FUSED) {                                                                        \
+      if (tap && tap->id == tap_idx) return fail(TCS_ERR_UNSUPPORTED, "raw conv output does not exist when GroupNorm is fused"); \
+      ++tap_idx;                                                                                         \
+    } else {                                                                                             \
+      TAP(0, raw, res, res, C);                                                                          \
+      GN(_w.gn, raw, slots_of(h, cid), res, C, static_cast<T*>(_w.act));                                  \
+    }                                                                                                    \
+    TAP(1, _w.act, res, res, C);                                                                         \
+  }
 #define GN(key, raw, slots, res, C, out) \
   { h->launches += 2; TCS_CHECK(launch_gn_apply<T>(raw, 0, part, slots, gnw(key), gnb(key), B, res, res, C, 1, out, h->gnstats.as<float2>(), st)); }
 
@@ -329,32 +356,17 @@ static int forward_chunk(tcs_handle* h, const PassArgs& a, cudaStream_t st, TapR
   TAP(0, h->raw64.p, 64, 64, 96);
   GN("down1.net.1", h->raw64.p, FIRST_CONV_SLOTS, 64, 96, h->p64_a.as<T>());
   TAP(1, h->p64_a.p, 64, 64, 96);
-  TCS_CHECK(run_conv<T>(h, C_D1B, B, st));
-  TAP(0, h->raw64.p, 64, 64, 96);
-  GN("down1.net.4", h->raw64.p, slots_of(h, C_D1B), 64, 96, h->p64_h1.as<T>());
-  TAP(1, h->p64_h1.p, 64, 64, 96);
+  CONV_GN(C_D1B, h->raw64.p, 64, 96);
   TCS_CHECK(run_conv<T>(h, C_DS1, B, st));
   TAP(1, h->p32_96a.p, 32, 32, 96);
   // ---- down2 -------------------------------------------------------------------------------
-  TCS_CHECK(run_conv<T>(h, C_D2A, B, st));
-  TAP(0, h->raw32.p, 32, 32, 192);
-  GN("down2.net.1", h->raw32.p, slots_of(h, C_D2A), 32, 192, h->p32_192a.as<T>());
-  TAP(1, h->p32_192a.p, 32, 32, 192);
-  TCS_CHECK(run_conv<T>(h, C_D2B, B, st));
-  TAP(0, h->raw32.p, 32, 32, 192);
-  GN("down2.net.4", h->raw32.p, slots_of(h, C_D2B), 32, 192, h->p32_192h2.as<T>());
-  TAP(1, h->p32_192h2.p, 32, 32, 192);
+  CONV_GN(C_D2A, h->raw32.p, 32, 192);
+  CONV_GN(C_D2B, h->raw32.p, 32, 192);
   TCS_CHECK(run_conv<T>(h, C_DS2, B, st));
   TAP(1, h->p16_a.p, 16, 16, 192);
   // ---- mid + attention ---------------------------------------------------------------------
-  TCS_CHECK(run_conv<T>(h, C_MA, B, st));
-  TAP(0, h->raw16.p, 16, 16, 192);
-  GN("mid.net.1", h->raw16.p, slots_of(h, C_MA), 16, 192, h->p16_b.as<T>());
-  TAP(1, h->p16_b.p, 16, 16, 192);
-  TCS_CHECK(run_conv<T>(h, C_MB, B, st));
-  TAP(0, h->raw16.p, 16, 16, 192);
-  GN("mid.net.4", h->raw16.p, slots_of(h, C_MB), 16, 192, h->p16_a.as<T>());   // x_in of the attention block
-  TAP(1, h->p16_a.p, 16, 16, 192);
+  CONV_GN(C_MA, h->raw16.p, 16, 192);
+  CONV_GN(C_MB, h->raw16.p, 16, 192);   // -> p16_a = x_in of the attention block
   ++h->launches;
   TCS_CHECK(launch_gn_stats<T>(h->p16_a.as<T>(), B, 16, 16, 192, part, st));
   h->launches += 2;
@@ -373,28 +385,16 @@ static int forward_chunk(tcs_handle* h, const PassArgs& a, cudaStream_t st, TapR
   TAP(1, h->p32_192a.p, 32, 32, 192);
   TCS_CHECK(run_conv<T>(h, C_US2, B, st));
   TAP(1, h->p32_192b.p, 32, 32, 192);
-  TCS_CHECK(run_conv<T>(h, C_U2A, B, st));
-  TAP(0, h->raw32.p, 32, 32, 96);
-  GN("up2.net.1", h->raw32.p, slots_of(h, C_U2A), 32, 96, h->p32_96a.as<T>());
-  TAP(1, h->p32_96a.p, 32, 32, 96);
-  TCS_CHECK(run_conv<T>(h, C_U2B, B, st));
-  TAP(0, h->raw32.p, 32, 32, 96);
-  GN("up2.net.4", h->raw32.p, slots_of(h, C_U2B), 32, 96, h->p32_96b.as<T>());
-  TAP(1, h->p32_96b.p, 32, 32, 96);
+  CONV_GN(C_U2A, h->raw32.p, 32, 96);
+  CONV_GN(C_U2B, h->raw32.p, 32, 96);
   // ---- up1 ---------------------------------------------------------------------------------
   ++h->launches;
   TCS_CHECK(launch_upsample2x<T>(h->p32_96b.as<T>(), B, 32, 32, 96, h->p64_a.as<T>(), st));
   TAP(1, h->p64_a.p, 64, 64, 96);
   TCS_CHECK(run_conv<T>(h, C_US1, B, st));
   TAP(1, h->p64_b.p, 64, 64, 96);
-  TCS_CHECK(run_conv<T>(h, C_U1A, B, st));
-  TAP(0, h->raw64.p, 64, 64, 96);
-  GN("up1.net.1", h->raw64.p, slots_of(h, C_U1A), 64, 96, h->p64_a.as<T>());
-  TAP(1, h->p64_a.p, 64, 64, 96);
-  TCS_CHECK(run_conv<T>(h, C_U1B, B, st));
-  TAP(0, h->raw64.p, 64, 64, 96);
-  GN("up1.net.4", h->raw64.p, slots_of(h, C_U1B), 64, 96, h->p64_b.as<T>());
-  TAP(1, h->p64_b.p, 64, 64, 96);
+  CONV_GN(C_U1A, h->raw64.p, 64, 96);
+  CONV_GN(C_U1B, h->raw64.p, 64, 96);
   // ---- out conv + CFG combine ------------------------------------------------------------------
   ++h->launches;
   TCS_CHECK(launch_out_conv<T>(h->p64_b.as<T>(), h->d_wout, h->out_bias, a.ns, a.dup, a.guidance, a.eps, st));
@@ -406,6 +406,7 @@ static int forward_chunk(tcs_handle* h, const PassArgs& a, cudaStream_t st, TapR
   }
 #undef TAP
 #undef GN
+#undef CONV_GN
   return TCS_OK;
 }
 
@@ -528,6 +529,10 @@ int tcs_create(tcs_handle** out, const tcs_config* cfg) {
   if (eng == TCS_ENGINE_AUTO) eng = h->bf16 ? TCS_ENGINE_TCGEN05 : TCS_ENGINE_SIMT;
   if (eng == TCS_ENGINE_TCGEN05 && !h->bf16) return fail(TCS_ERR_UNSUPPORTED, "the tcgen05 engine needs precision = bf16");
   h->use_tc = eng == TCS_ENGINE_TCGEN05;
+  {
+    const char* e = getenv("TCS_FUSE_GN");   // 0 = keep conv -> raw fp32 -> gn_apply (A/B switch)
+    h->fuse_gn = h->use_tc && !(e && atoi(e) == 0);
+  }
   h->chunk = cfg->chunk > 0 ? cfg->chunk : 256;
   if (h->chunk % 2) h->chunk += 1;
   TCS_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
