@@ -153,13 +153,14 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
-constexpr int TC_THREADS = 192;
+constexpr int EPI_WARPS = 8;
+constexpr int TC_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int MAX_STAGES = 8;
-constexpr uint32_t EPI_SLAB_BYTES = 4 * 2 * 4096;   // per-warp double-buffered 32x32 fp32 slabs
+constexpr uint32_t EPI_SLAB_BYTES = EPI_WARPS * 4096;   // one 32x32 fp32 slab per epilogue warp
 constexpr uint32_t EPI_BIAS_BYTES = 576 * 4;
 struct EpiFusedSmem {          // EPI_GN_FUSED scratch (lives right after the bias)
   float gamma[192], beta[192], scale[192], shift[192];
-  float red[4][16];
+  float red[EPI_WARPS][16];
   float mean[8], rstd[8];
 };
 constexpr uint32_t EPI_FUSED_BYTES = sizeof(EpiFusedSmem);
@@ -172,7 +173,34 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 __device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
   asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+// SiLU(y) = y * sigmoid(y) = h + h * tanh(h), h = y/2: one MUFU instead of two (ex2 + rcp)
+__device__ __forceinline__ float silu_fast(float y) {
+  const float h = 0.5f * y;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+// 32 bf16 channels of one pixel -> padded NHWC tensor, duplicated onto the circular halo where needed
+__device__ __forceinline__ void store_with_halo(__nv_bfloat16* obase, size_t pix, int wy, int wx, int Wp, int ldo,
+                                                int ch, const uint32_t* pk) {
+#pragma unroll
+  for (int cy = 0; cy < 2; ++cy) {
+    if (cy == 1 && wy == 0) continue;
+#pragma unroll
+    for (int cx = 0; cx < 2; ++cx) {
+      if (cx == 1 && wx == 0) continue;
+      const size_t dp = pix + static_cast<long long>(cy ? wy : 0) * Wp + (cx ? wx : 0);
+      uint4* dst = reinterpret_cast<uint4*>(obase + dp * ldo + ch);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+    }
+  }
+}
 
 struct __align__(8) TcBarriers {
   uint64_t full[MAX_STAGES];
@@ -189,8 +217,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                const ConvTcParams p) {
   constexpr int ACC_STRIDE = (N * MSUB <= 128) ? 128 : 256;  // TMEM columns per accumulator stage
   static_assert(N * MSUB <= 256, "accumulator does not fit a double-buffered TMEM stage");
-  constexpr int CPG = 0;  // (placeholder to keep the template list short)
-  (void)CPG;
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ TcBarriers bars;
@@ -218,7 +244,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(ptx::smem_u32(&bars.tmem_full[a]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bars.tmem_empty[a]), 4);
+      ptx::mbar_init(ptx::smem_u32(&bars.tmem_empty[a]), EPI_WARPS);
     }
     ptx::fence_barrier_init();
   }
@@ -292,46 +318,53 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
-    // ============================== epilogue ==================================
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    // ============================== epilogue (8 warps) ===========================
+    // TMEM lane quarter q = warp % 4 is served by two warps (u = 0, 1): with MSUB == 2 warp u owns
+    // sub-tile u, with MSUB == 1 (N = 192) it owns the 96-column half u.  96 columns per warp and tile.
+    const int e = warp - 2, q = warp & 3, u = e >> 2;
+    const int sub = (MSUB == 2) ? u : 0;
+    const int col0 = (MSUB == 2) ? 0 : u * 96;
     const int row = q * 32 + lane;
     const int HW = p.H * p.W;
-    uint32_t acc = 0, acc_phase = 0, slab_buf = 0;
-    (void)slab_buf;
+    const int Wp = p.W + 2, Hp = p.H + 2;
+    uint32_t acc = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int mt = tile / p.n_ntiles, nt = tile - mt * p.n_ntiles;
-      const int n_off = nt * N;
+      const int n_off = nt * N + col0;                       // first output channel of this warp
+      const int m = (mt * MSUB + sub) * 128 + row;           // global pixel index (b, y, x)
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_STRIDE + sub * N + col0;
       ptx::mbar_wait(ptx::smem_u32(&bars.tmem_full[acc]), acc_phase);
       ptx::tc_fence_after();
+
       if constexpr (EPI == EPI_GN_FUSED) {
-        // ---- conv + bias + GroupNorm + SiLU without leaving TMEM --------------------------------------
-        // The G = tiles_per_img CTAs blockIdx % G == 0..G-1 of a group hold one image between them.
-        // pass 1: per-group sums of this CTA's pixels -> global; arrive on the image counter; wait for
-        // the other G-1 CTAs (they run the same image in lock step); pass 2: normalise from TMEM.
-        constexpr int CPGN = N / 8;
+        // ---- conv + bias + GroupNorm + SiLU without leaving TMEM ----------------------------------
+        // The G = tiles_per_img CTAs with blockIdx % G == 0..G-1 hold one image between them and run it
+        // in lock step.  pass 1: per-group sums of this CTA's pixels -> global, arrive on the image's
+        // counter, wait for the other G-1 CTAs; pass 2: normalise + SiLU straight from TMEM.
+        constexpr int CPGN = N / 8;            // channels per group: 12 or 24
+        constexpr int NG = 96 / CPGN;          // groups inside this warp's 96 columns: 8 or 4
         const int G = p.tiles_per_img;
         const int img = mt / G;
-        float gs[8], gq[8];
+        float gs[NG], gq[NG];
 #pragma unroll
-        for (int g = 0; g < 8; ++g) gs[g] = gq[g] = 0.f;
+        for (int g = 0; g < NG; ++g) gs[g] = gq[g] = 0.f;
 #pragma unroll
-        for (int sub = 0; sub < MSUB; ++sub) {
-          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_STRIDE + sub * N;
+        for (int c0 = 0; c0 < 96; c0 += 32) {
+          float v[32];
+          ptx::tmem_ld32(taddr + c0, v);
+          ptx::tmem_ld_wait();
 #pragma unroll
-          for (int c0 = 0; c0 < N; c0 += 32) {
-            float v[32];
-            ptx::tmem_ld32(taddr + c0, v);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float t = v[i] + bias_s[c0 + i];
-              gs[(c0 + i) / CPGN] += t;
-              gq[(c0 + i) / CPGN] += t * t;
-            }
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n_off + c0 + i);
+            const float t0 = v[i] + b4.x, t1 = v[i + 1] + b4.y, t2 = v[i + 2] + b4.z, t3 = v[i + 3] + b4.w;
+            gs[(c0 + i) / CPGN] += t0; gq[(c0 + i) / CPGN] += t0 * t0;
+            gs[(c0 + i + 1) / CPGN] += t1; gq[(c0 + i + 1) / CPGN] += t1 * t1;
+            gs[(c0 + i + 2) / CPGN] += t2; gq[(c0 + i + 2) / CPGN] += t2 * t2;
+            gs[(c0 + i + 3) / CPGN] += t3; gq[(c0 + i + 3) / CPGN] += t3 * t3;
           }
         }
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
+        for (int g = 0; g < NG; ++g) {
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) {
             gs[g] += __shfl_xor_sync(0xffffffffu, gs[g], o);
@@ -339,14 +372,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           }
         }
         if (lane == 0) {
+          const int goff = col0 / CPGN;
 #pragma unroll
-          for (int g = 0; g < 8; ++g) { fs->red[warp - 2][2 * g] = gs[g]; fs->red[warp - 2][2 * g + 1] = gq[g]; }
+          for (int g = 0; g < NG; ++g) { fs->red[e][2 * (goff + g)] = gs[g]; fs->red[e][2 * (goff + g) + 1] = gq[g]; }
         }
         epi_bar_sync();
         if (warp == 2) {
           float* gpart = p.epi.partials + static_cast<size_t>(mt) * 16;
           if (lane < 16) {
-            __stcg(gpart + lane, (fs->red[0][lane] + fs->red[1][lane]) + (fs->red[2][lane] + fs->red[3][lane]));
+            float t = 0.f;
+            if (MSUB == 2) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) t += fs->red[k][lane];
+            } else {
+              const int u0 = (lane >> 1) / NG * 4;   // the four warps that own this group's columns
+#pragma unroll
+              for (int k = 0; k < 4; ++k) t += fs->red[u0 + k][lane];
+            }
+            __stcg(gpart + lane, t);
             __threadfence();
           }
           __syncwarp();
@@ -375,179 +418,144 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           }
         }
         epi_bar_sync();
-        for (int c = threadIdx.x - 64; c < N; c += 128) {
+        for (int c = threadIdx.x - 64; c < N; c += 32 * EPI_WARPS) {
           const int g = c / CPGN;
           const float sc = fs->rstd[g] * fs->gamma[c];
           fs->scale[c] = sc;
           fs->shift[c] = (bias_s[c] - fs->mean[g]) * sc + fs->beta[c];
         }
         epi_bar_sync();
-        const int Wp = p.W + 2, Hp = p.H + 2;
+        const int rem = m - img * HW;
+        const int y = rem / p.W, x = rem - y * p.W;
+        const int wy = (y == 0) ? p.H : ((y == p.H - 1) ? -p.H : 0);
+        const int wx = (x == 0) ? p.W : ((x == p.W - 1) ? -p.W : 0);
+        const size_t pix = (static_cast<size_t>(img) * Hp + (y + 1)) * Wp + (x + 1);
         __nv_bfloat16* obase = static_cast<__nv_bfloat16*>(p.epi.out);
 #pragma unroll
-        for (int sub = 0; sub < MSUB; ++sub) {
-          const int m = (mt * MSUB + sub) * 128 + row;
-          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_STRIDE + sub * N;
-          const int rem = m - img * HW;
-          const int y = rem / p.W, x = rem - y * p.W;
-          const int wy = (y == 0) ? p.H : ((y == p.H - 1) ? -p.H : 0);
-          const int wx = (x == 0) ? p.W : ((x == p.W - 1) ? -p.W : 0);
-          const size_t pix = (static_cast<size_t>(img) * Hp + (y + 1)) * Wp + (x + 1);
+        for (int c0 = 0; c0 < 96; c0 += 32) {
+          float v[32];
+          ptx::tmem_ld32(taddr + c0, v);
+          ptx::tmem_ld_wait();
+          uint32_t pk[16];
 #pragma unroll
-          for (int c0 = 0; c0 < N; c0 += 32) {
-            float v[32];
-            ptx::tmem_ld32(taddr + c0, v);
-            ptx::tmem_ld_wait();
-            uint32_t pk[16];
+          for (int i = 0; i < 32; i += 4) {
+            const float4 s4 = *reinterpret_cast<const float4*>(fs->scale + n_off + c0 + i);
+            const float4 h4 = *reinterpret_cast<const float4*>(fs->shift + n_off + c0 + i);
+            const float y0 = silu_fast(fmaf(v[i], s4.x, h4.x)), y1 = silu_fast(fmaf(v[i + 1], s4.y, h4.y));
+            const float y2 = silu_fast(fmaf(v[i + 2], s4.z, h4.z)), y3 = silu_fast(fmaf(v[i + 3], s4.w, h4.w));
+            pk[i / 2] = pack_bf16x2(y0, y1);
+            pk[i / 2 + 1] = pack_bf16x2(y2, y3);
+          }
+          store_with_halo(obase, pix, wy, wx, Wp, p.epi.ldo, n_off + c0, pk);
+        }
+      } else if constexpr (EPI == EPI_RAW_STATS) {
+        // fp32 tile -> swizzled 32x32 slab in shared memory -> TMA store (full 128 B lines, no LSU),
+        // plus per-(warp, group) partial sums for a separate GroupNorm pass (debug / A-B path)
+        constexpr int CPGN = N / 8;
+        constexpr int NG = 96 / CPGN;
+        float gs[NG], gq[NG];
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 s4 = *reinterpret_cast<const float4*>(fs->scale + c0 + i);
-              const float4 h4 = *reinterpret_cast<const float4*>(fs->shift + c0 + i);
-              float y0 = fmaf(v[i], s4.x, h4.x), y1 = fmaf(v[i + 1], s4.y, h4.y);
-              float y2 = fmaf(v[i + 2], s4.z, h4.z), y3 = fmaf(v[i + 3], s4.w, h4.w);
-              y0 = __fdividef(y0, 1.0f + __expf(-y0)); y1 = __fdividef(y1, 1.0f + __expf(-y1));
-              y2 = __fdividef(y2, 1.0f + __expf(-y2)); y3 = __fdividef(y3, 1.0f + __expf(-y3));
-              const __nv_bfloat162 a = __floats2bfloat162_rn(y0, y1), b2 = __floats2bfloat162_rn(y2, y3);
-              pk[i / 2] = *reinterpret_cast<const uint32_t*>(&a);
-              pk[i / 2 + 1] = *reinterpret_cast<const uint32_t*>(&b2);
-            }
+        for (int g = 0; g < NG; ++g) gs[g] = gq[g] = 0.f;
+        const uint32_t slab = slab_base + static_cast<uint32_t>(e) * 4096;
+        const int m_base = (mt * MSUB + sub) * 128 + q * 32;
 #pragma unroll
-            for (int cy = 0; cy < 2; ++cy) {
-              if (cy == 1 && wy == 0) continue;
+        for (int c0 = 0; c0 < 96; c0 += 32) {
+          float v[32];
+          ptx::tmem_ld32(taddr + c0, v);
+          ptx::tmem_ld_wait();
 #pragma unroll
-              for (int cx = 0; cx < 2; ++cx) {
-                if (cx == 1 && wx == 0) continue;
-                const size_t dp = pix + static_cast<size_t>(cy ? wy : 0) * Wp + (cx ? wx : 0);
-                uint4* dst = reinterpret_cast<uint4*>(obase + dp * p.epi.ldo + c0);
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n_off + c0 + i);
+            v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+          }
 #pragma unroll
-                for (int i = 0; i < 4; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-              }
-            }
+          for (int i = 0; i < 32; ++i) {
+            gs[(c0 + i) / CPGN] += v[i];
+            gq[(c0 + i) / CPGN] += v[i] * v[i];
+          }
+          if (lane == 0) ptx::bulk_wait_read<0>();   // the previous store has finished reading the slab
+          __syncwarp();
+          const uint32_t dst = slab + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            ptx::st_shared_v4(dst + ((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_2d(&mapO, slab, n_off + c0, m_base);
+            ptx::bulk_commit();
           }
         }
-      } else {
 #pragma unroll
-      for (int sub = 0; sub < MSUB; ++sub) {
-        const int m = (mt * MSUB + sub) * 128 + row;  // global pixel index (b, y, x)
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_STRIDE + sub * N;
-        if constexpr (EPI == EPI_RAW_STATS) {
-          constexpr int CPGN = (N == 96) ? 12 : 24;  // channels per GroupNorm group
-          float gs[8], gq[8];
+        for (int g = 0; g < NG; ++g) {
 #pragma unroll
-          for (int g = 0; g < 8; ++g) gs[g] = gq[g] = 0.f;
-          // fp32 tile -> swizzled 32x32 slab in shared memory -> TMA store (full 128 B lines, no LSU)
-          const uint32_t slab = slab_base + static_cast<uint32_t>(warp - 2) * 8192;
-          const int m_base = (mt * MSUB + sub) * 128 + q * 32;
-#pragma unroll
-          for (int c0 = 0; c0 < N; c0 += 32) {
-            float v[32];
-            ptx::tmem_ld32(taddr + c0, v);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n_off + c0 + i);
-              v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
-            }
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              gs[(c0 + i) / CPGN] += v[i];
-              gq[(c0 + i) / CPGN] += v[i] * v[i];
-            }
-            if (lane == 0) ptx::bulk_wait_read<1>();   // the slab written two chunks ago has been read
-            __syncwarp();
-            const uint32_t dst = slab + slab_buf * 4096 + lane * 128;
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              ptx::st_shared_v4(dst + ((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            ptx::fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-              ptx::tma_store_2d(&mapO, slab + slab_buf * 4096, n_off + c0, m_base);
-              ptx::bulk_commit();
-            }
-            slab_buf ^= 1;
+          for (int o = 16; o > 0; o >>= 1) {
+            gs[g] += __shfl_xor_sync(0xffffffffu, gs[g], o);
+            gq[g] += __shfl_xor_sync(0xffffffffu, gq[g], o);
           }
+        }
+        if (lane == 0) {
+          // slot layout [image][tile-in-image*MSUB + sub][quarter]; with MSUB == 1 the two column halves
+          // write disjoint groups of the same slot
+          const int b = m / HW;
+          const int slot = ((mt * MSUB + sub) % (p.tiles_per_img * MSUB)) * 4 + q;
+          float* dst = p.epi.partials + (static_cast<size_t>(b) * p.epi.slots + slot) * 16 + 2 * (col0 / CPGN);
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
+          for (int g = 0; g < NG; ++g) { dst[2 * g] = gs[g]; dst[2 * g + 1] = gq[g]; }
+        }
+      } else if constexpr (EPI == EPI_PADDED) {
+        const int b = m / HW, rem = m - b * HW;
+        const int y = rem / p.W, x = rem - y * p.W;
+        const int wy = (y == 0) ? p.H : ((y == p.H - 1) ? -p.H : 0);
+        const int wx = (x == 0) ? p.W : ((x == p.W - 1) ? -p.W : 0);
+        __nv_bfloat16* obase = static_cast<__nv_bfloat16*>(p.epi.out);
+        const size_t pix = (static_cast<size_t>(b) * Hp + (y + 1)) * Wp + (x + 1);
+        const __nv_bfloat16* rrow =
+            p.epi.residual ? static_cast<const __nv_bfloat16*>(p.epi.residual) + pix * p.ntot + n_off : nullptr;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              gs[g] += __shfl_xor_sync(0xffffffffu, gs[g], o);
-              gq[g] += __shfl_xor_sync(0xffffffffu, gq[g], o);
-            }
-          }
-          if (lane == 0) {
-            const int b = m / HW;
-            const int slot = (((mt * MSUB + sub) % (p.tiles_per_img * MSUB)) * 4 + q);
-            float* dst = p.epi.partials + (static_cast<size_t>(b) * p.epi.slots + slot) * 16;
+        for (int c0 = 0; c0 < 96; c0 += 32) {
+          float v[32];
+          ptx::tmem_ld32(taddr + c0, v);
+          ptx::tmem_ld_wait();
+          if (rrow) {
 #pragma unroll
-            for (int g = 0; g < 8; ++g) { dst[2 * g] = gs[g]; dst[2 * g + 1] = gq[g]; }
-          }
-        } else if constexpr (EPI == EPI_PADDED) {
-          const int b = m / HW, rem = m - b * HW;
-          const int y = rem / p.W, x = rem - y * p.W;
-          const int Wp = p.W + 2, Hp = p.H + 2;
-          const int wy = (y == 0) ? p.H : ((y == p.H - 1) ? -p.H : 0);
-          const int wx = (x == 0) ? p.W : ((x == p.W - 1) ? -p.W : 0);
-          __nv_bfloat16* obase = static_cast<__nv_bfloat16*>(p.epi.out);
-          const size_t pix = (static_cast<size_t>(b) * Hp + (y + 1)) * Wp + (x + 1);
-          const __nv_bfloat16* rrow =
-              p.epi.residual ? static_cast<const __nv_bfloat16*>(p.epi.residual) + pix * p.ntot + n_off : nullptr;
+            for (int i = 0; i < 4; ++i) {
+              const uint4 rr = *reinterpret_cast<const uint4*>(rrow + c0 + i * 8);
+              const uint32_t w4[4] = {rr.x, rr.y, rr.z, rr.w};
 #pragma unroll
-          for (int c0 = 0; c0 < N; c0 += 32) {
-            float v[32];
-            ptx::tmem_ld32(taddr + c0, v);
-            ptx::tmem_ld_wait();
-            uint4 pk[4];
-            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(pk);
-            if (rrow) {
-              uint4 rr[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) rr[i] = *reinterpret_cast<const uint4*>(rrow + c0 + i * 8);
-              const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(rr);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float2 rf = __bfloat1622float2(r2[i]);
-                v[2 * i] += rf.x;
-                v[2 * i + 1] += rf.y;
-              }
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              h2[i] = __floats2bfloat162_rn(v[2 * i] + bias_s[n_off + c0 + 2 * i],
-                                            v[2 * i + 1] + bias_s[n_off + c0 + 2 * i + 1]);
-#pragma unroll
-            for (int cy = 0; cy < 2; ++cy) {
-              if (cy == 1 && wy == 0) continue;
-#pragma unroll
-              for (int cx = 0; cx < 2; ++cx) {
-                if (cx == 1 && wx == 0) continue;
-                const size_t dp = pix + static_cast<size_t>(cy ? wy : 0) * Wp + (cx ? wx : 0);
-                uint4* dst = reinterpret_cast<uint4*>(obase + dp * p.epi.ldo + n_off + c0);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) dst[i] = pk[i];
+              for (int k = 0; k < 4; ++k) {
+                const float2 rf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[k]));
+                v[i * 8 + 2 * k] += rf.x;
+                v[i * 8 + 2 * k + 1] += rf.y;
               }
             }
           }
-        } else {  // EPI_PLAIN
-          __nv_bfloat16* orow = static_cast<__nv_bfloat16*>(p.epi.out) + static_cast<size_t>(m) * p.epi.ldo + n_off;
+          uint32_t pk[16];
 #pragma unroll
-          for (int c0 = 0; c0 < N; c0 += 32) {
-            float v[32];
-            ptx::tmem_ld32(taddr + c0, v);
-            ptx::tmem_ld_wait();
-            uint4 pk[4];
-            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(pk);
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n_off + c0 + i);
+            pk[i / 2] = pack_bf16x2(v[i] + b4.x, v[i + 1] + b4.y);
+            pk[i / 2 + 1] = pack_bf16x2(v[i + 2] + b4.z, v[i + 3] + b4.w);
+          }
+          store_with_halo(obase, pix, wy, wx, Wp, p.epi.ldo, n_off + c0, pk);
+        }
+      } else {  // EPI_PLAIN
+        __nv_bfloat16* orow = static_cast<__nv_bfloat16*>(p.epi.out) + static_cast<size_t>(m) * p.epi.ldo + n_off;
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              h2[i] = __floats2bfloat162_rn(v[2 * i] + bias_s[n_off + c0 + 2 * i],
-                                            v[2 * i + 1] + bias_s[n_off + c0 + 2 * i + 1]);
-            uint4* dst = reinterpret_cast<uint4*>(orow + c0);
+        for (int c0 = 0; c0 < 96; c0 += 32) {
+          float v[32];
+          ptx::tmem_ld32(taddr + c0, v);
+          ptx::tmem_ld_wait();
+          uint4* dst = reinterpret_cast<uint4*>(orow + c0);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) dst[i] = pk[i];
+          for (int i = 0; i < 32; i += 8) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n_off + c0 + i);
+            const float4 b5 = *reinterpret_cast<const float4*>(bias_s + n_off + c0 + i + 4);
+            dst[i / 8] = make_uint4(pack_bf16x2(v[i] + b4.x, v[i + 1] + b4.y), pack_bf16x2(v[i + 2] + b4.z, v[i + 3] + b4.w),
+                                    pack_bf16x2(v[i + 4] + b5.x, v[i + 5] + b5.y), pack_bf16x2(v[i + 6] + b5.z, v[i + 7] + b5.w));
           }
         }
       }
-      }  // !EPI_GN_FUSED
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars.tmem_empty[acc]));
@@ -663,16 +671,13 @@ int conv_tc_launch(const ConvTcPlan& pl, cudaStream_t st) {
   if (!pl.valid) return fail(TCS_ERR_STATE, "conv_tc_launch: plan not built");
 #define TCS_TC_CASE(NN, EE, MM) \
   if (pl.N == NN && pl.epi == EE && pl.msub == MM) return launch_t<NN, EE, MM>(pl, st);
-  TCS_TC_CASE(96, EPI_RAW_STATS, 1)
-  TCS_TC_CASE(96, EPI_PADDED, 1)
-  TCS_TC_CASE(96, EPI_PLAIN, 1)
+  TCS_TC_CASE(96, EPI_RAW_STATS, 2)
+  TCS_TC_CASE(96, EPI_PADDED, 2)
+  TCS_TC_CASE(96, EPI_PLAIN, 2)
+  TCS_TC_CASE(96, EPI_GN_FUSED, 2)
   TCS_TC_CASE(192, EPI_RAW_STATS, 1)
   TCS_TC_CASE(192, EPI_PADDED, 1)
   TCS_TC_CASE(192, EPI_PLAIN, 1)
-  TCS_TC_CASE(96, EPI_RAW_STATS, 2)
-  TCS_TC_CASE(96, EPI_PADDED, 2)
-  TCS_TC_CASE(96, EPI_GN_FUSED, 1)
-  TCS_TC_CASE(96, EPI_GN_FUSED, 2)
   TCS_TC_CASE(192, EPI_GN_FUSED, 1)
 #undef TCS_TC_CASE
   return fail(TCS_ERR_UNSUPPORTED, "conv_tc_launch: no kernel instance for this (N, epilogue, msub)");
@@ -690,13 +695,11 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, con
   pl.N = (g.ntot % 192 == 0) ? 192 : 96;
   if (g.ntot % pl.N) return fail(TCS_ERR_UNSUPPORTED, "conv_tc: C_out must be a multiple of 96");
   pl.epi = epi;
-  {
-    // two 128-pixel sub-tiles per CTA tile share every weight (B) stage: halves the B traffic per MAC.
-    // Only where two fp32 accumulator sets of MSUB*N columns still double-buffer in TMEM (N = 96).
-    const char* e = getenv("TCS_MSUB");
-    const int want = e ? atoi(e) : 2;
-    pl.msub = (want == 2 && pl.N == 96 && epi != EPI_PLAIN && (g.H % (2 * (128 / g.W)) == 0)) ? 2 : 1;
-  }
+  // N = 96: two 128-pixel sub-tiles per CTA tile share every weight (B) stage (half the B traffic per
+  // MAC) and give each of the 8 epilogue warps a 32-row x 96-column unit; N = 192: one sub-tile, the
+  // epilogue warps split its columns in halves.  Either way two accumulator sets double-buffer in TMEM.
+  pl.msub = pl.N == 96 ? 2 : 1;
+  if (g.H % (pl.msub * (128 / g.W))) return fail(TCS_ERR_UNSUPPORTED, "conv_tc: image height not a multiple of the tile");
   stage_shape(g, &p.T, &p.KYG, &p.KW);
   p.H = g.H; p.W = g.W; p.Rt = 128 / g.W;
   p.stride = g.stride;
