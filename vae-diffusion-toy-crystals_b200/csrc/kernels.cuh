@@ -32,6 +32,11 @@ int launch_first_conv(const float* x, const float* w9 /*[96][9]*/, const float* 
                       const int* step_ptr, int trow_off, const float* cvec, int n, int dup, float* raw,
                       float* partials, cudaStream_t st);
 constexpr int FIRST_CONV_SLOTS = 32;
+// the same conv with GroupNorm(down1.net.1)+SiLU fused: x -> padded T [n*dup,66,66,96] (no fp32 round trip)
+template <typename T>
+int launch_first_conv_gn(const float* x, const float* w9, const float* tvec, int tvec_stride, const int* step_ptr,
+                         int trow_off, const float* cvec, int n, int dup, const float* gamma, const float* beta, T* out,
+                         cudaStream_t st);
 
 // ---- GroupNorm apply (+SiLU) -> padded T with halo -----------------------------------------
 // in: fp32 raw plain [B,H,W,C] (in_padded=0) or padded T (in_padded=1); partials [B][slots][8][2]

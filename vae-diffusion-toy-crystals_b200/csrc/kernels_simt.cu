@@ -7,6 +7,8 @@
 // modules it calls (_ConvBlock :97-111, SelfAttention2d :114-167, nn.Upsample :217,221).
 #include "kernels.cuh"
 
+#include <cstdlib>
+
 namespace tcs {
 
 // ------------------------------------------------------------------------------------------
@@ -108,6 +110,123 @@ int launch_first_conv(const float* x, const float* w9, const float* tvec, int tv
   TCS_CUDA(cudaGetLastError());
   return TCS_OK;
 }
+
+template <bool FAST> __device__ __forceinline__ float silu_f(float v);
+
+// ------------------------------------------------------------------------------------------
+// first conv + GroupNorm + SiLU in ONE kernel (down1.net.0 + down1.net.1 + SiLU): one block per
+// sample; the 1->96 conv costs 9 MACs per output, so it is simply evaluated twice (pass 1: group
+// statistics, pass 2: normalise + write the padded activation) instead of round-tripping fp32.
+// thread = (output-channel pair, pixel phase): 48 x 8 = 384 threads.
+// ------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ void store_pair(T* p, float a, float b);
+template <> __device__ __forceinline__ void store_pair<float>(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+template <> __device__ __forceinline__ void store_pair<__nv_bfloat16>(__nv_bfloat16* p, float a, float b) {
+  *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(384) first_conv_gn_kernel(const float* __restrict__ x, const float* __restrict__ w9,
+                                                           const float* __restrict__ tvec, int tvec_stride,
+                                                           const int* __restrict__ step_ptr, int trow_off,
+                                                           const float* __restrict__ cvec, int dup,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           T* __restrict__ out) {
+  constexpr bool FAST = sizeof(T) == 2;
+  constexpr int P = IMG + 2;
+  __shared__ float xs[P][P];
+  __shared__ float red[384][2][2];
+  __shared__ float s_mean[2][GN_GROUPS], s_rstd[2][GN_GROUPS];
+  const int i = blockIdx.x, t = threadIdx.x, op = t % 48, pg = t / 48, oc = 2 * op;
+  for (int e = t; e < P * P; e += 384) {
+    const int r = e / P, c = e - r * P;
+    xs[r][c] = x[(static_cast<size_t>(i) * IMG + ((r - 1 + IMG) & (IMG - 1))) * IMG + ((c - 1 + IMG) & (IMG - 1))];
+  }
+  float w0[9], w1[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { w0[k] = w9[oc * 9 + k]; w1[k] = w9[(oc + 1) * 9 + k]; }
+  const int trow = (step_ptr ? *step_ptr : 0) + trow_off + i * tvec_stride;
+  float b0[2], b1[2];
+  for (int u = 0; u < 2; ++u) {
+    const int uu = u < dup ? u : 0;
+    b0[u] = tvec[static_cast<size_t>(trow) * 96 + oc] + cvec[(static_cast<size_t>(i) * dup + uu) * 96 + oc];
+    b1[u] = tvec[static_cast<size_t>(trow) * 96 + oc + 1] + cvec[(static_cast<size_t>(i) * dup + uu) * 96 + oc + 1];
+  }
+  __syncthreads();
+  float s[2] = {0.f, 0.f}, q[2] = {0.f, 0.f};
+  for (int p = pg; p < IMG_PIX; p += 8) {
+    const int yy = p >> 6, xx = p & 63;
+    float c0 = 0.f, c1 = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const float xv = xs[yy + ky][xx + kx];
+        c0 = fmaf(w0[ky * 3 + kx], xv, c0);
+        c1 = fmaf(w1[ky * 3 + kx], xv, c1);
+      }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const float v0 = c0 + b0[u], v1 = c1 + b1[u];
+      s[u] += v0 + v1;
+      q[u] += v0 * v0 + v1 * v1;
+    }
+  }
+  for (int u = 0; u < 2; ++u) { red[t][u][0] = s[u]; red[t][u][1] = q[u]; }
+  __syncthreads();
+  if (t < GN_GROUPS * 2) {
+    const int g = t & 7, u = t >> 3;
+    double sd = 0.0, qd = 0.0;
+    for (int k = 0; k < 8; ++k)        // pixel phases
+      for (int j = 0; j < 6; ++j) {    // the six channel pairs of group g
+        sd += static_cast<double>(red[k * 48 + g * 6 + j][u][0]);
+        qd += static_cast<double>(red[k * 48 + g * 6 + j][u][1]);
+      }
+    const double cnt = static_cast<double>(IMG_PIX) * 12.0;
+    const double mean = sd / cnt;
+    double var = qd / cnt - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    s_mean[u][g] = static_cast<float>(mean);
+    s_rstd[u][g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(GN_EPS)));
+  }
+  __syncthreads();
+  const int g = op / 6;
+  const float ga0 = gamma[oc], ga1 = gamma[oc + 1], be0 = beta[oc], be1 = beta[oc + 1];
+  for (int p = pg; p < IMG_PIX; p += 8) {
+    const int yy = p >> 6, xx = p & 63;
+    float c0 = 0.f, c1 = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const float xv = xs[yy + ky][xx + kx];
+        c0 = fmaf(w0[ky * 3 + kx], xv, c0);
+        c1 = fmaf(w1[ky * 3 + kx], xv, c1);
+      }
+    const int wy = halo_wrap(yy, IMG), wx = halo_wrap(xx, IMG);
+    for (int u = 0; u < dup; ++u) {
+      const float y0 = silu_f<FAST>(((c0 + b0[u]) - s_mean[u][g]) * s_rstd[u][g] * ga0 + be0);
+      const float y1 = silu_f<FAST>(((c1 + b1[u]) - s_mean[u][g]) * s_rstd[u][g] * ga1 + be1);
+      const size_t base = ((static_cast<size_t>(i) * dup + u) * P + yy + 1) * P + xx + 1;
+      store_pair<T>(out + base * 96 + oc, y0, y1);
+      if (wy) store_pair<T>(out + (base + static_cast<long long>(wy) * P) * 96 + oc, y0, y1);
+      if (wx) store_pair<T>(out + (base + wx) * 96 + oc, y0, y1);
+      if (wy && wx) store_pair<T>(out + (base + static_cast<long long>(wy) * P + wx) * 96 + oc, y0, y1);
+    }
+  }
+}
+
+template <typename T>
+int launch_first_conv_gn(const float* x, const float* w9, const float* tvec, int tvec_stride, const int* step_ptr,
+                         int trow_off, const float* cvec, int n, int dup, const float* gamma, const float* beta, T* out,
+                         cudaStream_t st) {
+  if (n <= 0) return TCS_OK;
+  first_conv_gn_kernel<T><<<n, 384, 0, st>>>(x, w9, tvec, tvec_stride, step_ptr, trow_off, cvec, dup, gamma, beta, out);
+  TCS_CUDA(cudaGetLastError());
+  return TCS_OK;
+}
+template int launch_first_conv_gn<float>(const float*, const float*, const float*, int, const int*, int, const float*, int, int, const float*, const float*, float*, cudaStream_t);
+template int launch_first_conv_gn<__nv_bfloat16>(const float*, const float*, const float*, int, const int*, int, const float*, int, int, const float*, const float*, __nv_bfloat16*, cudaStream_t);
 
 // ------------------------------------------------------------------------------------------
 // GroupNorm statistics from partial sums (fp64 combine, fixed order -> deterministic)
@@ -394,9 +513,183 @@ __global__ void __launch_bounds__(ATT_TOK) attention_kernel(const T* __restrict_
     ov.store(orow + d8);
   }
 }
+// ------------------------------------------------------------------------------------------
+// bf16 attention on the tensor cores (mma.sync m16n8k16, fp32 accumulate), flash-style:
+// block = (image, head), 8 warps x 32 query rows; K and V of the head live in shared memory
+// (112-byte rows: conflict-free ldmatrix); keys are consumed in chunks of 64 with an online
+// softmax in base 2.  The whole problem per block is 256 x 256 x 48, so nothing is tiled further.
+// ------------------------------------------------------------------------------------------
+constexpr int ATT_STRIDE = 56;  // bf16 elements per K/V row in shared memory (48 + 8 pad)
+
+__device__ __forceinline__ void mma_bf16_16816(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t* r) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t addr, uint32_t* r) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t* r) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(256) attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                           __nv_bfloat16* __restrict__ yout) {
+  extern __shared__ __align__(16) uint8_t att_raw[];
+  __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(att_raw);
+  __nv_bfloat16* Vs = Ks + ATT_TOK * ATT_STRIDE;
+  const int b = blockIdx.x >> 2, head = blockIdx.x & 3;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+  const __nv_bfloat16* base = qkv + static_cast<size_t>(b) * ATT_TOK * (3 * ATT_C) + head * ATT_D;
+  for (int e = tid; e < ATT_TOK * 6; e += 256) {
+    const int tok = e / 6, ch = e - tok * 6;
+    const uint4 kv = *reinterpret_cast<const uint4*>(base + static_cast<size_t>(tok) * (3 * ATT_C) + ATT_C + ch * 8);
+    const uint4 vv = *reinterpret_cast<const uint4*>(base + static_cast<size_t>(tok) * (3 * ATT_C) + 2 * ATT_C + ch * 8);
+    *reinterpret_cast<uint4*>(Ks + tok * ATT_STRIDE + ch * 8) = kv;
+    *reinterpret_cast<uint4*>(Vs + tok * ATT_STRIDE + ch * 8) = vv;
+  }
+  // Q fragments: 2 m-tiles x 3 k-steps, straight from global memory
+  uint32_t qf[2][3][4];
+  const int row0 = warp * 32;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int ks = 0; ks < 3; ++ks) {
+      const __nv_bfloat16* q0 = base + static_cast<size_t>(row0 + mt * 16 + g) * (3 * ATT_C) + ks * 16 + 2 * t4;
+      const __nv_bfloat16* q1 = q0 + 8 * (3 * ATT_C);
+      qf[mt][ks][0] = *reinterpret_cast<const uint32_t*>(q0);
+      qf[mt][ks][1] = *reinterpret_cast<const uint32_t*>(q1);
+      qf[mt][ks][2] = *reinterpret_cast<const uint32_t*>(q0 + 8);
+      qf[mt][ks][3] = *reinterpret_cast<const uint32_t*>(q1 + 8);
+    }
+  __syncthreads();
+  const uint32_t ks_addr = static_cast<uint32_t>(__cvta_generic_to_shared(Ks));
+  const uint32_t vs_addr = static_cast<uint32_t>(__cvta_generic_to_shared(Vs));
+  const float c = 0.14433756729740643f * 1.4426950408889634f;  // (1/sqrt(48)) * log2(e)
+  float o[2][6][4];
+  float mrow[2][2], lrow[2][2];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    mrow[mt][0] = mrow[mt][1] = -INFINITY;
+    lrow[mt][0] = lrow[mt][1] = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 6; ++nt)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[mt][nt][k] = 0.f;
+  }
+  for (int kc = 0; kc < ATT_TOK; kc += 64) {
+    float sacc[2][8][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) sacc[mt][nt][k] = 0.f;
+    // ---- S = Q K^T for 64 keys ------------------------------------------------------------------
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      uint32_t kb[6];
+      const uint32_t rowaddr = ks_addr + static_cast<uint32_t>((kc + nt * 8 + (lane & 7)) * ATT_STRIDE * 2);
+      ldsm_x4(rowaddr + (lane >> 3) * 16, kb);             // d chunks 0..3 -> (b0,b1) of k-steps 0,1
+      ldsm_x2(rowaddr + (4 + ((lane >> 3) & 1)) * 16, kb + 4);  // d chunks 4,5 -> k-step 2
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int ks = 0; ks < 3; ++ks) mma_bf16_16816(sacc[mt][nt], qf[mt][ks], kb[2 * ks], kb[2 * ks + 1]);
+    }
+    // ---- online softmax (base 2) --------------------------------------------------------------------
+    uint32_t pf[2][4][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      float mx0 = mrow[mt][0], mx1 = mrow[mt][1];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        mx0 = fmaxf(mx0, fmaxf(sacc[mt][nt][0], sacc[mt][nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(sacc[mt][nt][2], sacc[mt][nt][3]));
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float corr0 = exp2f((mrow[mt][0] - mx0) * c), corr1 = exp2f((mrow[mt][1] - mx1) * c);
+      mrow[mt][0] = mx0; mrow[mt][1] = mx1;
+      const float off0 = mx0 * c, off1 = mx1 * c;
+      float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const float p0 = exp2f(fmaf(sacc[mt][nt][0], c, -off0)), p1 = exp2f(fmaf(sacc[mt][nt][1], c, -off0));
+        const float p2 = exp2f(fmaf(sacc[mt][nt][2], c, -off1)), p3 = exp2f(fmaf(sacc[mt][nt][3], c, -off1));
+        ps0 += p0 + p1; ps1 += p2 + p3;
+        pf[mt][nt >> 1][(nt & 1) * 2] = pack2_bf16(p0, p1);
+        pf[mt][nt >> 1][(nt & 1) * 2 + 1] = pack2_bf16(p2, p3);
+      }
+      lrow[mt][0] = lrow[mt][0] * corr0 + ps0;
+      lrow[mt][1] = lrow[mt][1] * corr1 + ps1;
+#pragma unroll
+      for (int nt = 0; nt < 6; ++nt) {
+        o[mt][nt][0] *= corr0; o[mt][nt][1] *= corr0;
+        o[mt][nt][2] *= corr1; o[mt][nt][3] *= corr1;
+      }
+    }
+    // ---- O += P V ---------------------------------------------------------------------------------------
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {      // 16 keys per k-step
+#pragma unroll
+      for (int np = 0; np < 3; ++np) {    // pairs of d-tiles
+        uint32_t vb[4];
+        const int key = kc + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        ldsm_x4_trans(vs_addr + static_cast<uint32_t>(key * ATT_STRIDE * 2 + (np * 2 + (lane >> 4)) * 16), vb);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          mma_bf16_16816(o[mt][np * 2], pf[mt][kk], vb[0], vb[1]);
+          mma_bf16_16816(o[mt][np * 2 + 1], pf[mt][kk], vb[2], vb[3]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    float l0 = lrow[mt][0], l1 = lrow[mt][1];
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+    __nv_bfloat16* y0 = yout + (static_cast<size_t>(b) * ATT_TOK + row0 + mt * 16 + g) * ATT_C + head * ATT_D + 2 * t4;
+    __nv_bfloat16* y1 = y0 + 8 * ATT_C;
+#pragma unroll
+    for (int nt = 0; nt < 6; ++nt) {
+      *reinterpret_cast<uint32_t*>(y0 + nt * 8) = pack2_bf16(o[mt][nt][0] * i0, o[mt][nt][1] * i0);
+      *reinterpret_cast<uint32_t*>(y1 + nt * 8) = pack2_bf16(o[mt][nt][2] * i1, o[mt][nt][3] * i1);
+    }
+  }
+}
+
+int launch_attention_mma(const __nv_bfloat16* qkv, int B, __nv_bfloat16* y, cudaStream_t st) {
+  if (B <= 0) return TCS_OK;
+  const size_t smem = 2 * ATT_TOK * ATT_STRIDE * sizeof(__nv_bfloat16);
+  static bool done = false;
+  if (!done) {
+    TCS_CUDA(cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    done = true;
+  }
+  attention_mma_kernel<<<B * N_HEADS, 256, smem, st>>>(qkv, y);
+  TCS_CUDA(cudaGetLastError());
+  return TCS_OK;
+}
+
 template <typename T>
 int launch_attention(const T* qkv, int B, T* y, cudaStream_t st) {
   if (B <= 0) return TCS_OK;
+  if constexpr (sizeof(T) == 2) {
+    static const bool simt = getenv("TCS_ATT_SIMT") && atoi(getenv("TCS_ATT_SIMT")) == 1;
+    if (!simt) return launch_attention_mma(qkv, B, y, st);
+  }
   const size_t smem = 2 * ATT_TOK * ATT_D * sizeof(float);
   static bool done = false;
   if (!done) {

@@ -115,7 +115,7 @@ using namespace tcs;
 struct tcs_handle {
   tcs_config cfg;
   int sm_count = 148;
-  bool bf16 = false, use_tc = false, fuse_gn = false;
+  bool bf16 = false, use_tc = false, fuse_gn = false, fuse_first = true;
   size_t esz = 4;
   cudaStream_t stream = nullptr;   // internal stream all work runs on
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
@@ -350,11 +350,18 @@ static int forward_chunk(tcs_handle* h, const PassArgs& a, cudaStream_t st, TapR
   { h->launches += 2; TCS_CHECK(launch_gn_apply<T>(raw, 0, part, slots, gnw(key), gnb(key), B, res, res, C, 1, out, h->gnstats.as<float2>(), st)); }
 
   // ---- down1 -------------------------------------------------------------------------------
-  ++h->launches;
-  TCS_CHECK(launch_first_conv(a.x, h->d_w9, a.tvec, a.tvec_stride, a.step_ptr, a.trow_off, a.cvec, a.ns, a.dup,
-                              h->raw64.as<float>(), part, st));
-  TAP(0, h->raw64.p, 64, 64, 96);
-  GN("down1.net.1", h->raw64.p, FIRST_CONV_SLOTS, 64, 96, h->p64_a.as<T>());
+  if (h->fuse_first && !(tap && tap->id == 0)) {
+    ++h->launches;
+    TCS_CHECK(launch_first_conv_gn<T>(a.x, h->d_w9, a.tvec, a.tvec_stride, a.step_ptr, a.trow_off, a.cvec, a.ns, a.dup,
+                                      gnw("down1.net.1"), gnb("down1.net.1"), h->p64_a.as<T>(), st));
+    ++tap_idx;
+  } else {   // unfused variant (also serves the "down1.net.0.raw" debug tap)
+    ++h->launches;
+    TCS_CHECK(launch_first_conv(a.x, h->d_w9, a.tvec, a.tvec_stride, a.step_ptr, a.trow_off, a.cvec, a.ns, a.dup,
+                                h->raw64.as<float>(), part, st));
+    TAP(0, h->raw64.p, 64, 64, 96);
+    GN("down1.net.1", h->raw64.p, FIRST_CONV_SLOTS, 64, 96, h->p64_a.as<T>());
+  }
   TAP(1, h->p64_a.p, 64, 64, 96);
   CONV_GN(C_D1B, h->raw64.p, 64, 96);
   TCS_CHECK(run_conv<T>(h, C_DS1, B, st));
@@ -532,6 +539,7 @@ int tcs_create(tcs_handle** out, const tcs_config* cfg) {
   {
     const char* e = getenv("TCS_FUSE_GN");   // 0 = keep conv -> raw fp32 -> gn_apply (A/B switch)
     h->fuse_gn = h->use_tc && !(e && atoi(e) == 0);
+    h->fuse_first = !(e && atoi(e) == 0);
   }
   h->chunk = cfg->chunk > 0 ? cfg->chunk : 256;
   if (h->chunk % 2) h->chunk += 1;
