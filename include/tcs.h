@@ -136,6 +136,14 @@ int64_t tcs_debug_layer(tcs_handle* h, const char* name, const float* x, const f
                         const float* y_cont, int32_t n, int32_t uncond, float* out, int64_t out_capacity,
                         void* stream);
 
+/* tcs_score for one network pass (n * (guidance > 0 ? 2 : 1) <= chunk images) with CUDA events recorded, on the
+ * library's own stream, around every tensor-core conv launch.  conv_ms[15] is in execution order: down1.net.3,
+ * ds1, down2.net.0, down2.net.3, ds2, mid.net.0, mid.net.3, attn.qkv, attn.proj, us2_conv, up2.net.0, up2.net.3,
+ * us1_conv, up1.net.0, up1.net.3 (GroupNorm+SiLU included where fused); *total_ms = the whole pass.  Synchronous. */
+int tcs_score_profiled(tcs_handle* h, const float* x, const float* t, const int64_t* y_cat, const float* y_cont,
+                       int32_t n, float guidance, float* eps_out, float* conv_ms_host, float* total_ms_host,
+                       void* stream);
+
 /* Run ONE convolution layer in isolation (synchronous; allocates its own scratch).
  *   in0/in1 : fp32 NHWC [B, H_out*stride, W_out*stride, cin] (in1 may be NULL when cin1 == 0)
  *   weight  : [cout, cin0+cin1, k, k] (PyTorch layout), bias [cout]

@@ -125,6 +125,11 @@ template <> __device__ __forceinline__ void store_pair<__nv_bfloat16>(__nv_bfloa
   *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
 }
 
+// Statistics without a first pass: with circular padding  sum_p conv_c(p) = (sum_k w_ck) * sum_p x_p  and
+// sum_p conv_c(p)^2 = sum_{k,l} w_ck w_cl R(k-l)  with  R(d) = sum_p x_p x_{p+d}  (circular autocorrelation at
+// the 25 lags |dy|,|dx| <= 2), both exact identities; R and the quadratic forms are evaluated in fp64.
+// Each sample is split over FC_SPLIT blocks (row bands); every block recomputes the (cheap) statistics.
+constexpr int FC_SPLIT = 2;
 template <typename T>
 __global__ void __launch_bounds__(384) first_conv_gn_kernel(const float* __restrict__ x, const float* __restrict__ w9,
                                                            const float* __restrict__ tvec, int tvec_stride,
@@ -133,55 +138,74 @@ __global__ void __launch_bounds__(384) first_conv_gn_kernel(const float* __restr
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            T* __restrict__ out) {
   constexpr bool FAST = sizeof(T) == 2;
-  constexpr int P = IMG + 2;
+  constexpr int P = IMG + 4;                 // halo of 2 for the autocorrelation lags
   __shared__ float xs[P][P];
-  __shared__ float red[384][2][2];
+  __shared__ double racc[12][14];            // per-warp partial: 13 lags + sum x
+  __shared__ double R[5][5];
+  __shared__ double S1;
+  __shared__ double csum[96][2][2];          // per channel, per branch: sum v, sum v^2
   __shared__ float s_mean[2][GN_GROUPS], s_rstd[2][GN_GROUPS];
-  const int i = blockIdx.x, t = threadIdx.x, op = t % 48, pg = t / 48, oc = 2 * op;
+  const int i = blockIdx.x / FC_SPLIT, band = blockIdx.x % FC_SPLIT;
+  const int t = threadIdx.x, op = t % 48, pg = t / 48, oc = 2 * op;
+  const int warp = t >> 5, lane = t & 31;
   for (int e = t; e < P * P; e += 384) {
     const int r = e / P, c = e - r * P;
-    xs[r][c] = x[(static_cast<size_t>(i) * IMG + ((r - 1 + IMG) & (IMG - 1))) * IMG + ((c - 1 + IMG) & (IMG - 1))];
-  }
-  float w0[9], w1[9];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) { w0[k] = w9[oc * 9 + k]; w1[k] = w9[(oc + 1) * 9 + k]; }
-  const int trow = (step_ptr ? *step_ptr : 0) + trow_off + i * tvec_stride;
-  float b0[2], b1[2];
-  for (int u = 0; u < 2; ++u) {
-    const int uu = u < dup ? u : 0;
-    b0[u] = tvec[static_cast<size_t>(trow) * 96 + oc] + cvec[(static_cast<size_t>(i) * dup + uu) * 96 + oc];
-    b1[u] = tvec[static_cast<size_t>(trow) * 96 + oc + 1] + cvec[(static_cast<size_t>(i) * dup + uu) * 96 + oc + 1];
+    xs[r][c] = x[(static_cast<size_t>(i) * IMG + ((r - 2 + IMG) & (IMG - 1))) * IMG + ((c - 2 + IMG) & (IMG - 1))];
   }
   __syncthreads();
-  float s[2] = {0.f, 0.f}, q[2] = {0.f, 0.f};
-  for (int p = pg; p < IMG_PIX; p += 8) {
-    const int yy = p >> 6, xx = p & 63;
-    float c0 = 0.f, c1 = 0.f;
+  {  // R(dy,dx) for the 13 lags with (dy > 0) or (dy == 0 and dx >= 0); R(-d) = R(d)
+    double acc[14];
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
+    for (int k = 0; k < 14; ++k) acc[k] = 0.0;
+    for (int p = t; p < IMG_PIX; p += 384) {
+      const int yy = (p >> 6) + 2, xx = (p & 63) + 2;
+      const double x0 = xs[yy][xx];
+      acc[13] += x0;
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const float xv = xs[yy + ky][xx + kx];
-        c0 = fmaf(w0[ky * 3 + kx], xv, c0);
-        c1 = fmaf(w1[ky * 3 + kx], xv, c1);
+      for (int k = 0; k < 13; ++k) {
+        const int dy = (k + 2) / 5, dx = (k + 2) % 5 - 2;   // k=0..2 -> dy=0,dx=0..2 ; then dy=1,2 with dx=-2..2
+        acc[k] += x0 * static_cast<double>(xs[yy + dy][xx + dx]);
       }
+    }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const float v0 = c0 + b0[u], v1 = c1 + b1[u];
-      s[u] += v0 + v1;
-      q[u] += v0 * v0 + v1 * v1;
+    for (int k = 0; k < 14; ++k) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+      if (lane == 0) racc[warp][k] = acc[k];
     }
   }
-  for (int u = 0; u < 2; ++u) { red[t][u][0] = s[u]; red[t][u][1] = q[u]; }
   __syncthreads();
-  if (t < GN_GROUPS * 2) {
+  if (t < 14) {
+    double v = 0.0;
+    for (int w = 0; w < 12; ++w) v += racc[w][t];
+    if (t == 13) S1 = v;
+    else {
+      const int dy = (t + 2) / 5, dx = (t + 2) % 5 - 2;
+      R[2 + dy][2 + dx] = v;
+      R[2 - dy][2 - dx] = v;
+    }
+  }
+  const int trow = (step_ptr ? *step_ptr : 0) + trow_off + i * tvec_stride;
+  __syncthreads();
+  if (t < 96) {
+    double wk[9], A = 0.0, Q = 0.0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { wk[k] = w9[t * 9 + k]; A += wk[k]; }
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+#pragma unroll
+      for (int l = 0; l < 9; ++l) Q += wk[k] * wk[l] * R[2 + k / 3 - l / 3][2 + k % 3 - l % 3];
+    for (int u = 0; u < dup; ++u) {
+      const double bb = static_cast<double>(tvec[static_cast<size_t>(trow) * 96 + t] + cvec[(static_cast<size_t>(i) * dup + u) * 96 + t]);
+      csum[t][u][0] = A * S1 + IMG_PIX * bb;
+      csum[t][u][1] = Q + 2.0 * bb * A * S1 + IMG_PIX * bb * bb;
+    }
+  }
+  __syncthreads();
+  if (t < GN_GROUPS * dup) {
     const int g = t & 7, u = t >> 3;
     double sd = 0.0, qd = 0.0;
-    for (int k = 0; k < 8; ++k)        // pixel phases
-      for (int j = 0; j < 6; ++j) {    // the six channel pairs of group g
-        sd += static_cast<double>(red[k * 48 + g * 6 + j][u][0]);
-        qd += static_cast<double>(red[k * 48 + g * 6 + j][u][1]);
-      }
+    for (int j = 0; j < 12; ++j) { sd += csum[g * 12 + j][u][0]; qd += csum[g * 12 + j][u][1]; }
     const double cnt = static_cast<double>(IMG_PIX) * 12.0;
     const double mean = sd / cnt;
     double var = qd / cnt - mean * mean;
@@ -189,17 +213,28 @@ __global__ void __launch_bounds__(384) first_conv_gn_kernel(const float* __restr
     s_mean[u][g] = static_cast<float>(mean);
     s_rstd[u][g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(GN_EPS)));
   }
+  float w0[9], w1[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { w0[k] = w9[oc * 9 + k]; w1[k] = w9[(oc + 1) * 9 + k]; }
+  float b0[2], b1[2];
+  for (int u = 0; u < 2; ++u) {
+    const int uu = u < dup ? u : 0;
+    b0[u] = tvec[static_cast<size_t>(trow) * 96 + oc] + cvec[(static_cast<size_t>(i) * dup + uu) * 96 + oc];
+    b1[u] = tvec[static_cast<size_t>(trow) * 96 + oc + 1] + cvec[(static_cast<size_t>(i) * dup + uu) * 96 + oc + 1];
+  }
   __syncthreads();
   const int g = op / 6;
   const float ga0 = gamma[oc], ga1 = gamma[oc + 1], be0 = beta[oc], be1 = beta[oc + 1];
-  for (int p = pg; p < IMG_PIX; p += 8) {
+  constexpr int PO = IMG + 2;
+  const int p_begin = band * (IMG_PIX / FC_SPLIT), p_end = p_begin + IMG_PIX / FC_SPLIT;
+  for (int p = p_begin + pg; p < p_end; p += 8) {
     const int yy = p >> 6, xx = p & 63;
     float c0 = 0.f, c1 = 0.f;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
-        const float xv = xs[yy + ky][xx + kx];
+        const float xv = xs[yy + 1 + ky][xx + 1 + kx];
         c0 = fmaf(w0[ky * 3 + kx], xv, c0);
         c1 = fmaf(w1[ky * 3 + kx], xv, c1);
       }
@@ -207,11 +242,11 @@ __global__ void __launch_bounds__(384) first_conv_gn_kernel(const float* __restr
     for (int u = 0; u < dup; ++u) {
       const float y0 = silu_f<FAST>(((c0 + b0[u]) - s_mean[u][g]) * s_rstd[u][g] * ga0 + be0);
       const float y1 = silu_f<FAST>(((c1 + b1[u]) - s_mean[u][g]) * s_rstd[u][g] * ga1 + be1);
-      const size_t base = ((static_cast<size_t>(i) * dup + u) * P + yy + 1) * P + xx + 1;
+      const size_t base = ((static_cast<size_t>(i) * dup + u) * PO + yy + 1) * PO + xx + 1;
       store_pair<T>(out + base * 96 + oc, y0, y1);
-      if (wy) store_pair<T>(out + (base + static_cast<long long>(wy) * P) * 96 + oc, y0, y1);
+      if (wy) store_pair<T>(out + (base + static_cast<long long>(wy) * PO) * 96 + oc, y0, y1);
       if (wx) store_pair<T>(out + (base + wx) * 96 + oc, y0, y1);
-      if (wy && wx) store_pair<T>(out + (base + static_cast<long long>(wy) * P + wx) * 96 + oc, y0, y1);
+      if (wy && wx) store_pair<T>(out + (base + static_cast<long long>(wy) * PO + wx) * 96 + oc, y0, y1);
     }
   }
 }
@@ -221,7 +256,8 @@ int launch_first_conv_gn(const float* x, const float* w9, const float* tvec, int
                          int trow_off, const float* cvec, int n, int dup, const float* gamma, const float* beta, T* out,
                          cudaStream_t st) {
   if (n <= 0) return TCS_OK;
-  first_conv_gn_kernel<T><<<n, 384, 0, st>>>(x, w9, tvec, tvec_stride, step_ptr, trow_off, cvec, dup, gamma, beta, out);
+  first_conv_gn_kernel<T><<<n * FC_SPLIT, 384, 0, st>>>(x, w9, tvec, tvec_stride, step_ptr, trow_off, cvec, dup, gamma,
+                                                        beta, out);
   TCS_CUDA(cudaGetLastError());
   return TCS_OK;
 }
@@ -902,28 +938,23 @@ template int launch_conv_simt<__nv_bfloat16>(const ConvGeom&, const __nv_bfloat1
 // out conv 96 -> 1 (3x3 circular) + CFG combine  (sde_score_model.py:225,266 and :418-423)
 // 8 lanes per output pixel, 12 channels per lane; 32 pixels per 256-thread block
 // ------------------------------------------------------------------------------------------
-template <typename T> __device__ __forceinline__ void load12(const T* p, float* f);
-template <> __device__ __forceinline__ void load12<float>(const float* p, float* f) {
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    const float4 v = *reinterpret_cast<const float4*>(p + 4 * i);
-    f[4 * i] = v.x; f[4 * i + 1] = v.y; f[4 * i + 2] = v.z; f[4 * i + 3] = v.w;
-  }
+// lane `sl` of the 8 lanes that share a pixel handles the 12 channels 12 sl .. 12 sl + 11 (three 4-channel loads)
+template <typename T> __device__ __forceinline__ void load4(const T* p, float* f);
+template <> __device__ __forceinline__ void load4<float>(const float* p, float* f) {
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
 }
-template <> __device__ __forceinline__ void load12<__nv_bfloat16>(const __nv_bfloat16* p, float* f) {
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    const uint2 u = *reinterpret_cast<const uint2*>(p + 4 * i);
-    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
-    const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
-    f[4 * i] = a.x; f[4 * i + 1] = a.y; f[4 * i + 2] = c.x; f[4 * i + 3] = c.y;
-  }
+template <> __device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, float* f) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+  const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  f[0] = a.x; f[1] = a.y; f[2] = c.x; f[3] = c.y;
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256) out_conv_kernel(const T* __restrict__ act, const float* __restrict__ w, float bias,
                                                       int dup, float guidance, float* __restrict__ eps) {
-  __shared__ float ws[9 * 96];
+  __shared__ __align__(16) float ws[9 * 96];
   for (int e = threadIdx.x; e < 9 * 96; e += 256) ws[e] = w[e];
   __syncthreads();
   const int sl = threadIdx.x & 7;                       // channel slice
@@ -938,11 +969,14 @@ __global__ void __launch_bounds__(256) out_conv_kernel(const T* __restrict__ act
     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
-        float f[12];
-        load12<T>(img + (static_cast<size_t>(y + ky) * Wp + x + kx) * 96, f);
-        const float* wk = ws + (ky * 3 + kx) * 96 + sl * 12;
+        const T* px = img + (static_cast<size_t>(y + ky) * Wp + x + kx) * 96;
 #pragma unroll
-        for (int c = 0; c < 12; ++c) a = fmaf(f[c], wk[c], a);
+        for (int j = 0; j < 3; ++j) {
+          float f[4];
+          load4<T>(px + j * 4, f);
+          const float4 w4 = *reinterpret_cast<const float4*>(ws + (ky * 3 + kx) * 96 + sl * 12 + j * 4);
+          a = fmaf(f[0], w4.x, a); a = fmaf(f[1], w4.y, a); a = fmaf(f[2], w4.z, a); a = fmaf(f[3], w4.w, a);
+        }
       }
     a += __shfl_xor_sync(0xffffffffu, a, 4);
     a += __shfl_xor_sync(0xffffffffu, a, 2);

@@ -120,6 +120,8 @@ struct tcs_handle {
   cudaStream_t stream = nullptr;   // internal stream all work runs on
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   int64_t launches = 0;
+  cudaEvent_t prof_ev[2 * 16] = {};   // tcs_score_profiled: begin/end per conv id
+  bool profiling = false;
 
   std::map<std::string, HostTensor> host_w;
   bool finalized = false;
@@ -154,6 +156,7 @@ struct tcs_handle {
     if (ev_in) cudaEventDestroy(ev_in);
     if (ev_out) cudaEventDestroy(ev_out);
     if (ev_pinned) cudaEventDestroy(ev_pinned);
+    for (cudaEvent_t e : prof_ev) if (e) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
   }
 };
@@ -280,7 +283,19 @@ static int build_plans(tcs_handle* h) {
 }
 
 template <typename T>
+static int run_conv_inner(tcs_handle* h, int id, int B, cudaStream_t st);
+
+template <typename T>
 static int run_conv(tcs_handle* h, int id, int B, cudaStream_t st) {
+  if (!h->profiling) return run_conv_inner<T>(h, id, B, st);
+  TCS_CUDA(cudaEventRecord(h->prof_ev[2 * id], st));
+  TCS_CHECK(run_conv_inner<T>(h, id, B, st));
+  TCS_CUDA(cudaEventRecord(h->prof_ev[2 * id + 1], st));
+  return TCS_OK;
+}
+
+template <typename T>
+static int run_conv_inner(tcs_handle* h, int id, int B, cudaStream_t st) {
   ++h->launches;
   if (h->use_tc) {
     ConvTcPlan pl = h->plan[id];
@@ -541,7 +556,7 @@ int tcs_create(tcs_handle** out, const tcs_config* cfg) {
     h->fuse_gn = h->use_tc && !(e && atoi(e) == 0);
     h->fuse_first = !(e && atoi(e) == 0);
   }
-  h->chunk = cfg->chunk > 0 ? cfg->chunk : 256;
+  h->chunk = cfg->chunk > 0 ? cfg->chunk : 512;
   if (h->chunk % 2) h->chunk += 1;
   TCS_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   TCS_CUDA(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
@@ -675,6 +690,39 @@ int tcs_score(tcs_handle* h, const float* x, const float* t, const int64_t* y_ca
   TCS_CHECK(launch_cond_embed(h->ew, y_cat, y_cont, n, dup, h->cvec.as<float>(), st));
   TCS_CHECK(launch_time_embed(h->ew, t, n, h->tvec.as<float>(), st));
   TCS_CHECK(forward_all(h, x, h->cvec.as<float>(), h->tvec.as<float>(), 1, nullptr, 0, n, dup, guidance, eps_out, st));
+  return leave(h, user);
+}
+
+int tcs_score_profiled(tcs_handle* h, const float* x, const float* t, const int64_t* y_cat, const float* y_cont,
+                       int32_t n, float guidance, float* eps_out, float* conv_ms, float* total_ms, void* stream) {
+  TCS_CHECK(check_ready(h, "tcs_score_profiled"));
+  if (!x || !t || !y_cat || !y_cont || !eps_out || !conv_ms || !total_ms || n < 1)
+    return fail(TCS_ERR_BAD_ARGUMENT, "tcs_score_profiled: bad argument");
+  const int dup = guidance > 0.f ? 2 : 1;
+  if (n * dup > h->chunk) return fail(TCS_ERR_BAD_ARGUMENT, "tcs_score_profiled: n exceeds one pass (chunk)");
+  cudaStream_t user = static_cast<cudaStream_t>(stream);
+  TCS_CHECK(enter(h, user));
+  for (cudaEvent_t& e : h->prof_ev)
+    if (!e) TCS_CUDA(cudaEventCreate(&e));
+  TCS_CHECK(h->cvec.ensure(static_cast<size_t>(n) * dup * 96 * 4));
+  TCS_CHECK(h->tvec.ensure(static_cast<size_t>(n) * 96 * 4));
+  cudaStream_t st = h->stream;
+  TCS_CHECK(launch_cond_embed(h->ew, y_cat, y_cont, n, dup, h->cvec.as<float>(), st));
+  TCS_CHECK(launch_time_embed(h->ew, t, n, h->tvec.as<float>(), st));
+  PassArgs a;
+  a.x = x; a.cvec = h->cvec.as<float>(); a.tvec = h->tvec.as<float>(); a.tvec_stride = 1; a.step_ptr = nullptr;
+  a.trow_off = 0; a.ns = n; a.dup = dup; a.guidance = guidance; a.eps = eps_out;
+  h->profiling = true;
+  cudaError_t e0 = cudaEventRecord(h->prof_ev[30], st);
+  int rc = h->bf16 ? forward_chunk<__nv_bfloat16>(h, a, st, nullptr) : forward_chunk<float>(h, a, st, nullptr);
+  cudaError_t e1 = cudaEventRecord(h->prof_ev[31], st);
+  h->profiling = false;
+  TCS_CHECK(rc);
+  TCS_CUDA(e0);
+  TCS_CUDA(e1);
+  TCS_CUDA(cudaStreamSynchronize(st));
+  for (int id = 0; id < C_COUNT; ++id) TCS_CUDA(cudaEventElapsedTime(conv_ms + id, h->prof_ev[2 * id], h->prof_ev[2 * id + 1]));
+  TCS_CUDA(cudaEventElapsedTime(total_ms, h->prof_ev[30], h->prof_ev[31]));
   return leave(h, user);
 }
 

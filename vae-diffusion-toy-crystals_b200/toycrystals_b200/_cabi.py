@@ -52,6 +52,8 @@ SIGNATURES = {
     "tcs_last_error": (C.c_char_p, []),
     "tcs_debug_layer": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                     C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
+    "tcs_score_profiled": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float,
+                                     C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p]),
     "tcs_debug_conv": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
