@@ -331,7 +331,7 @@ def profile_kernels(model, sde, dev):
     out = {"conv_tflops": sum(flops) / (sum(conv_ms) * 1e-3) / 1e12, "conv_ms": sum(conv_ms), "images": images,
            "conv_share": sum(conv_ms) / (tots / reps), "per_layer": per_layer, "traffic": None}
     # the fused VP-SDE update, Philox noise in registers: 48 KiB of algorithmic traffic per sample
-    ns = 8192
+    ns = 32768
     xs = torch.randn((ns, 1, 64, 64), device=dev)
     es = torch.randn_like(xs)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -356,8 +356,8 @@ def main():
     ap.add_argument("--n", type=int, default=1024, help="samples per GPU per job")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--chunk", type=int, default=0)
-    ap.add_argument("--cpu-n", type=int, default=16)
-    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--cpu-n", type=int, default=64)
+    ap.add_argument("--cpu-steps", type=int, default=15)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
