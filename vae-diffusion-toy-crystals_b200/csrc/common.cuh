@@ -42,7 +42,8 @@ enum Epilogue : int {
   EPI_RAW_STATS = 0,  // fp32 [B,H,W,N] + bias, plus GroupNorm partial sums
   EPI_PADDED = 1,     // T [B,H+2,W+2,ldo] + bias (+ residual), halo written
   EPI_PLAIN = 2,      // T [M, ldo] + bias
-  EPI_GN_FUSED = 3    // tcgen05 engine only: bias + GroupNorm + SiLU from TMEM -> padded bf16 (halo written)
+  EPI_GN_FUSED = 3,   // tcgen05 engine only: bias + GroupNorm + SiLU from TMEM -> padded bf16 (halo written)
+  EPI_EPS = 4         // tcgen05 engine only: the 96 -> 1 output conv (N padded to 16) + CFG combine -> fp32 [n,4096]
 };
 
 struct ConvGeom {

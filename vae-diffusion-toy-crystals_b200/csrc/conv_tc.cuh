@@ -18,6 +18,9 @@ struct ConvTcParams {
   int kstages;              // pipeline stages (K iterations) per tile
   int nstage;               // smem ring depth
   uint32_t a_bytes, stage_bytes;
+  int pair;                 // EPI_EPS: 1 = the two sub-tiles are the same pixels of images 2i (cond) and 2i+1 (uncond)
+  float guidance;           // EPI_EPS with pair: eps = e_u + guidance (e_c - e_u)
+  int debug;                // TCS_DEBUG bits (timing experiments only): 1 = no inter-CTA wait, 2 = no pass-2 stores
   EpiArgs epi;
 };
 
@@ -44,6 +47,7 @@ void conv_tc_pack_weights(const ConvGeom& g, const float* w, __nv_bfloat16* out_
 int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, const void* src1,
                       const __nv_bfloat16* wpacked, int epi, const EpiArgs& ea, int sm_count);
 int conv_tc_launch(const ConvTcPlan& plan, cudaStream_t stream);
+int conv_tc_make_pair(ConvTcPlan* plan, const void* src, int B);
 // grid for B images (persistent: <= one CTA per SM; whole image groups for EPI_GN_FUSED)
 int conv_tc_grid(const ConvTcPlan& plan, int B, int sm_count);
 

@@ -139,6 +139,10 @@ struct tcs_handle {
   DevBuf p32_96a, p32_96b, p32_192a, p32_192h2, p32_192b;
   DevBuf p16_a, p16_b, p16_c, qkv, atty;
   ConvTcPlan plan[C_COUNT];
+  ConvTcPlan plan_eps, plan_eps_pair;     // 96 -> 1 output conv on the tensor pipe (N padded to 16)
+  DevBuf wpack_out;
+  const float* d_bias16 = nullptr;
+  bool tc_out = false;
 
   // per-call state
   DevBuf cvec, tvec, tvals, coef, x, xpred, d0, eps, step_ctr, ycat_tmp, ycont_tmp;
@@ -265,6 +269,17 @@ static int slots_of(tcs_handle* h, int id) {
 
 static int build_plans(tcs_handle* h) {
   if (!h->use_tc) return TCS_OK;
+  {
+    const char* e = getenv("TCS_TC_OUT");   // 0 = keep the CUDA-core out conv (A/B switch)
+    h->tc_out = !(e && atoi(e) == 0);
+    ConvGeom g = geom_of(C_U1B, h->chunk, 1);
+    g.ntot = 16;
+    EpiArgs ea{};
+    ea.bias = h->d_bias16; ea.out = nullptr; ea.ldo = 1;
+    TCS_CHECK(conv_tc_make_plan(&h->plan_eps, g, h->p64_b.p, nullptr, h->wpack_out.as<__nv_bfloat16>(), EPI_EPS, ea, h->sm_count));
+    h->plan_eps_pair = h->plan_eps;
+    TCS_CHECK(conv_tc_make_pair(&h->plan_eps_pair, h->p64_b.p, h->chunk));
+  }
   for (int id = 0; id < C_COUNT; ++id) {
     const ConvWiring w = wiring(h, id);
     const ConvGeom g = geom_of(id, h->chunk, w.in_pad);
@@ -419,7 +434,16 @@ static int forward_chunk(tcs_handle* h, const PassArgs& a, cudaStream_t st, TapR
   CONV_GN(C_U1B, h->raw64.p, 64, 96);
   // ---- out conv + CFG combine ------------------------------------------------------------------
   ++h->launches;
-  TCS_CHECK(launch_out_conv<T>(h->p64_b.as<T>(), h->d_wout, h->out_bias, a.ns, a.dup, a.guidance, a.eps, st));
+  if (h->use_tc && h->tc_out) {
+    ConvTcPlan pl = a.dup == 2 ? h->plan_eps_pair : h->plan_eps;
+    pl.p.n_mtiles = (a.dup == 2 ? B / 2 : B) * pl.p.tiles_per_img;
+    pl.p.guidance = a.guidance;
+    pl.p.epi.out = a.eps;
+    pl.grid = conv_tc_grid(pl, B, h->sm_count);
+    TCS_CHECK(conv_tc_launch(pl, st));
+  } else {
+    TCS_CHECK(launch_out_conv<T>(h->p64_b.as<T>(), h->d_wout, h->out_bias, a.ns, a.dup, a.guidance, a.eps, st));
+  }
   if (tap && tap->id == kNumTaps - 1) {
     const int64_t cnt = static_cast<int64_t>(a.ns) * 4096;
     if (cnt > tap->capacity) return fail(TCS_ERR_BAD_ARGUMENT, "tcs_debug_layer: output buffer too small");
@@ -614,7 +638,7 @@ int tcs_finalize_weights(tcs_handle* h) {
   for (int c = 0; c < 96; ++c)
     for (int k = 0; k < 9; ++k) wout[k * 96 + c] = wo.v[c * 9 + k];
   h->out_bias = h->host_w.at("out.bias").v[0];
-  const size_t extra = 96 * 16 + 96 * 9 + 9 * 96 + 256;
+  const size_t extra = 96 * 16 + 96 * 9 + 9 * 96 + 64 + 256;
   TCS_CHECK(h->arena.ensure((total + extra) * 4));
   float* base = h->arena.as<float>();
   size_t off = 0;
@@ -632,6 +656,9 @@ int tcs_finalize_weights(tcs_handle* h) {
     return TCS_OK;
   };
   const float* d_wsum = nullptr;
+  std::vector<float> bias16(16, 0.f);
+  bias16[0] = h->out_bias;
+  TCS_CHECK(put(bias16, &h->d_bias16));
   TCS_CHECK(put(wsum, &d_wsum));
   TCS_CHECK(put(w9, &h->d_w9));
   TCS_CHECK(put(wout, &h->d_wout));
@@ -661,6 +688,16 @@ int tcs_finalize_weights(tcs_handle* h) {
       TCS_CHECK(h->wpack[id].ensure(pk.size() * 4));
       TCS_CUDA(cudaMemcpy(h->wpack[id].p, pk.data(), pk.size() * 4, cudaMemcpyHostToDevice));
     }
+  }
+  if (h->use_tc) {   // out conv as a 16-channel GEMM: row 0 = out.weight, rows 1..15 zero
+    ConvGeom g = geom_of(C_U1B, 1, 1);
+    g.ntot = 16;
+    std::vector<float> w16(16 * 96 * 9, 0.f);
+    for (int k = 0; k < 96 * 9; ++k) w16[k] = wo.v[k];
+    std::vector<__nv_bfloat16> pk(conv_tc_packed_elems(g));
+    conv_tc_pack_weights(g, w16.data(), pk.data());
+    TCS_CHECK(h->wpack_out.ensure(pk.size() * 2));
+    TCS_CUDA(cudaMemcpy(h->wpack_out.p, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
   }
   TCS_CHECK(alloc_workspace(h));
   TCS_CHECK(build_plans(h));
