@@ -116,6 +116,55 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// ---- cta_group::2 (CTA pair) variants ---------------------------------------------------------------
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> rank 0
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_rank0(uint32_t bar) {   // arrive on CTA 0's copy of this barrier
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_512_2sm(uint32_t dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(dst_smem) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_512_2sm(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(taddr) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {   // arrives on this barrier in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(static_cast<uint16_t>(3)) : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile(
@@ -209,6 +258,20 @@ __device__ __forceinline__ void store_with_halo(__nv_bfloat16* obase, size_t pix
   }
 }
 
+// tile index -> (M tile, N tile).  With CTA pairs the two CTAs of a pair (consecutive tile indices) must share the
+// N tile, because one MMA reads the weight tile half from each of them.
+template <int CG>
+__device__ __forceinline__ void tile_to_mn(int tile, int n_ntiles, int& mt, int& nt) {
+  if (CG == 2) {
+    const int pt = tile >> 1;
+    nt = pt % n_ntiles;
+    mt = ((pt / n_ntiles) << 1) | (tile & 1);
+  } else {
+    mt = tile / n_ntiles;
+    nt = tile - mt * n_ntiles;
+  }
+}
+
 struct __align__(8) TcBarriers {
   uint64_t full[MAX_STAGES];
   uint64_t empty[MAX_STAGES];
@@ -217,7 +280,11 @@ struct __align__(8) TcBarriers {
   uint32_t tmem_base;
 };
 
-template <int N, int EPI, int MSUB>
+// CG = 2: the kernel runs as CTA pairs (cluster of 2).  Each CTA still owns its own M tile (its 128-row sub-tiles,
+// its TMEM accumulators, its epilogue), but one tcgen05.mma.cta_group::2 of the leader drives both tensor cores
+// with M = 256 and reads the weight tile HALF from each CTA's shared memory: every CTA fetches only N/2 weight
+// rows per stage, which halves the dominant L2 -> SM operand stream.
+template <int N, int EPI, int MSUB, int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapO,
@@ -251,13 +318,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(ptx::smem_u32(&bars.tmem_full[a]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bars.tmem_empty[a]), 4);
+      ptx::mbar_init(ptx::smem_u32(&bars.tmem_empty[a]), 4 * CG);
     }
     ptx::fence_barrier_init();
   }
-  if (warp == 1) ptx::tmem_alloc_512(ptx::smem_u32(&bars.tmem_base));
+  const uint32_t cta_rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;
+  constexpr int NB = N / CG;    // weight rows this CTA keeps per tap
+  if (warp == 1) {
+    if (CG == 2) ptx::tmem_alloc_512_2sm(ptx::smem_u32(&bars.tmem_base));
+    else ptx::tmem_alloc_512(ptx::smem_u32(&bars.tmem_base));
+  }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CG == 2) ptx::cluster_sync_all();   // peer barriers are initialised before anyone signals them
   ptx::tc_fence_after();
   const uint32_t tmem_base = bars.tmem_base;
 
@@ -265,7 +338,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     // ============================== TMA producer ==============================
     uint32_t stage = 0, phase = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int mt = tile / p.n_ntiles, nt = tile - mt * p.n_ntiles;
+      int mt, nt;
+      tile_to_mn<CG>(tile, p.n_ntiles, mt, nt);
       // pair mode (EPI_EPS + CFG): tile = the same Rt rows of images 2i and 2i+1, one window each
       const int rows_per_tile = p.pair ? p.Rt : p.Rt * MSUB;
       const int b = (mt / p.tiles_per_img) * (p.pair ? 2 : 1);
@@ -281,26 +355,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 const uint32_t full = ptx::smem_u32(&bars.full[stage]);
                 const uint32_t a_dst = smem_base + stage * p.stage_bytes;
                 const uint32_t b_dst = a_dst + p.a_bytes;
-                ptx::mbar_expect_tx(full, p.a_bytes + p.T * N * 64);
-                ptx::tma_load_4d(a_dst, mapA, full, cb * 32, kx + p.base_off[src],
-                                 p.stride * y0 + kyg + p.base_off[src], b);
-                if (p.pair)
-                  ptx::tma_load_4d(a_dst + p.a_bytes / 2, mapA, full, cb * 32, kx + p.base_off[src],
-                                   p.stride * y0 + kyg + p.base_off[src], b + 1);
-                for (int j = 0; j < p.T; ++j)
-                  ptx::tma_load_2d(b_dst + j * N * 64, &mapW, full, 0, (ks * p.T + j) * p.ntot + nt * N);
+                if (CG == 2) {
+                  // both CTAs' loads complete on the LEADER's full barrier; the leader arms it for both
+                  if (cta_rank == 0) ptx::mbar_expect_tx(full, 2 * (p.a_bytes + p.T * NB * 64));
+                  ptx::tma_load_4d_2sm(a_dst, mapA, full, cb * 32, kx + p.base_off[src],
+                                       p.stride * y0 + kyg + p.base_off[src], b);
+                  for (int j = 0; j < p.T; ++j)
+                    ptx::tma_load_2d_2sm(b_dst + j * NB * 64, &mapW, full, 0,
+                                         (ks * p.T + j) * p.ntot + nt * N + static_cast<int>(cta_rank) * NB);
+                } else {
+                  ptx::mbar_expect_tx(full, p.a_bytes + p.T * N * 64);
+                  ptx::tma_load_4d(a_dst, mapA, full, cb * 32, kx + p.base_off[src],
+                                   p.stride * y0 + kyg + p.base_off[src], b);
+                  if (p.pair)
+                    ptx::tma_load_4d(a_dst + p.a_bytes / 2, mapA, full, cb * 32, kx + p.base_off[src],
+                                     p.stride * y0 + kyg + p.base_off[src], b + 1);
+                  for (int j = 0; j < p.T; ++j)
+                    ptx::tma_load_2d(b_dst + j * N * 64, &mapW, full, 0, (ks * p.T + j) * p.ntot + nt * N);
+                }
               }
               __syncwarp();
               if (++stage == static_cast<uint32_t>(p.nstage)) { stage = 0; phase ^= 1; }
             }
       }
     }
-  } else if (warp == 1) {
-    // ============================== MMA issuer ================================
-    constexpr uint32_t idesc = make_idesc(128, N);
+  } else if (warp == 1 && cta_rank == 0) {
+    // ============================== MMA issuer (leader CTA only when CG == 2) ====
+    constexpr uint32_t idesc = make_idesc(128 * CG, N);
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
     const uint32_t row_shift = p.W * 64;  // one image row inside the window
     const uint32_t sub_stride = p.pair ? p.a_bytes / 2 : p.Rt * row_shift;  // second sub-tile: next window / next rows
+    const uint32_t a_inc_j = row_shift >> 4, a_inc_sub = sub_stride >> 4;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       ptx::mbar_wait(ptx::smem_u32(&bars.tmem_empty[acc]), acc_phase ^ 1);
       ptx::tc_fence_after();
@@ -308,29 +393,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         ptx::mbar_wait(ptx::smem_u32(&bars.full[stage]), phase);
         ptx::tc_fence_after();
         if (lane == 0) {
+          // descriptors: one base per operand and stage, then 16-byte-unit increments (the issuing thread must
+          // sustain one MMA per 48 tensor cycles at N = 96, so the per-MMA scalar work is kept to a few adds)
           const uint32_t a_base = smem_base + stage * p.stage_bytes;
-          const uint32_t b_base = a_base + p.a_bytes;
+          const uint64_t adesc = make_desc_sw64(a_base), bdesc = make_desc_sw64(a_base + p.a_bytes);
+          const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
           for (int j = 0; j < p.T; ++j) {
 #pragma unroll
             for (int sub = 0; sub < MSUB; ++sub) {
-              const uint32_t a_tap = a_base + j * row_shift + sub * sub_stride;
-              const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE + sub * N;
 #pragma unroll
               for (int k = 0; k < 2; ++k) {
-                ptx::umma_bf16(d_tmem, make_desc_sw64(a_tap + k * 32), make_desc_sw64(b_base + j * N * 64 + k * 32),
-                               idesc, (ks | j | k) != 0 ? 1u : 0u);
+                const uint64_t ad = adesc + (j * a_inc_j + sub * a_inc_sub + k * 2);
+                const uint64_t bd = bdesc + (j * ((NB * 64) >> 4) + k * 2);
+                const uint32_t accum = (ks | j | k) != 0 ? 1u : 0u;
+                if (CG == 2) ptx::umma_bf16_2sm(d_tmem + sub * N, ad, bd, idesc, accum);
+                else ptx::umma_bf16(d_tmem + sub * N, ad, bd, idesc, accum);
               }
             }
           }
-          ptx::umma_commit(ptx::smem_u32(&bars.empty[stage]));
-          if (ks == p.kstages - 1) ptx::umma_commit(ptx::smem_u32(&bars.tmem_full[acc]));
+          if (CG == 2) {
+            ptx::umma_commit_2sm(ptx::smem_u32(&bars.empty[stage]));
+            if (ks == p.kstages - 1) ptx::umma_commit_2sm(ptx::smem_u32(&bars.tmem_full[acc]));
+          } else {
+            ptx::umma_commit(ptx::smem_u32(&bars.empty[stage]));
+            if (ks == p.kstages - 1) ptx::umma_commit(ptx::smem_u32(&bars.tmem_full[acc]));
+          }
         }
         __syncwarp();
         if (++stage == static_cast<uint32_t>(p.nstage)) { stage = 0; phase ^= 1; }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-  } else {
+  } else if (warp >= 2) {
     // ============================== epilogue (2 groups x 4 warps) ================
     // Group grp = 0/1 owns TMEM accumulator set grp and therefore every second tile of this CTA; inside a
     // group warp q = warp % 4 reads TMEM lane quarter q: 32 pixel rows x all MSUB*N = 192 columns.  A group has
@@ -344,7 +438,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     uint32_t acc_phase = 0;
     EpiGroupSmem* gsm = &fs->grp[grp];
     for (int tile = blockIdx.x + grp * gridDim.x; tile < n_tiles; tile += 2 * gridDim.x, acc_phase ^= 1) {
-      const int mt = tile / p.n_ntiles, nt = tile - mt * p.n_ntiles;
+      int mt, nt;
+      tile_to_mn<CG>(tile, p.n_ntiles, mt, nt);
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_STRIDE;
       ptx::mbar_wait(ptx::smem_u32(&bars.tmem_full[acc]), acc_phase);
       ptx::tc_fence_after();
@@ -596,15 +691,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars.tmem_empty[acc]));
+      if (lane == 0) {
+        if (CG == 2) ptx::mbar_arrive_rank0(ptx::smem_u32(&bars.tmem_empty[acc]));   // the leader's MMA warp waits on it
+        else ptx::mbar_arrive(ptx::smem_u32(&bars.tmem_empty[acc]));
+      }
     }
     if (EPI == EPI_RAW_STATS && lane == 0) ptx::bulk_wait_all();   // staged stores have left shared memory
   }
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (CG == 2) ptx::cluster_sync_all();   // the leader's MMAs read the peer's shared memory / write its TMEM
   ptx::tc_fence_after();
-  if (warp == 1) ptx::tmem_dealloc_512(tmem_base);
+  if (warp == 1) {
+    if (CG == 2) ptx::tmem_dealloc_512_2sm(tmem_base);
+    else ptx::tmem_dealloc_512(tmem_base);
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -705,38 +807,47 @@ int conv_tc_grid(const ConvTcPlan& pl, int B, int sm_count) {
   const int tiles = (pl.p.pair ? B / 2 : B) * pl.p.tiles_per_img * pl.p.n_ntiles;
   int grid = tiles < sm_count ? tiles : sm_count;
   if (pl.epi == EPI_GN_FUSED) grid = grid / pl.p.tiles_per_img * pl.p.tiles_per_img;  // whole image groups only
+  if (pl.cg == 2) grid &= ~1;                                                         // whole CTA pairs
   return grid;
 }
 
-template <int N, int EPI, int MSUB>
+template <int N, int EPI, int MSUB, int CG>
 static int launch_t(const ConvTcPlan& pl, cudaStream_t st) {
-  auto kern = conv_tc_kernel<N, EPI, MSUB>;
+  auto kern = conv_tc_kernel<N, EPI, MSUB, CG>;
   static bool attr_done = false;
   if (!attr_done) {
     TCS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
     attr_done = true;
   }
-  if (EPI == EPI_GN_FUSED) {
-    // the CTAs of an image group wait on one another: zero the arrival counters, launch co-resident
+  if (EPI == EPI_GN_FUSED)   // the CTAs of an image group wait on one another: zero the arrival counters
     TCS_CUDA(cudaMemsetAsync(pl.p.epi.counters, 0, sizeof(int) * (pl.p.n_mtiles / pl.p.tiles_per_img), st));
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(pl.grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = pl.smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeCooperative;
-    at[0].val.cooperative = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    TCS_CUDA(cudaLaunchKernelEx(&cfg, kern, pl.mapA[0], pl.mapA[1], pl.mapW, pl.mapO, pl.p));
-  } else {
-    kern<<<pl.grid, TC_THREADS, pl.smem, st>>>(pl.mapA[0], pl.mapA[1], pl.mapW, pl.mapO, pl.p);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(pl.grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = pl.smem; cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (EPI == EPI_GN_FUSED && CG == 1) {   // co-resident launch (with CTA pairs the grid <= #SMs, 1 CTA/SM guarantees it)
+    at[na].id = cudaLaunchAttributeCooperative;
+    at[na].val.cooperative = 1;
+    ++na;
   }
+  if (CG == 2) {
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = 2; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = at; cfg.numAttrs = na;
+  TCS_CUDA(cudaLaunchKernelEx(&cfg, kern, pl.mapA[0], pl.mapA[1], pl.mapW, pl.mapO, pl.p));
   TCS_CUDA(cudaGetLastError());
   return TCS_OK;
 }
 
 int conv_tc_launch(const ConvTcPlan& pl, cudaStream_t st) {
   if (!pl.valid) return fail(TCS_ERR_STATE, "conv_tc_launch: plan not built");
-#define TCS_TC_CASE(NN, EE, MM) \
-  if (pl.N == NN && pl.epi == EE && pl.msub == MM) return launch_t<NN, EE, MM>(pl, st);
+#define TCS_TC_CASE(NN, EE, MM)                                                        \
+  if (pl.N == NN && pl.epi == EE && pl.msub == MM) {                                    \
+    if (pl.cg == 2) { if constexpr (NN >= 96) return launch_t<NN, EE, MM, 2>(pl, st); } \
+    else return launch_t<NN, EE, MM, 1>(pl, st);                                        \
+  }
   TCS_TC_CASE(96, EPI_RAW_STATS, 2)
   TCS_TC_CASE(96, EPI_PADDED, 2)
   TCS_TC_CASE(96, EPI_PLAIN, 2)
@@ -766,6 +877,10 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, con
   // MAC) and give each of the 8 epilogue warps a 32-row x 96-column unit; N = 192: one sub-tile, the
   // epilogue warps split its columns in halves.  Either way two accumulator sets double-buffer in TMEM.
   pl.msub = pl.N == 192 ? 1 : 2;
+  {
+    const char* e = getenv("TCS_CG");   // 1 = single-CTA MMA everywhere (A/B switch)
+    pl.cg = (pl.N >= 96 && !(e && atoi(e) == 1)) ? 2 : 1;
+  }
   if (g.H % (pl.msub * (128 / g.W))) return fail(TCS_ERR_UNSUPPORTED, "conv_tc: image height not a multiple of the tile");
   p.debug = getenv("TCS_DEBUG") ? atoi(getenv("TCS_DEBUG")) : 0;
   stage_shape(g, &p.T, &p.KYG, &p.KW);
@@ -781,7 +896,7 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, con
   p.n_ntiles = g.ntot / pl.N;
   p.kstages = conv_tc_kstages(g);
   p.a_bytes = static_cast<uint32_t>(p.WR) * g.W * 64;
-  p.stage_bytes = (p.a_bytes + p.T * pl.N * 64 + 1023u) & ~1023u;
+  p.stage_bytes = (p.a_bytes + p.T * (pl.N / pl.cg) * 64 + 1023u) & ~1023u;
   const size_t budget = 227 * 1024 - 2048 - 1024 - EPI_SLAB_BYTES - EPI_BIAS_BYTES - EPI_FUSED_BYTES;
   p.nstage = static_cast<int>(budget / p.stage_bytes);
   if (p.nstage > MAX_STAGES) p.nstage = MAX_STAGES;
@@ -817,7 +932,7 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, con
   {
     cuuint64_t dims[2] = {32, static_cast<cuuint64_t>(p.kstages) * p.T * g.ntot};
     cuuint64_t strides[1] = {64};
-    cuuint32_t box[2] = {32, static_cast<cuuint32_t>(pl.N)};
+    cuuint32_t box[2] = {32, static_cast<cuuint32_t>(pl.N / pl.cg)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(&pl.mapW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(wpacked), dims,
                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,

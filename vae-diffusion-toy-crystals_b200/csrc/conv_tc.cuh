@@ -32,6 +32,7 @@ struct ConvTcPlan {
   int N;       // N tile (96 or 192)
   int epi;     // Epilogue
   int msub;    // 128-row sub-tiles per CTA tile
+  int cg;      // 1 = one CTA per MMA, 2 = CTA pairs (tcgen05 cta_group::2, weights split across the pair)
   int grid;
   size_t smem;
   bool valid = false;
