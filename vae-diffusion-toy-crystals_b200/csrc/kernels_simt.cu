@@ -129,7 +129,7 @@ template <> __device__ __forceinline__ void store_pair<__nv_bfloat16>(__nv_bfloa
 // sum_p conv_c(p)^2 = sum_{k,l} w_ck w_cl R(k-l)  with  R(d) = sum_p x_p x_{p+d}  (circular autocorrelation at
 // the 25 lags |dy|,|dx| <= 2), both exact identities; R and the quadratic forms are evaluated in fp64.
 // Each sample is split over FC_SPLIT blocks (row bands); every block recomputes the (cheap) statistics.
-constexpr int FC_SPLIT = 2;
+constexpr int FC_SPLIT = 4;
 template <typename T>
 __global__ void __launch_bounds__(384) first_conv_gn_kernel(const float* __restrict__ x, const float* __restrict__ w9,
                                                            const float* __restrict__ tvec, int tvec_stride,
@@ -224,7 +224,16 @@ __global__ void __launch_bounds__(384) first_conv_gn_kernel(const float* __restr
   }
   __syncthreads();
   const int g = op / 6;
-  const float ga0 = gamma[oc], ga1 = gamma[oc + 1], be0 = beta[oc], be1 = beta[oc + 1];
+  // y = conv * sc + sh with sc = rstd * gamma, sh = (bias - mean) * sc + beta   (per branch u, per channel)
+  float sc0[2], sh0[2], sc1[2], sh1[2];
+  {
+    const float ga0 = gamma[oc], ga1 = gamma[oc + 1], be0 = beta[oc], be1 = beta[oc + 1];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      sc0[u] = s_rstd[u][g] * ga0; sh0[u] = (b0[u] - s_mean[u][g]) * sc0[u] + be0;
+      sc1[u] = s_rstd[u][g] * ga1; sh1[u] = (b1[u] - s_mean[u][g]) * sc1[u] + be1;
+    }
+  }
   constexpr int PO = IMG + 2;
   const int p_begin = band * (IMG_PIX / FC_SPLIT), p_end = p_begin + IMG_PIX / FC_SPLIT;
   for (int p = p_begin + pg; p < p_end; p += 8) {
@@ -239,9 +248,11 @@ __global__ void __launch_bounds__(384) first_conv_gn_kernel(const float* __restr
         c1 = fmaf(w1[ky * 3 + kx], xv, c1);
       }
     const int wy = halo_wrap(yy, IMG), wx = halo_wrap(xx, IMG);
-    for (int u = 0; u < dup; ++u) {
-      const float y0 = silu_f<FAST>(((c0 + b0[u]) - s_mean[u][g]) * s_rstd[u][g] * ga0 + be0);
-      const float y1 = silu_f<FAST>(((c1 + b1[u]) - s_mean[u][g]) * s_rstd[u][g] * ga1 + be1);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u >= dup) break;
+      const float y0 = silu_f<FAST>(fmaf(c0, sc0[u], sh0[u]));
+      const float y1 = silu_f<FAST>(fmaf(c1, sc1[u], sh1[u]));
       const size_t base = ((static_cast<size_t>(i) * dup + u) * PO + yy + 1) * PO + xx + 1;
       store_pair<T>(out + base * 96 + oc, y0, y1);
       if (wy) store_pair<T>(out + (base + static_cast<long long>(wy) * PO) * 96 + oc, y0, y1);
@@ -292,7 +303,12 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const float* __restric
 }
 
 template <bool FAST> __device__ __forceinline__ float silu_f(float v) {
-  if constexpr (FAST) return __fdividef(v, 1.0f + __expf(-v));
+  if constexpr (FAST) {   // y*sigmoid(y) = h + h*tanh(h), h = y/2: one MUFU
+    const float h = 0.5f * v;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+  }
   return v / (1.0f + expf(-v));
 }
 
@@ -422,6 +438,8 @@ template int launch_gn_stats<__nv_bfloat16>(const __nv_bfloat16*, int, int, int,
 // bilinear x2, align_corners=False, edge clamp (nn.Upsample, sde_score_model.py:217,221)
 // value = wy0*(wx0*a + wx1*b) + wy1*(wx0*c + wx1*d)
 // ------------------------------------------------------------------------------------------
+// thread = (input pixel, 8 channels): reads the clamped 3x3 input neighbourhood once and produces the 2x2 output
+// block (2iy..2iy+1, 2ix..2ix+1): horizontal lerps first, then vertical (the order PyTorch evaluates them in).
 template <typename T>
 __global__ void __launch_bounds__(256) upsample2x_kernel(const T* __restrict__ in, int h, int w, int C,
                                                         T* __restrict__ out, long long total) {
@@ -430,40 +448,60 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const T* __restrict__ i
   const int cv = C / 8;
   const int c = static_cast<int>(e % cv) * 8;
   long long r = e / cv;
-  const int H = 2 * h, W = 2 * w;
-  const int x = static_cast<int>(r % W); r /= W;
-  const int y = static_cast<int>(r % H);
-  const int b = static_cast<int>(r / H);
-  const float sy = fmaxf(0.5f * (y + 0.5f) - 0.5f, 0.f), sx = fmaxf(0.5f * (x + 0.5f) - 0.5f, 0.f);
-  const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
-  const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
-  const float ly = sy - y0, lx = sx - x0;
-  const float wy0 = 1.f - ly, wx0 = 1.f - lx;
+  const int ix = static_cast<int>(r % w); r /= w;
+  const int iy = static_cast<int>(r % h);
+  const int b = static_cast<int>(r / h);
   const int wp = w + 2, hp = h + 2;
+  const int H = 2 * h, W = 2 * w, Wp = W + 2, Hp = H + 2;
+  const int ys[3] = {max(iy - 1, 0), iy, min(iy + 1, h - 1)};
+  const int xs[3] = {max(ix - 1, 0), ix, min(ix + 1, w - 1)};
   const T* ib = in + static_cast<size_t>(b) * hp * wp * C + c;
-  Vec8<T> va, vb, vc, vd;
-  va.load(ib + (static_cast<size_t>(y0 + 1) * wp + x0 + 1) * C);
-  vb.load(ib + (static_cast<size_t>(y0 + 1) * wp + x1 + 1) * C);
-  vc.load(ib + (static_cast<size_t>(y1 + 1) * wp + x0 + 1) * C);
-  vd.load(ib + (static_cast<size_t>(y1 + 1) * wp + x1 + 1) * C);
-  float fa[8], fb[8], fc[8], fd[8], o[8];
-  va.get(fa); vb.get(fb); vc.get(fc); vd.get(fd);
+  float hl[3][8], hr[3][8];   // horizontal lerps for output columns 2ix (left) and 2ix+1 (right), per input row
 #pragma unroll
-  for (int k = 0; k < 8; ++k) o[k] = wy0 * (wx0 * fa[k] + lx * fb[k]) + ly * (wx0 * fc[k] + lx * fd[k]);
-  Vec8<T> ov;
-  ov.set(o);
-  const int Wp = W + 2, Hp = H + 2;
-  const int wy = halo_wrap(y, H), wx = halo_wrap(x, W);
-  const size_t base = (static_cast<size_t>(b) * Hp + y + 1) * Wp + x + 1;
-  ov.store(out + base * C + c);
-  if (wy) ov.store(out + (base + static_cast<long long>(wy) * Wp) * C + c);
-  if (wx) ov.store(out + (base + wx) * C + c);
-  if (wy && wx) ov.store(out + (base + static_cast<long long>(wy) * Wp + wx) * C + c);
+  for (int j = 0; j < 3; ++j) {
+    Vec8<T> v0, v1, v2;
+    v0.load(ib + (static_cast<size_t>(ys[j] + 1) * wp + xs[0] + 1) * C);
+    v1.load(ib + (static_cast<size_t>(ys[j] + 1) * wp + xs[1] + 1) * C);
+    v2.load(ib + (static_cast<size_t>(ys[j] + 1) * wp + xs[2] + 1) * C);
+    float f0[8], f1[8], f2[8];
+    v0.get(f0); v1.get(f1); v2.get(f2);
+    // output x = 2ix: src = ix - 0.25 -> (ix-1, ix) weights (0.25, 0.75), clamped at ix = 0 to (ix, ix) = f1
+    // output x = 2ix+1: src = ix + 0.25 -> (ix, ix+1) weights (0.75, 0.25); the clamp is in xs[2]
+    const float wl0 = ix == 0 ? 1.0f : 0.25f, wl1 = ix == 0 ? 0.0f : 0.75f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      hl[j][k] = ix == 0 ? f1[k] : (wl0 * f0[k] + wl1 * f1[k]);
+      hr[j][k] = 0.75f * f1[k] + 0.25f * f2[k];
+    }
+  }
+#pragma unroll
+  for (int py = 0; py < 2; ++py) {
+    const int y = 2 * iy + py;
+#pragma unroll
+    for (int px = 0; px < 2; ++px) {
+      const int x = 2 * ix + px;
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float t0 = px ? hr[0][k] : hl[0][k], t1 = px ? hr[1][k] : hl[1][k], t2 = px ? hr[2][k] : hl[2][k];
+        if (py == 0) o[k] = iy == 0 ? t1 : (0.25f * t0 + 0.75f * t1);
+        else o[k] = 0.75f * t1 + 0.25f * t2;
+      }
+      Vec8<T> ov;
+      ov.set(o);
+      const int wy = halo_wrap(y, H), wx = halo_wrap(x, W);
+      const size_t base = (static_cast<size_t>(b) * Hp + y + 1) * Wp + x + 1;
+      ov.store(out + base * C + c);
+      if (wy) ov.store(out + (base + static_cast<long long>(wy) * Wp) * C + c);
+      if (wx) ov.store(out + (base + wx) * C + c);
+      if (wy && wx) ov.store(out + (base + static_cast<long long>(wy) * Wp + wx) * C + c);
+    }
+  }
 }
 template <typename T>
 int launch_upsample2x(const T* in, int B, int h, int w, int C, T* out, cudaStream_t st) {
   if (B <= 0) return TCS_OK;
-  const long long total = static_cast<long long>(B) * 4 * h * w * (C / 8);
+  const long long total = static_cast<long long>(B) * h * w * (C / 8);
   upsample2x_kernel<T><<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(in, h, w, C, out, total);
   TCS_CUDA(cudaGetLastError());
   return TCS_OK;
