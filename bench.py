@@ -153,6 +153,35 @@ def cpu_reference_samples_per_sec(n: int = 16, steps: int = 3, repeats: int = 1)
     return sps, cores, desc
 
 
+def cuda_eager_reference_samples_per_sec(n: int = 256, steps: int = 2, tf32: bool = True):
+    """The reference algorithm as eager PyTorch ON THE GPU (the oracle's torch.nn.functional calls are the
+    reference's own ATen/cuDNN ops; cuDNN TF32 convs = PyTorch's default, as the reference leaves it)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import toycrystals_oracle as orc
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.backends.cudnn.allow_tf32 = tf32
+    torch.backends.cuda.matmul.allow_tf32 = tf32
+    sd = {k: v.to(dev) for k, v in orc.default_init_state_dict(1).items()}
+    y_cat, y_cont = orc.condition_grid(n, 4, 4, device=dev)
+    x0 = torch.randn((n, 1, 64, 64), device=dev)
+    noise = [torch.randn((n, 1, 64, 64), device=dev) for _ in range(steps)]
+    sch = orc.Schedule(0.1, 30.0)
+    best = None
+    for rep in range(3):
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        orc.sample(sd, orc.DEFAULT_CFG, sch, y_cat, y_cont, x0, "sde", steps, CFG, T_END, noise, keep_trace=False)
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        if rep:
+            best = dt if best is None else min(best, dt)
+    sps = n / (best / (steps + 1) * (SDE_STEPS + 1))
+    return {"value": sps, "unit": "samples/s", "tf32": tf32,
+            "sample": f"eager PyTorch {torch.__version__} on {torch.cuda.get_device_name(dev)}, n={n}, {steps + 1} CFG evaluations "
+                      f"in {best:.3f}s, extrapolated linearly to {SDE_STEPS + 1}"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -173,6 +202,13 @@ def run_reference(args):
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    try:   # context only (north_star quotes its target against the reference's CUDA eager sampler)
+        import torch
+        if torch.cuda.is_available() and not args.no_cuda_eager:
+            line["reference_cuda_eager"] = [cuda_eager_reference_samples_per_sec(tf32=True),
+                                            cuda_eager_reference_samples_per_sec(tf32=False)]
+    except Exception as e:  # noqa: BLE001
+        line["reference_cuda_eager"] = {"error": str(e)[:200]}
     print(json.dumps(line), flush=True)
     return 0
 
@@ -329,8 +365,14 @@ def profile_kernels(model, sde, dev):
     conv_ms = [a / reps for a in acc]
     flops = [2e6 * m * images for m in TC_CONV_MMAC]
     per_layer = {k: round(f / (ms * 1e-3) / 1e12, 1) for k, f, ms in zip(TC_CONV_NAMES, flops, conv_ms)}
+    traffic = None   # DRAM bytes of the same 15 launches from the committed `ncu --set full` capture (256 images)
+    tp = os.path.join(ROOT, "profiles", "r1_conv_ncu_full.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        if tj.get("images_per_pass") == images:
+            traffic = tj["traffic_bytes_per_pass"]
     out = {"conv_tflops": sum(flops) / (sum(conv_ms) * 1e-3) / 1e12, "conv_ms": sum(conv_ms), "images": images,
-           "conv_share": sum(conv_ms) / (tots / reps), "per_layer": per_layer, "traffic": None}
+           "conv_share": sum(conv_ms) / (tots / reps), "per_layer": per_layer, "traffic": traffic}
     # the fused VP-SDE update, Philox noise in registers: 48 KiB of algorithmic traffic per sample
     ns = 32768
     xs = torch.randn((ns, 1, 64, 64), device=dev)
@@ -360,6 +402,7 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=64)
     ap.add_argument("--cpu-steps", type=int, default=15)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cuda-eager", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
