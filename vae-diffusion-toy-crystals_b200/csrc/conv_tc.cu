@@ -241,6 +241,71 @@ __device__ __forceinline__ float silu_fast(float y) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
   return fmaf(h, t, h);
 }
+__device__ __forceinline__ void store_with_halo(__nv_bfloat16* obase, size_t pix, int wy, int wx, int Wp, int ldo,
+                                                int ch, const uint32_t* pk);
+
+// packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2): halves the epilogue's floating-point instruction count
+__device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void add2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x));
+  return t;
+}
+__device__ __forceinline__ void st_shared_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+// 32 pixels (one per lane, consecutive in an image row) x 32 bf16 channels -> padded NHWC output.
+// W >= 32: the warp stages the 2 KB block in a SWIZZLE_64B slab and one lane TMA-stores it (plus the wrapped
+// row copy); only the lanes on the left/right image border write their column-halo copy themselves.
+// W == 16: plain per-lane 16-byte stores (the 16x16 layers are small).
+__device__ __forceinline__ void store_padded_block(const CUtensorMap* mapO, bool use_tma, uint32_t slab, uint32_t& slab_buf,
+                                                   int lane, __nv_bfloat16* obase, size_t pix, int wy, int wx, int Wp,
+                                                   int ldo, int ch, int img, int y, int x, const uint32_t* pk) {
+  if (!use_tma) {
+    store_with_halo(obase, pix, wy, wx, Wp, ldo, ch, pk);
+    return;
+  }
+  if (lane == 0) ptx::bulk_wait_read<1>();   // the slab half written two blocks ago has been read
+  __syncwarp();
+  const uint32_t base = slab + slab_buf * 2048;
+  const uint32_t dst = base + lane * 64;
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) st_shared_u4(dst + ((j ^ sw) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+  ptx::fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) {   // lane 0 holds the first pixel of the block: (y, x) -> padded (y+1, x+1)
+    tma_store_4d(mapO, base, ch, x + 1, y + 1, img);
+    if (wy) tma_store_4d(mapO, base, ch, x + 1, y + 1 + wy, img);
+    ptx::bulk_commit();
+  }
+  slab_buf ^= 1;
+  if (wx) {   // column halo (and the corner when this pixel is also on a border row)
+    uint4* d0 = reinterpret_cast<uint4*>(obase + (pix + wx) * ldo + ch);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d0[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+    if (wy) {
+      uint4* d1 = reinterpret_cast<uint4*>(obase + (pix + static_cast<long long>(wy) * Wp + wx) * ldo + ch);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) d1[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+    }
+  }
+}
+
 // 32 bf16 channels of one pixel -> padded NHWC tensor, duplicated onto the circular halo where needed
 __device__ __forceinline__ void store_with_halo(__nv_bfloat16* obase, size_t pix, int wy, int wx, int Wp, int ldo,
                                                 int ch, const uint32_t* pk) {
@@ -311,7 +376,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     ptx::prefetch_tmap(&mapA0);
     ptx::prefetch_tmap(&mapA1);
     ptx::prefetch_tmap(&mapW);
-    if (EPI == EPI_RAW_STATS) ptx::prefetch_tmap(&mapO);
+    if (EPI != EPI_PLAIN && EPI != EPI_EPS) ptx::prefetch_tmap(&mapO);
     for (int s = 0; s < p.nstage; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bars.full[s]), 1);
       ptx::mbar_init(ptx::smem_u32(&bars.empty[s]), 1);
@@ -435,8 +500,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const int HW = p.H * p.W;
     const int Wp = p.W + 2, Hp = p.H + 2;
     const uint32_t acc = grp;
-    uint32_t acc_phase = 0;
+    uint32_t acc_phase = 0, slab_buf = 0;
+    (void)slab_buf;
     EpiGroupSmem* gsm = &fs->grp[grp];
+    const uint32_t slab = slab_base + static_cast<uint32_t>(e) * 4096;      // this warp's 2 x 2 KB staging halves
+    const bool use_tma_out = p.W >= 32 && !(p.debug & 4);
     for (int tile = blockIdx.x + grp * gridDim.x; tile < n_tiles; tile += 2 * gridDim.x, acc_phase ^= 1) {
       int mt, nt;
       tile_to_mn<CG>(tile, p.n_ntiles, mt, nt);
@@ -467,9 +535,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         constexpr int CPGN = N / 8;            // channels per group: 12 or 24
         const int G = p.tiles_per_img;
         const int img = mt / G;
-        float gs[8], gq[8];
+        float gs[8], gq[8];        // per group: (even-column, odd-column) partial sums kept packed
+        float gs1[8], gq1[8];
 #pragma unroll
-        for (int g = 0; g < 8; ++g) gs[g] = gq[g] = 0.f;
+        for (int g = 0; g < 8; ++g) gs[g] = gq[g] = gs1[g] = gq1[g] = 0.f;
 #pragma unroll
         for (int u = 0; u < 2; ++u) {          // the two 96-column units: sub-tile u (MSUB 2) or column half u
           const int ch0 = (MSUB == 2) ? 0 : u * 96;
@@ -481,16 +550,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
               const float4 b4 = *reinterpret_cast<const float4*>(bias_s + ch0 + c0 + i);
-              const float t0 = v[i] + b4.x, t1 = v[i + 1] + b4.y, t2 = v[i + 2] + b4.z, t3 = v[i + 3] + b4.w;
-              gs[(ch0 + c0 + i) / CPGN] += t0; gq[(ch0 + c0 + i) / CPGN] += t0 * t0;
-              gs[(ch0 + c0 + i + 1) / CPGN] += t1; gq[(ch0 + c0 + i + 1) / CPGN] += t1 * t1;
-              gs[(ch0 + c0 + i + 2) / CPGN] += t2; gq[(ch0 + c0 + i + 2) / CPGN] += t2 * t2;
-              gs[(ch0 + c0 + i + 3) / CPGN] += t3; gq[(ch0 + c0 + i + 3) / CPGN] += t3 * t3;
+              float t0, t1, t2, t3;
+              add2(t0, t1, v[i], v[i + 1], b4.x, b4.y);
+              add2(t2, t3, v[i + 2], v[i + 3], b4.z, b4.w);
+              const int g0 = (ch0 + c0 + i) / CPGN, g1 = (ch0 + c0 + i + 2) / CPGN;   // pairs never straddle a group
+              add2(gs[g0], gs1[g0], gs[g0], gs1[g0], t0, t1);
+              fma2(gq[g0], gq1[g0], t0, t1, t0, t1, gq[g0], gq1[g0]);
+              add2(gs[g1], gs1[g1], gs[g1], gs1[g1], t2, t3);
+              fma2(gq[g1], gq1[g1], t2, t3, t2, t3, gq[g1], gq1[g1]);
             }
           }
         }
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
+          gs[g] += gs1[g];
+          gq[g] += gq1[g];
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) {
             gs[g] += __shfl_xor_sync(0xffffffffu, gs[g], o);
@@ -537,8 +611,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         for (int c = threadIdx.x - 64 - grp * 128; c < N; c += 128) {
           const int g = c / CPGN;
           const float sc = gsm->rstd[g] * fs->gamma[c];
-          gsm->scale[c] = sc;
-          gsm->shift[c] = (bias_s[c] - gsm->mean[g]) * sc + fs->beta[c];
+          gsm->scale[c] = 0.5f * sc;                                                  // h = y / 2 = v * scale + shift
+          gsm->shift[c] = 0.5f * ((bias_s[c] - gsm->mean[g]) * sc + fs->beta[c]);
         }
         epi_bar_sync(grp);
         __nv_bfloat16* obase = static_cast<__nv_bfloat16*>(p.epi.out);
@@ -562,12 +636,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             for (int i = 0; i < 32; i += 4) {
               const float4 s4 = *reinterpret_cast<const float4*>(gsm->scale + ch0 + c0 + i);
               const float4 h4 = *reinterpret_cast<const float4*>(gsm->shift + ch0 + c0 + i);
-              const float y0 = silu_fast(fmaf(v[i], s4.x, h4.x)), y1 = silu_fast(fmaf(v[i + 1], s4.y, h4.y));
-              const float y2 = silu_fast(fmaf(v[i + 2], s4.z, h4.z)), y3 = silu_fast(fmaf(v[i + 3], s4.w, h4.w));
+              float h0, h1, h2, h3, y0, y1, y2, y3;
+              fma2(h0, h1, v[i], v[i + 1], s4.x, s4.y, h4.x, h4.y);          // h = y/2
+              fma2(h2, h3, v[i + 2], v[i + 3], s4.z, s4.w, h4.z, h4.w);
+              fma2(y0, y1, h0, h1, tanh_fast(h0), tanh_fast(h1), h0, h1);    // SiLU(y) = h + h tanh(h)
+              fma2(y2, y3, h2, h3, tanh_fast(h2), tanh_fast(h3), h2, h3);
               pk[i / 2] = pack_bf16x2(y0, y1);
               pk[i / 2 + 1] = pack_bf16x2(y2, y3);
             }
-            if (!(p.debug & 2)) store_with_halo(obase, pix, wy, wx, Wp, p.epi.ldo, ch0 + c0, pk);
+            if (!(p.debug & 2))
+              store_padded_block(&mapO, use_tma_out, slab, slab_buf, lane, obase, pix, wy, wx, Wp, p.epi.ldo, ch0 + c0, img,
+                                 y, x, pk);
             else if (pk[0] == 0x12345678u && pk[7] == 0x9abcdef0u) obase[0] = __float2bfloat16(0.f);
           }
         }
@@ -587,7 +666,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             float gs[NG], gq[NG];
 #pragma unroll
             for (int g = 0; g < NG; ++g) gs[g] = gq[g] = 0.f;
-            const uint32_t slab = slab_base + static_cast<uint32_t>(e) * 4096;
             const int m_base = (mt * MSUB + sub) * 128 + q * 32;
 #pragma unroll
             for (int c0 = 0; c0 < 96; c0 += 32) {
@@ -668,7 +746,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 pk[i / 2] = pack_bf16x2(v[i] + b4.x, v[i + 1] + b4.y);
                 pk[i / 2 + 1] = pack_bf16x2(v[i + 2] + b4.z, v[i + 3] + b4.w);
               }
-              store_with_halo(obase, pix, wy, wx, Wp, p.epi.ldo, n_off + c0, pk);
+              store_padded_block(&mapO, use_tma_out, slab, slab_buf, lane, obase, pix, wy, wx, Wp, p.epi.ldo, n_off + c0, b, y, x,
+                                 pk);
             }
           } else {  // EPI_PLAIN
             __nv_bfloat16* orow = static_cast<__nv_bfloat16*>(p.epi.out) + static_cast<size_t>(m) * p.epi.ldo + n_off;
@@ -696,7 +775,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         else ptx::mbar_arrive(ptx::smem_u32(&bars.tmem_empty[acc]));
       }
     }
-    if (EPI == EPI_RAW_STATS && lane == 0) ptx::bulk_wait_all();   // staged stores have left shared memory
+    if (lane == 0) ptx::bulk_wait_all();   // staged TMA stores have left shared memory
   }
 
   ptx::tc_fence_before();
@@ -949,6 +1028,17 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, con
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(TCS_ERR_CUDA, "cuTensorMapEncodeTiled(O) failed: " + std::to_string(r));
+  }
+  if ((epi == EPI_GN_FUSED || epi == EPI_PADDED) && g.W >= 32) {   // bf16 padded output, 32-pixel x 32-channel boxes
+    const cuuint64_t C = static_cast<cuuint64_t>(ea.ldo);
+    cuuint64_t dims[4] = {C, static_cast<cuuint64_t>(g.W + 2), static_cast<cuuint64_t>(g.H + 2), static_cast<cuuint64_t>(g.B)};
+    cuuint64_t strides[3] = {C * 2, C * 2 * (g.W + 2), C * 2 * (g.W + 2) * (g.H + 2)};
+    cuuint32_t box[4] = {32, 32, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&pl.mapO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ea.out, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(TCS_ERR_CUDA, "cuTensorMapEncodeTiled(O padded) failed: " + std::to_string(r));
   }
   pl.valid = true;
   return TCS_OK;
