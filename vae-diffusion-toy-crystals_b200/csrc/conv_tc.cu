@@ -539,21 +539,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         float gs1[8], gq1[8];
 #pragma unroll
         for (int g = 0; g < 8; ++g) gs[g] = gq[g] = gs1[g] = gq1[g] = 0.f;
+        {
+          // six 32-column chunks (two 96-column units); the TMEM load of chunk k+1 is in flight while chunk k is
+          // reduced (tcgen05.wait::ld waits for everything outstanding, so it sits right before the next issue)
+          float vbuf[2][32];
+          ptx::tmem_ld32(tbase, vbuf[0]);
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {          // the two 96-column units: sub-tile u (MSUB 2) or column half u
-          const int ch0 = (MSUB == 2) ? 0 : u * 96;
-#pragma unroll
-          for (int c0 = 0; c0 < 96; c0 += 32) {
-            float v[32];
-            ptx::tmem_ld32(tbase + u * 96 + c0, v);
+          for (int k = 0; k < 6; ++k) {
             ptx::tmem_ld_wait();
+            if (k < 5) ptx::tmem_ld32(tbase + (k + 1) * 32, vbuf[(k + 1) & 1]);
+            const float* v = vbuf[k & 1];
+            const int cc = (MSUB == 2) ? (k % 3) * 32 : k * 32;     // channel of the chunk's first column
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + ch0 + c0 + i);
+              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + cc + i);
               float t0, t1, t2, t3;
               add2(t0, t1, v[i], v[i + 1], b4.x, b4.y);
               add2(t2, t3, v[i + 2], v[i + 3], b4.z, b4.w);
-              const int g0 = (ch0 + c0 + i) / CPGN, g1 = (ch0 + c0 + i + 2) / CPGN;   // pairs never straddle a group
+              const int g0 = (cc + i) / CPGN, g1 = (cc + i + 2) / CPGN;   // pairs never straddle a group
               add2(gs[g0], gs1[g0], gs[g0], gs1[g0], t0, t1);
               fma2(gq[g0], gq1[g0], t0, t1, t0, t1, gq[g0], gq1[g0]);
               add2(gs[g1], gs1[g1], gs[g1], gs1[g1], t2, t3);
@@ -561,19 +564,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             }
           }
         }
+        // lane reduction as a reduce-scatter: 16 values -> 8 -> 4 -> 2 -> 1 per lane (16 shuffles instead of 80);
+        // lane L ends with the warp total of value index bits(L>>1) for lanes with even L
+        float rv[16];
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          gs[g] += gs1[g];
-          gq[g] += gq1[g];
+        for (int g = 0; g < 8; ++g) { rv[2 * g] = gs[g] + gs1[g]; rv[2 * g + 1] = gq[g] + gq1[g]; }
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            gs[g] += __shfl_xor_sync(0xffffffffu, gs[g], o);
-            gq[g] += __shfl_xor_sync(0xffffffffu, gq[g], o);
+        for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
+          const bool hi = (lane & off) != 0;
+#pragma unroll
+          for (int i = 0; i < half; ++i) {
+            const float send = hi ? rv[i] : rv[i + half];
+            const float keep = hi ? rv[i + half] : rv[i];
+            rv[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
           }
         }
-        if (lane == 0) {
-#pragma unroll
-          for (int g = 0; g < 8; ++g) { gsm->red[q][2 * g] = gs[g]; gsm->red[q][2 * g + 1] = gq[g]; }
+        rv[0] += __shfl_xor_sync(0xffffffffu, rv[0], 1);
+        if ((lane & 1) == 0) {
+          const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+          gsm->red[q][idx] = rv[0];
         }
         epi_bar_sync(grp);
         if (q == 2) {   // warps 2 and 6 are the groups' leaders (warp % 4 == 2)
@@ -616,26 +625,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         }
         epi_bar_sync(grp);
         __nv_bfloat16* obase = static_cast<__nv_bfloat16*>(p.epi.out);
+        {
+          float vbuf[2][32];
+          ptx::tmem_ld32(tbase, vbuf[0]);
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int sub = (MSUB == 2) ? u : 0;
-          const int ch0 = (MSUB == 2) ? 0 : u * 96;
-          const int m = (mt * MSUB + sub) * 128 + row;
-          const int rem = m - img * HW;
-          const int y = rem / p.W, x = rem - y * p.W;
-          const int wy = (y == 0) ? p.H : ((y == p.H - 1) ? -p.H : 0);
-          const int wx = (x == 0) ? p.W : ((x == p.W - 1) ? -p.W : 0);
-          const size_t pix = (static_cast<size_t>(img) * Hp + (y + 1)) * Wp + (x + 1);
-#pragma unroll
-          for (int c0 = 0; c0 < 96; c0 += 32) {
-            float v[32];
-            ptx::tmem_ld32(tbase + u * 96 + c0, v);
+          for (int k = 0; k < 6; ++k) {
             ptx::tmem_ld_wait();
+            if (k < 5) ptx::tmem_ld32(tbase + (k + 1) * 32, vbuf[(k + 1) & 1]);
+            const float* v = vbuf[k & 1];
+            const int sub = (MSUB == 2) ? k / 3 : 0;
+            const int cc = (MSUB == 2) ? (k % 3) * 32 : k * 32;
+            const int m = (mt * MSUB + sub) * 128 + row;
+            const int rem = m - img * HW;
+            const int y = rem / p.W, x = rem - y * p.W;
+            const int wy = (y == 0) ? p.H : ((y == p.H - 1) ? -p.H : 0);
+            const int wx = (x == 0) ? p.W : ((x == p.W - 1) ? -p.W : 0);
+            const size_t pix = (static_cast<size_t>(img) * Hp + (y + 1)) * Wp + (x + 1);
             uint32_t pk[16];
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              const float4 s4 = *reinterpret_cast<const float4*>(gsm->scale + ch0 + c0 + i);
-              const float4 h4 = *reinterpret_cast<const float4*>(gsm->shift + ch0 + c0 + i);
+              const float4 s4 = *reinterpret_cast<const float4*>(gsm->scale + cc + i);
+              const float4 h4 = *reinterpret_cast<const float4*>(gsm->shift + cc + i);
               float h0, h1, h2, h3, y0, y1, y2, y3;
               fma2(h0, h1, v[i], v[i + 1], s4.x, s4.y, h4.x, h4.y);          // h = y/2
               fma2(h2, h3, v[i + 2], v[i + 3], s4.z, s4.w, h4.z, h4.w);
@@ -645,8 +655,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
               pk[i / 2 + 1] = pack_bf16x2(y2, y3);
             }
             if (!(p.debug & 2))
-              store_padded_block(&mapO, use_tma_out, slab, slab_buf, lane, obase, pix, wy, wx, Wp, p.epi.ldo, ch0 + c0, img,
-                                 y, x, pk);
+              store_padded_block(&mapO, use_tma_out, slab, slab_buf, lane, obase, pix, wy, wx, Wp, p.epi.ldo, cc, img, y, x, pk);
             else if (pk[0] == 0x12345678u && pk[7] == 0x9abcdef0u) obase[0] = __float2bfloat16(0.f);
           }
         }

@@ -131,7 +131,7 @@ template <> __device__ __forceinline__ void store_pair<__nv_bfloat16>(__nv_bfloa
 // Each sample is split over FC_SPLIT blocks (row bands); every block recomputes the (cheap) statistics.
 constexpr int FC_SPLIT = 4;
 template <typename T>
-__global__ void __launch_bounds__(384) first_conv_gn_kernel(const float* __restrict__ x, const float* __restrict__ w9,
+__global__ void __launch_bounds__(384, 2) first_conv_gn_kernel(const float* __restrict__ x, const float* __restrict__ w9,
                                                            const float* __restrict__ tvec, int tvec_stride,
                                                            const int* __restrict__ step_ptr, int trow_off,
                                                            const float* __restrict__ cvec, int dup,
