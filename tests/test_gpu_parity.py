@@ -355,5 +355,8 @@ def test_c1_full_config_against_the_reference(golden_dir):
         e_err = pu.rel_l2(e, g["eps_final"])
         print(f"C1 {precision}/{engine}: x0_hat rel-L2 {x0_err:.3e}, mismatched pixels {mism:.4%}, final eps (teacher-forced) {e_err:.3e}")
         assert e_err < TOL_EPS[precision]
+        # stated per-pixel tolerance for final PF-ODE samples (measured on B200: fp32 3.8e-7 / 0 pixels, bf16 1.3e-3 / 0.08 %)
         if precision == "fp32":
-            assert x0_err < 1e-3 and mism < 5e-3, (x0_err, mism)
+            assert x0_err < 1e-5 and mism < 1e-4, (x0_err, mism)
+        else:
+            assert x0_err < 1e-2 and mism < 1e-2, (x0_err, mism)
