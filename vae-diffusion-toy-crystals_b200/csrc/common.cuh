@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/tcs.h"
 
@@ -68,6 +69,27 @@ struct EpiArgs {
   const float* beta;
   int* counters;          // EPI_GN_FUSED: per-image arrival counters [B], zeroed before the launch
 };
+
+// device buffer that only ever grows (cudaMalloc / cudaFree outside the hot loop)
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { if (p) cudaFree(p); }
+  int ensure(size_t b) {
+    if (b <= bytes) return TCS_OK;
+    if (p) cudaFree(p);
+    p = nullptr; bytes = 0;
+    TCS_CUDA(cudaMalloc(&p, b));
+    bytes = b;
+    return TCS_OK;
+  }
+  template <typename U> U* as() const { return static_cast<U*>(p); }
+};
+
+struct HostTensor { std::vector<float> v; std::vector<int64_t> shape; };
 
 // GroupNorm partial-sum slots per image written by each conv engine
 inline int tc_slots(int H, int W) { return (H * W / 128) * 4; }

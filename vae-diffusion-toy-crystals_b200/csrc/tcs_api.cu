@@ -52,25 +52,6 @@ struct Sched {
   }
 };
 
-// ------------------------------------------------------------------------------------------
-// device buffer helper
-// ------------------------------------------------------------------------------------------
-struct DevBuf {
-  void* p = nullptr;
-  size_t bytes = 0;
-  ~DevBuf() { if (p) cudaFree(p); }
-  int ensure(size_t b) {
-    if (b <= bytes) return TCS_OK;
-    if (p) cudaFree(p);
-    p = nullptr; bytes = 0;
-    TCS_CUDA(cudaMalloc(&p, b));
-    bytes = b;
-    return TCS_OK;
-  }
-  template <typename U> U* as() const { return static_cast<U*>(p); }
-};
-
-struct HostTensor { std::vector<float> v; std::vector<int64_t> shape; };
 
 enum ConvId { C_D1B, C_DS1, C_D2A, C_D2B, C_DS2, C_MA, C_MB, C_QKV, C_PROJ, C_US2, C_U2A, C_U2B, C_US1, C_U1A, C_U1B, C_COUNT };
 struct ConvSpec { const char* key; int cin0, cin1, cout, k, stride, res; };
