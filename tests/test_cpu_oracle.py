@@ -135,7 +135,8 @@ def test_philox_known_answer_vectors():
 
 # ---- C-ABI surface ---------------------------------------------------------------------------------
 def test_library_exports_every_declared_symbol():
-    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "tcs.h")).read(), flags=re.S)
+    hdr = "".join(re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", f)).read(), flags=re.S)
+                  for f in ("tcs.h", "tcs_prior.h"))
     declared = set(re.findall(r"\b(tcs_[a-z0-9_]+)\s*\(", hdr))
     assert declared, "no declarations parsed"
     L = _cabi.lib()

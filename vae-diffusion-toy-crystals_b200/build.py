@@ -16,7 +16,8 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "toycrystals_b200")
 LIB = os.path.join(OUT_DIR, "libtcs.so")
 OBJ_DIR = os.path.join(HERE, "build")
-SOURCES = ["tcs_api.cu", "conv_tc.cu", "kernels_simt.cu", "kernels_embed.cu", "kernels_step.cu"]
+SOURCES = ["tcs_api.cu", "conv_tc.cu", "kernels_simt.cu", "kernels_embed.cu", "kernels_step.cu",
+           "prior_api.cu", "linear_tc.cu", "kernels_prior.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
@@ -33,6 +34,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ_DIR, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(HERE, "..", "include", "tcs.h"))
+    headers.append(os.path.join(HERE, "..", "include", "tcs_prior.h"))
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
     if not force and _newer(LIB, srcs + headers + [os.path.abspath(__file__)]):
         return LIB

@@ -29,7 +29,24 @@ class TcsSampleArgs(C.Structure):
                 ("x_out", C.c_void_p), ("trace_eps", C.c_void_p), ("trace_x", C.c_void_p), ("x0_hat", C.c_void_p)]
 
 
-# every symbol include/tcs.h declares: name -> (restype, argtypes)
+class TcsPriorConfig(C.Structure):
+    _fields_ = [("z_dim", C.c_int32), ("n_types", C.c_int32), ("y_cont_dim", C.c_int32), ("t_emb_dim", C.c_int32),
+                ("width", C.c_int32), ("n_blocks", C.c_int32), ("y_cat_emb_dim", C.c_int32), ("T", C.c_int32),
+                ("beta_start", C.c_double), ("beta_end", C.c_double), ("precision", C.c_int32), ("device", C.c_int32),
+                ("use_graph", C.c_int32)]
+
+
+class TcsDdimArgs(C.Structure):
+    _fields_ = [("n", C.c_int32), ("n_steps", C.c_int32), ("y_cat", C.c_void_p), ("y_cont", C.c_void_p),
+                ("z_init", C.c_void_p), ("seed", C.c_uint64), ("global_index_offset", C.c_uint64),
+                ("z0_out", C.c_void_p), ("trace_eps", C.c_void_p), ("trace_z", C.c_void_p)]
+
+
+class TcsVaeConfig(C.Structure):
+    _fields_ = [("z_dim", C.c_int32), ("n_types", C.c_int32), ("y_cont_dim", C.c_int32), ("device", C.c_int32)]
+
+
+# every symbol include/tcs.h and include/tcs_prior.h declare: name -> (restype, argtypes)
 SIGNATURES = {
     "tcs_default_config": (None, [C.POINTER(TcsConfig)]),
     "tcs_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(TcsConfig)]),
@@ -54,6 +71,27 @@ SIGNATURES = {
                                     C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "tcs_score_profiled": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float,
                                      C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p]),
+    # ---- include/tcs_prior.h ----
+    "tcs_prior_default_config": (None, [C.POINTER(TcsPriorConfig)]),
+    "tcs_prior_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(TcsPriorConfig)]),
+    "tcs_prior_destroy": (None, [C.c_void_p]),
+    "tcs_prior_set_weight": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),
+    "tcs_prior_finalize_weights": (C.c_int, [C.c_void_p]),
+    "tcs_prior_eps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                C.c_void_p]),
+    "tcs_prior_ddim_sample": (C.c_int, [C.c_void_p, C.POINTER(TcsDdimArgs), C.c_void_p]),
+    "tcs_prior_schedule_host": (C.c_int, [C.c_int32, C.c_double, C.c_double, C.POINTER(C.c_float)]),
+    "tcs_prior_timesteps_host": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
+    "tcs_prior_launch_count": (C.c_int64, [C.c_void_p]),
+    "tcs_vae_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(TcsVaeConfig)]),
+    "tcs_vae_destroy": (None, [C.c_void_p]),
+    "tcs_vae_set_weight": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),
+    "tcs_vae_finalize_weights": (C.c_int, [C.c_void_p]),
+    "tcs_vae_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p]),
+    "tcs_vae_launch_count": (C.c_int64, [C.c_void_p]),
+    "tcs_debug_linear": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "tcs_debug_conv": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
