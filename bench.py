@@ -12,6 +12,10 @@ device->host read of the images, copies inside the timed region.
 
 `--impl reference` times the reference algorithm's CPU implementation (the oracle port, which is
 bit-identical to the reference module in fp32) on the host cores, on a bounded sample.
+
+`--workload prior` (not the default; BASELINE configs[3]) benches the latent-diffusion-prior path with
+the same contract: one "step" = one job of n=4096 samples per GPU = 50-step DDIM over the FiLM-MLP prior (T=1000, width
+1024, z_dim 32, beta_end 0.05) followed by the CondVAE decode to 64x64.
 """
 from __future__ import annotations
 
@@ -182,6 +186,202 @@ def cuda_eager_reference_samples_per_sec(n: int = 256, steps: int = 2, tf32: boo
                       f"in {best:.3f}s, extrapolated linearly to {SDE_STEPS + 1}"}
 
 
+# ---------------------------------------------------------------------------------------------------
+# --workload prior: BASELINE configs[3]
+# ---------------------------------------------------------------------------------------------------
+PRIOR = dict(z_dim=32, n_types=4, y_cont_dim=4, t_emb_dim=64, width=1024, n_blocks=8, y_cat_emb_dim=64)
+PRIOR_T, PRIOR_B0, PRIOR_B1, DDIM_STEPS = 1000, 1e-4, 0.05, 50
+# tensor-core work per sample per DDIM step: fc1 + fc2 of the 8 blocks (the `cond` Linears are hoisted out of the loop)
+PRIOR_GEMM_MFLOP_PER_STEP = 8 * 2 * 2 * 1024 * 4096 / 1e6
+PRIOR_METRIC = "samples_per_sec_latent_prior_ddim50_vae_decode_64x64"
+
+
+def prior_workload_config(args, n_per_gpu, world):
+    return {"workload": f"latent diffusion prior (FiLM MLP, width 1024, 8 blocks, z_dim 32, T=1000, beta_end 0.05), "
+                        f"{DDIM_STEPS}-step DDIM (eta 0), then CondVAE decode to 64x64, n={n_per_gpu} per GPU, random-init "
+                        f"weights (BASELINE configs[3])",
+            "n_per_gpu": n_per_gpu, "n_total": n_per_gpu * world, "ddim_steps": DDIM_STEPS, "precision": args.precision,
+            "parallelism": f"dp{world} (batch sharded, all-gather of images)",
+            "l2_policy": "inputs larger than L2: weights 206 MB bf16 + 268 MB FiLM table + activations per step >> 126 MB; "
+                         "no explicit flush"}
+
+
+def cpu_prior_samples_per_sec(n: int = 64, steps: int = 5):
+    """The reference algorithm (oracle port) on the host cores: `steps` DDIM evaluations + one decode on n samples,
+    the DDIM part extrapolated linearly to 50 steps."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import latent_prior_oracle as po
+    import toycrystals_oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    psd, vsd = po.prior_default_init(0), po.vae_default_init(2)
+    y_cat, y_cont = orc.condition_grid(n, 4, 4)
+    z = torch.randn((n, 32), generator=torch.Generator().manual_seed(1234))
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        for k in range(steps):
+            t = torch.full((n,), 999 - 20 * k, dtype=torch.int64)
+            eps = po.film_prior(psd, po.PRIOR_CFG, z, t, y_cat, y_cont)
+            z = z - 0.01 * eps
+        t1 = time.perf_counter()
+        po.vae_decode(vsd, po.VAE_CFG, z, y_cat, y_cont)
+        t2 = time.perf_counter()
+    per_job = (t1 - t0) / steps * DDIM_STEPS + (t2 - t1)
+    desc = (f"reference algorithm (oracle port, torch {torch.__version__} CPU fp32, {torch.get_num_threads()} threads): n={n}, "
+            f"{steps} prior evaluations in {t1 - t0:.2f}s (extrapolated linearly to {DDIM_STEPS}) + decode {t2 - t1:.2f}s")
+    return n / per_job, cores, desc
+
+
+def run_reference_prior(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    n = args.n or 4096
+    vals = []
+    for i in range(args.warmup + args.steps):
+        sps, cores, desc = cpu_prior_samples_per_sec(n=max(args.cpu_n, 512), steps=max(2, args.cpu_steps // 3))
+        if i >= args.warmup:
+            vals.append(sps)
+    v = statistics.mean(vals)
+    print(json.dumps({
+        "impl": "reference", "metric": PRIOR_METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * args.cpu_n / v if v else None, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": prior_workload_config(args, n, args.gpus),
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+    return 0
+
+
+def run_gpu_prior(args):
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from toycrystals_b200 import _cabi
+    from toycrystals_b200.models import diffusion_prior as pshim
+    from toycrystals_b200.models import sde_score_model as shim
+    from toycrystals_b200.models import vae as vshim
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = os.environ.get("TCS_NCCL_DEBUG", "WARN")
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.n or 4096
+    n_total = n * world
+    lo, hi = shard_range(n_total, rank, world)
+    torch.manual_seed(0)
+    prior = pshim.DiffusionPriorFiLM(**PRIOR, precision=args.precision).to(dev).eval()
+    torch.manual_seed(2)
+    vae = vshim.CondVAE(z_dim=32, n_types=4, y_cont_dim=4).to(dev).eval()
+    sched = pshim.DiffusionSchedule.linear(PRIOR_T, PRIOR_B0, PRIOR_B1, dev)
+    # conditions exactly as save_diffusion_samples builds them, for this rank's block of global indices
+    gi = torch.arange(lo, hi, device=dev)
+    y_cat = (gi % 4).to(torch.int64)
+    y_cont = torch.zeros((n, 4), device=dev)
+    y_cont[:, 1] = torch.linspace(0.0, 3.141592653589793 / 3.0, steps=n_total, device=dev)[lo:hi]
+    g = torch.Generator().manual_seed(7)
+    h_mean = (torch.randn((32,), generator=g) * 0.3).pin_memory()
+    h_std = (torch.rand((32,), generator=g) + 0.5).pin_memory()
+    z_mean, z_std = h_mean.to(dev), h_std.to(dev)
+    h_cat, h_cont = y_cat.cpu().pin_memory(), y_cont.cpu().pin_memory()
+    h_img = torch.empty((n, 1, 64, 64), dtype=torch.float32).pin_memory()
+    seed = 1234
+
+    def job_device():
+        x = pshim.sample_images(vae, prior, sched, y_cat, y_cont, z_mean, z_std, DDIM_STEPS, seed=seed, global_index_offset=lo)
+        return gather_images(x, n_total, world)
+
+    def job_e2e():
+        yc, yk = h_cat.to(dev, non_blocking=True), h_cont.to(dev, non_blocking=True)
+        zm, zs = h_mean.to(dev, non_blocking=True), h_std.to(dev, non_blocking=True)
+        x = pshim.sample_images(vae, prior, sched, yc, yk, zm, zs, DDIM_STEPS, seed=seed, global_index_offset=lo)
+        full = gather_images(x, n_total, world)
+        h_img.copy_(full[lo:hi], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(h_img[0, 0, 0, 0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1), dev)
+
+    for _ in range(args.warmup):
+        job_device()
+    l0 = prior.launch_count() + vae.launch_count()
+    with ClockSampler(local_rank) as clk:
+        ms = timed(job_device, args.steps)
+    launches = prior.launch_count() + vae.launch_count() - l0
+    job_e2e()
+    ms_e2e = timed(job_e2e, args.steps)
+    # decode alone (device events on the current stream; the library orders its stream against it)
+    z = torch.randn((n, 32), device=dev)
+    ms_dec = timed(lambda: vae.decode(z, y_cat, y_cont, z_mean=z_mean, z_std=z_std), 5) / 5
+    kms = (C.c_float * 4)()
+    if rank == 0:
+        _cabi.check(_cabi.lib().tcs_prior_profile(prior.engine_handle(sched), n, 20, kms))
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sps, cores, desc = cpu_prior_samples_per_sec(n=max(args.cpu_n, 512), steps=max(2, args.cpu_steps // 3))
+        cpu = {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port", "sample": desc}
+    if rank == 0:
+        peaks = load_peaks()
+        value = n_total * args.steps / (ms / 1e3)
+        e2e = n_total * args.steps / (ms_e2e / 1e3)
+        burst = peaks.get("bf16_tflops", PEAKS_FALLBACK["bf16_tflops"])
+        sustained = peaks.get("bf16_tflops_sustained", PEAKS_FALLBACK["bf16_tflops_sustained"])
+        hbm = peaks.get("hbm_gbs", PEAKS_FALLBACK["hbm_gbs"])
+        gemm_flop = 2.0 * n * 1024 * 4096
+        gemm_ms = 0.5 * (kms[0] + kms[1])
+        gemm_tflops = gemm_flop / (gemm_ms * 1e-3) / 1e12
+        job_tflops = value / world * DDIM_STEPS * PRIOR_GEMM_MFLOP_PER_STEP / 1e6
+        lnf_bytes = n * (1024 * 4 + 2 * 1024 * 4 + 1024 * (2 if args.precision == "bf16" else 4))
+        line = {
+            "metric": PRIOR_METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "config": prior_workload_config(args, n, world),
+            "e2e": {"value": e2e, "unit": "samples/s",
+                    "h2d_bytes_per_step": int(h_cat.numel() * 8 + h_cont.numel() * 4 + 2 * 32 * 4),
+                    "d2h_bytes_per_step": int(h_img.numel() * 4)},
+            "gpu_launches": int(launches), "clocks": clk.summary(),
+            # dominant kernel = linear_tc_kernel (fc1 / fc2 of the FiLM blocks: 16 of the 25 launches of a DDIM step),
+            # timed live with CUDA events on the library's stream (tcs_prior_profile)
+            "roofline": {"bound": "tensor", "kernel": "tcs::linear_tc_kernel", "achieved": gemm_tflops, "peak": burst,
+                         "unit": "TFLOP/s", "frac": gemm_tflops / burst, "traffic": None,
+                         "peak_source": f"bf16_tflops burst ({peaks['_source']})", "launch_ms": gemm_ms,
+                         "rows_per_launch": n, "fc1_ms": kms[0], "fc2_ms": kms[1],
+                         "flop_per_launch": gemm_flop},
+            "whole_job": {"achieved": job_tflops, "peak": sustained, "unit": "TFLOP/s", "frac": job_tflops / sustained,
+                          "note": f"fc1+fc2 FLOPs of the job ({DDIM_STEPS} steps x {PRIOR_GEMM_MFLOP_PER_STEP:.1f} MFLOP/sample) / "
+                                  f"time per GPU, vs bf16 sustained peak ({peaks['_source']}); decode and the per-call FiLM "
+                                  f"table are inside the time but not the FLOP count"},
+            "ln_film_kernel": {"bound": "hbm", "achieved": lnf_bytes / (kms[2] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                               "frac": lnf_bytes / (kms[2] * 1e-3) / 1e9 / hbm, "launch_ms": kms[2],
+                               "bytes_per_row": lnf_bytes // n},
+            "tail_kernel_ms": kms[3], "decode_ms": ms_dec, "decode_share_of_job": ms_dec / (ms / args.steps),
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -197,7 +397,7 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * args.cpu_n / v if v else None, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, n_per_gpu=args.n, world=args.gpus),
+        "config": workload_config(args, n_per_gpu=args.n or 1024, world=args.gpus),
         "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -240,7 +440,7 @@ def run_gpu(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ["NCCL_DEBUG"] = os.environ.get("TCS_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
-    n = args.n
+    n = args.n or 1024
     n_total = n * world
     lo, hi = shard_range(n_total, rank, world)
 
@@ -396,7 +596,9 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=1024, help="samples per GPU per job")
+    ap.add_argument("--workload", default="sde", choices=["sde", "prior"],
+                    help="sde = BASELINE configs[1] (the headline); prior = configs[3] (latent prior DDIM + VAE decode)")
+    ap.add_argument("--n", type=int, default=0, help="samples per GPU per job (default 1024 for sde, 4096 for prior)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--cpu-n", type=int, default=64)
@@ -404,6 +606,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-eager", action="store_true")
     args = ap.parse_args()
+    if args.workload == "prior":
+        return run_reference_prior(args) if args.impl == "reference" else run_gpu_prior(args)
     if args.impl == "reference":
         return run_reference(args)
     return run_gpu(args)

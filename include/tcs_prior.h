@@ -93,6 +93,8 @@ typedef struct tcs_vae_config {
   int32_t n_types;
   int32_t y_cont_dim;
   int32_t device;
+  int32_t precision;   /* tcs_precision: TCS_BF16 = the three wide ConvTranspose2d stages on tcgen05 (bf16 activations
+                          and weights, fp32 accumulate); TCS_FP32 = FFMA kernels throughout (the parity mode) */
 } tcs_vae_config;
 
 int tcs_vae_create(tcs_vae** out, const tcs_vae_config* cfg);
@@ -105,6 +107,13 @@ int tcs_vae_finalize_weights(tcs_vae* h);
 int tcs_vae_decode(tcs_vae* h, const float* z, const int64_t* y_cat, const float* y_cont, int32_t n, const float* z_mean,
                    const float* z_std, float* x_out, void* stream);
 int64_t tcs_vae_launch_count(const tcs_vae* h);
+
+/* Timing hook for bench.py: runs, `reps` times each and back to back on the library's stream with CUDA events around
+ * the group, the four per-step kernels of block 0 on the first n rows of the workspace left by the last
+ * tcs_prior_ddim_sample call (which must have covered >= n rows): ms_host[0] = fc1 GEMM (tcgen05 in bf16 mode),
+ * [1] = fc2 GEMM, [2] = LayerNorm+FiLM, [3] = tail (out_norm/out_proj/DDIM/in_proj).  Average ms per launch.
+ * The residual stream is scratch afterwards.  Synchronous. */
+int tcs_prior_profile(tcs_prior* h, int32_t n, int32_t reps, float* ms_host);
 
 /* ---- test hook (tests/ only) ------------------------------------------------------------------------------ */
 /* One dense layer in isolation, synchronous: out[M,N] = act(A[M,K] W[N,K]^T + bias) (+ out when accumulate).

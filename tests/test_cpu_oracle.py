@@ -215,3 +215,27 @@ def test_cli_checkpoint_errors(tmp_path):
     ck = orc.make_checkpoint()
     assert set(ck) == {"epoch_next", "model", "opt", "loss_hist", "config", "ema"}
     assert ck["config"]["beta_max"] == 30.0 and len(ck["model"]) == 71
+
+
+def test_adopt_accepts_any_module_with_the_reference_state_dict():
+    class Foreign(torch.nn.Module):     # stands in for the training script's reference model / ema_model
+        def __init__(self, sd):
+            super().__init__()
+            self.inner = shim.CondUNetTiny(**orc.DEFAULT_CFG)
+            self.inner.load_state_dict(sd)
+
+        def state_dict(self, *a, **k):
+            return self.inner.state_dict(*a, **k)
+
+    sd = orc.default_init_state_dict(1)
+    f = Foreign(sd)
+    fast = shim.adopt(f)
+    assert isinstance(fast, shim.CondUNetTiny) and fast._arch == {**orc.DEFAULT_CFG}
+    assert all(torch.equal(v, sd[k]) for k, v in fast.state_dict().items())
+    assert shim.adopt(f) is fast            # cached while the parameters are unchanged
+    with torch.no_grad():
+        f.inner.out.bias.add_(1.0)          # an optimiser / EMA step
+    again = shim.adopt(f)
+    assert float(again.state_dict()["out.bias"]) == pytest.approx(float(sd["out.bias"]) + 1.0, rel=1e-6)
+    with pytest.raises(TypeError, match="does not carry"):
+        shim.adopt(torch.nn.Linear(2, 2))

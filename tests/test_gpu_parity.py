@@ -360,3 +360,32 @@ def test_c1_full_config_against_the_reference(golden_dir):
             assert x0_err < 1e-5 and mism < 1e-4, (x0_err, mism)
         else:
             assert x0_err < 1e-2 and mism < 1e-2, (x0_err, mism)
+
+
+def test_training_hook_accepts_a_foreign_module(tmp_path):
+    """scripts/train_sde_score_model.py:263-279 calls save_sde_samples(model=<its own nn.Module>)."""
+    import toycrystals_oracle as orc
+    from toycrystals_b200.models import sde_score_model as shim
+    P = _pu()
+
+    class Foreign(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.inner = shim.CondUNetTiny(**orc.DEFAULT_CFG)
+            self.inner.load_state_dict(orc.default_init_state_dict(1))
+            self.n_types, self.y_cont_dim = 4, 4
+
+        def state_dict(self, *a, **k):
+            return self.inner.state_dict(*a, **k)
+
+    f = Foreign().to("cuda")
+    out = tmp_path / "grid.png"
+    shim.save_sde_samples(model=f, sde=shim.VPSDE(0.1, 30.0), out_path=str(out), device=torch.device("cuda"), steps=2, cfg=1.5,
+                          t_end=0.005, sampler="sde")
+    assert out.exists() and out.stat().st_size > 1000
+    y_cat, y_cont = (t.cuda() for t in orc.condition_grid(4, 4, 4))
+    x = torch.randn((4, 1, 64, 64), device="cuda")
+    t = torch.full((4,), 0.4, device="cuda")
+    a = shim.predict_eps_cfg(f, x, t, y_cat, y_cont, 1.5)
+    b = shim.predict_eps_cfg(P.model("bf16", seed=1), x, t, y_cat, y_cont, 1.5)
+    assert torch.equal(a, b)

@@ -41,12 +41,13 @@ def prior(precision, cfg=None, seed=0, use_graph=True):
     return _cache[key]
 
 
-def vae():
-    if "vae" not in _cache:
-        v = vshim.CondVAE(z_dim=32, n_types=4, y_cont_dim=4)
+def vae(precision="fp32"):
+    key = ("vae", precision)
+    if key not in _cache:
+        v = vshim.CondVAE(z_dim=32, n_types=4, y_cont_dim=4, precision=precision)
         v.load_state_dict(po.vae_default_init(2))
-        _cache["vae"] = v.to("cuda").eval()
-    return _cache["vae"]
+        _cache[key] = v.to("cuda").eval()
+    return _cache[key]
 
 
 def sched_gpu():
@@ -218,6 +219,28 @@ def test_decode_matches_the_reference_golden_vectors():
     want = po.vae_decode(vsd, po.VAE_CFG, z.double(), y_cat, y_cont.double())
     got = v.decode(z.cuda(), y_cat.cuda(), y_cont.cuda())
     assert float((got.cpu().double() - want).abs().max()) < 2e-5
+
+
+def test_decode_on_the_tensor_cores():
+    """bf16 mode: the three wide ConvTranspose2d stages run as tcgen05 parity-class GEMMs (bf16 activations)."""
+    G = gold()
+    v = vae("bf16")
+    x = v.decode(G["z_init"].cuda(), G["y_cat"].cuda(), G["y_cont"].cuda())
+    d = (x.cpu() - G["x_dec"]).abs()
+    assert float(d.max()) < 1e-2 and float(d.mean()) < 1e-3, (float(d.max()), float(d.mean()))
+    # ragged batches around the tile sizes (8 images per 128-row tile in the first stage, 2 in the second)
+    vsd = po.vae_default_init(2)
+    g = torch.Generator().manual_seed(11)
+    for n in (1, 7, 9, 130):
+        z = torch.randn((n, 32), generator=g) * 2.0
+        y_cat, y_cont = orc.condition_grid(n, 4, 4)
+        want = po.vae_decode(vsd, po.VAE_CFG, z, y_cat, y_cont)
+        got = v.decode(z.cuda(), y_cat.cuda(), y_cont.cuda()).cpu()
+        d = (got - want).abs()
+        assert float(d.max()) < 1e-2 and float(d.mean()) < 1e-3, (n, float(d.max()), float(d.mean()))
+    # each image is independent of its batch
+    a = v.decode(z[:50].cuda(), y_cat[:50].cuda(), y_cont[:50].cuda())
+    assert torch.equal(a.cpu(), got[:50])
 
 
 def test_sample_images_end_to_end():

@@ -257,26 +257,29 @@ __global__ void __launch_bounds__(256) ln_film_kernel(const float* __restrict__ 
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (r >= n) return;
-  float4 u[NV];
-  warp_layernorm<NV>(h + static_cast<size_t>(r) * W, lane, ln_w, ln_b, u);
+  // the FiLM rows are independent of the LayerNorm result: issue their loads first so that both DRAM round trips overlap
   const float* fr = film_row ? film_row + static_cast<size_t>(r) * film_ld + off : nullptr;
   const float* fs = film_step ? film_step + static_cast<size_t>(step_ptr ? *step_ptr : 0) * film_step_ld + off : nullptr;
+  float4 g[NV], b[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = i * 128 + lane * 4;
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (fr) {
-      g = __ldg(reinterpret_cast<const float4*>(fr + c));
-      b = __ldg(reinterpret_cast<const float4*>(fr + W + c));
-    }
+    g[i] = fr ? __ldg(reinterpret_cast<const float4*>(fr + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    b[i] = fr ? __ldg(reinterpret_cast<const float4*>(fr + W + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float4 u[NV];
+  warp_layernorm<NV>(h + static_cast<size_t>(r) * W, lane, ln_w, ln_b, u);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = i * 128 + lane * 4;
     if (fs) {
       const float4 g2 = __ldg(reinterpret_cast<const float4*>(fs + c));
       const float4 b2 = __ldg(reinterpret_cast<const float4*>(fs + W + c));
-      g.x += g2.x; g.y += g2.y; g.z += g2.z; g.w += g2.w;
-      b.x += b2.x; b.y += b2.y; b.z += b2.z; b.w += b2.w;
+      g[i].x += g2.x; g[i].y += g2.y; g[i].z += g2.z; g[i].w += g2.w;
+      b[i].x += b2.x; b[i].y += b2.y; b[i].z += b2.z; b[i].w += b2.w;
     }
-    const float o0 = u[i].x * (1.0f + g.x) + b.x, o1 = u[i].y * (1.0f + g.y) + b.y;
-    const float o2 = u[i].z * (1.0f + g.z) + b.z, o3 = u[i].w * (1.0f + g.w) + b.w;
+    const float o0 = u[i].x * (1.0f + g[i].x) + b[i].x, o1 = u[i].y * (1.0f + g[i].y) + b[i].y;
+    const float o2 = u[i].z * (1.0f + g[i].z) + b[i].z, o3 = u[i].w * (1.0f + g[i].w) + b[i].w;
     if constexpr (sizeof(TO) == 4) {
       *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + static_cast<size_t>(r) * W + c) = make_float4(o0, o1, o2, o3);
     } else {
@@ -315,56 +318,87 @@ template int launch_ln_film<__nv_bfloat16>(const float*, int, int, const float*,
 // ------------------------------------------------------------------------------------------------
 constexpr int TAIL_ROWS = 16;
 
+// Phases (one CTA = 16 rows, 16 warps):
+//   1. warp w: LayerNorm(out_norm) of row w -> u_s[w][:] (shared memory, fp32)
+//   2. warp w: out_proj outputs 2w, 2w+1 for all 16 rows (the two weight rows live in registers, so every CTA reads
+//      out_proj.weight exactly once instead of once per row)
+//   3. thread (r, j): DDIM update of z[r][j]
+//   4. thread c: in_proj column c for the 16 rows (weights of the column in registers)
 template <int NV>
 __global__ void __launch_bounds__(512) prior_tail_kernel(const PriorTailArgs a) {
   constexpr int W = 128 * NV;
-  __shared__ float zs[TAIL_ROWS][PRIOR_MAX_Z];
+  extern __shared__ __align__(16) float u_s[];          // [TAIL_ROWS][W]
+  __shared__ __align__(16) float zs[TAIL_ROWS][PRIOR_MAX_Z];
+  __shared__ float eps_s[TAIL_ROWS][PRIOR_MAX_Z];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = blockIdx.x * TAIL_ROWS;
-  const int r = row0 + warp;
   const int zd = a.zd;
   const int step = a.step_ptr ? *a.step_ptr : 0;
-  bool last = false;
+  zs[warp][lane] = 0.f;   // columns >= zd and rows >= n stay zero
+  __syncthreads();
 
   if (a.mode == TAIL_INIT) {
+    const int r = row0 + warp;
     if (r < a.n && lane < zd) zs[warp][lane] = a.z[static_cast<size_t>(r) * zd + lane];
-  } else if (r < a.n) {
-    float4 u[NV];
-    warp_layernorm<NV>(a.h + static_cast<size_t>(r) * W, lane, a.on_w, a.on_b, u);
-    // out_proj: 32 partial dot products per lane, then a reduce-scatter so that lane j ends with output j
-    float pv[PRIOR_MAX_Z];
+  } else {
+    {   // phase 1
+      const int r = row0 + warp;
+      float4 u[NV];
+      if (r < a.n) {
+        warp_layernorm<NV>(a.h + static_cast<size_t>(r) * W, lane, a.on_w, a.on_b, u);
+      } else {
 #pragma unroll
-    for (int o = 0; o < PRIOR_MAX_Z; ++o) {
-      float acc = 0.f;
-      if (o < zd) {
-        const float* wr = a.op_w + static_cast<size_t>(o) * W + lane * 4;
+        for (int i = 0; i < NV; ++i) u[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < NV; ++i) *reinterpret_cast<float4*>(u_s + warp * W + i * 128 + lane * 4) = u[i];
+    }
+    __syncthreads();
+    // phase 2: every row of u_s is read once per warp and used for both of the warp's outputs
+    {
+      const int o0 = warp * 2;
+      float4 wa[NV], wb[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        wa[i] = o0 < zd ? __ldg(reinterpret_cast<const float4*>(a.op_w + static_cast<size_t>(o0) * W + i * 128 + lane * 4))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        wb[i] = o0 + 1 < zd ? __ldg(reinterpret_cast<const float4*>(a.op_w + static_cast<size_t>(o0 + 1) * W + i * 128 + lane * 4))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      float mine_a = 0.f, mine_b = 0.f;   // lane r keeps the results of row r
+#pragma unroll 2
+      for (int r = 0; r < TAIL_ROWS; ++r) {
+        float acc_a = 0.f, acc_b = 0.f;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
-          const float4 w4 = __ldg(reinterpret_cast<const float4*>(wr + i * 128));
-          acc = fmaf(u[i].x, w4.x, acc); acc = fmaf(u[i].y, w4.y, acc);
-          acc = fmaf(u[i].z, w4.z, acc); acc = fmaf(u[i].w, w4.w, acc);
+          const float4 x = *reinterpret_cast<const float4*>(u_s + r * W + i * 128 + lane * 4);
+          acc_a = fmaf(x.x, wa[i].x, acc_a); acc_a = fmaf(x.y, wa[i].y, acc_a);
+          acc_a = fmaf(x.z, wa[i].z, acc_a); acc_a = fmaf(x.w, wa[i].w, acc_a);
+          acc_b = fmaf(x.x, wb[i].x, acc_b); acc_b = fmaf(x.y, wb[i].y, acc_b);
+          acc_b = fmaf(x.z, wb[i].z, acc_b); acc_b = fmaf(x.w, wb[i].w, acc_b);
         }
-      }
-      pv[o] = acc;
-    }
 #pragma unroll
-    for (int half = 16, off = 16; half >= 1; half >>= 1, off >>= 1) {
-      const bool hi = (lane & off) != 0;
-#pragma unroll
-      for (int i = 0; i < half; ++i) {
-        const float send = hi ? pv[i] : pv[i + half];
-        const float keep = hi ? pv[i + half] : pv[i];
-        pv[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        for (int off = 16; off > 0; off >>= 1) {
+          acc_a += __shfl_xor_sync(0xffffffffu, acc_a, off);
+          acc_b += __shfl_xor_sync(0xffffffffu, acc_b, off);
+        }
+        if (lane == r) { mine_a = acc_a; mine_b = acc_b; }
+      }
+      if (lane < TAIL_ROWS) {
+        if (o0 < zd) eps_s[lane][o0] = mine_a + __ldg(a.op_b + o0);
+        if (o0 + 1 < zd) eps_s[lane][o0 + 1] = mine_b + __ldg(a.op_b + o0 + 1);
       }
     }
-    if (lane < zd) {
-      const float eps = pv[0] + __ldg(a.op_b + lane);
+    __syncthreads();
+    // phase 3
+    const int r = row0 + warp;
+    if (r < a.n && lane < zd) {
+      const float eps = eps_s[warp][lane];
       const size_t zi = static_cast<size_t>(r) * zd + lane;
       if (a.mode == TAIL_EPS) {
         a.eps_out[zi] = eps;
       } else {
         const DdimCoef c = a.coef[step];
-        last = c.last != 0;
         const float z = a.z[zi];
         const size_t ti = (static_cast<size_t>(step) * a.trace_n + r) * zd + lane;
         if (a.trace_eps) a.trace_eps[ti] = eps;
@@ -378,43 +412,70 @@ __global__ void __launch_bounds__(512) prior_tail_kernel(const PriorTailArgs a) 
         zs[warp][lane] = zn;
       }
     }
-  }
-  if (a.mode == TAIL_EPS) return;
-  if (a.mode == TAIL_DDIM) {
+    if (a.mode == TAIL_EPS) return;
     if (a.coef[step].last) return;   // uniform over the grid
   }
-  (void)last;
   __syncthreads();
-  // in_proj for the 16 rows of this CTA: thread -> column c, weights of the column in registers
-  for (int c = threadIdx.x; c < W; c += 512) {
-    float w[PRIOR_MAX_Z];
+  // phase 4: in_proj for the 16 rows of this CTA.  in_proj.weight [W][zd] is staged through the (now free) row buffer
+  // in coalesced 16-byte pieces, XOR-swizzled so that thread c can read "its" row with conflict-free 128-bit loads;
+  // W/2 columns per pass (zd = 32; smaller zd just leaves the tail of every row unused)
+  constexpr int CPP = W / 2;                          // columns per pass: CPP * 32 floats = the row buffer
+  float4* w_s = reinterpret_cast<float4*>(u_s);
+  const int zq = zd >> 2;                             // float4 per weight row
+  for (int c0 = 0; c0 < W; c0 += CPP) {
+    __syncthreads();                                  // the previous contents of the buffer are dead
+    for (int f = threadIdx.x; f < CPP * 8; f += 512) {
+      const int cl = f >> 3, j4 = f & 7;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j4 < zq) v = __ldg(reinterpret_cast<const float4*>(a.ip_w + static_cast<size_t>(c0 + cl) * zd) + j4);
+      w_s[cl * 8 + (j4 ^ (cl & 7))] = v;
+    }
+    __syncthreads();
+    for (int cl = threadIdx.x; cl < CPP; cl += 512) {
+      float4 w[8];
 #pragma unroll
-    for (int j = 0; j < PRIOR_MAX_Z; ++j) w[j] = j < zd ? __ldg(a.ip_w + static_cast<size_t>(c) * zd + j) : 0.f;
-    const float b = __ldg(a.ip_b + c);
-    for (int rr = 0; rr < TAIL_ROWS; ++rr) {
-      if (row0 + rr >= a.n) break;
-      float acc = b;
+      for (int j4 = 0; j4 < 8; ++j4) w[j4] = w_s[cl * 8 + (j4 ^ (cl & 7))];
+      const int c = c0 + cl;
+      const float b = __ldg(a.ip_b + c);
+      for (int rr = 0; rr < TAIL_ROWS; ++rr) {
+        if (row0 + rr >= a.n) break;
+        float acc = b;
 #pragma unroll
-      for (int j = 0; j < PRIOR_MAX_Z; ++j)
-        if (j < zd) acc = fmaf(w[j], zs[rr][j], acc);
-      a.h[static_cast<size_t>(row0 + rr) * W + c] = acc;
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 zv = *reinterpret_cast<const float4*>(&zs[rr][j4 * 4]);   // zero beyond zd
+          acc = fmaf(w[j4].x, zv.x, acc); acc = fmaf(w[j4].y, zv.y, acc);
+          acc = fmaf(w[j4].z, zv.z, acc); acc = fmaf(w[j4].w, zv.w, acc);
+        }
+        a.h[static_cast<size_t>(row0 + rr) * W + c] = acc;
+      }
     }
   }
+}
+
+template <int NV>
+static int launch_tail_t(const PriorTailArgs& a, cudaStream_t st) {
+  auto kern = prior_tail_kernel<NV>;
+  const size_t smem = static_cast<size_t>(TAIL_ROWS) * 128 * NV * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    TCS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr_done = true;
+  }
+  kern<<<(a.n + TAIL_ROWS - 1) / TAIL_ROWS, 512, smem, st>>>(a);
+  TCS_CUDA(cudaGetLastError());
+  return TCS_OK;
 }
 
 int launch_prior_tail(const PriorTailArgs& a, cudaStream_t st) {
   if (a.n < 1) return TCS_OK;
   if (a.zd > PRIOR_MAX_Z) return fail(TCS_ERR_UNSUPPORTED, "prior_tail: z_dim must be <= 32");
-  const dim3 grid((a.n + TAIL_ROWS - 1) / TAIL_ROWS);
   switch (a.W) {
-    case 256: prior_tail_kernel<2><<<grid, 512, 0, st>>>(a); break;
-    case 512: prior_tail_kernel<4><<<grid, 512, 0, st>>>(a); break;
-    case 1024: prior_tail_kernel<8><<<grid, 512, 0, st>>>(a); break;
-    case 2048: prior_tail_kernel<16><<<grid, 512, 0, st>>>(a); break;
+    case 256: return launch_tail_t<2>(a, st);
+    case 512: return launch_tail_t<4>(a, st);
+    case 1024: return launch_tail_t<8>(a, st);
+    case 2048: return launch_tail_t<16>(a, st);
     default: return fail(TCS_ERR_UNSUPPORTED, "prior_tail: width must be 256, 512, 1024 or 2048");
   }
-  TCS_CUDA(cudaGetLastError());
-  return TCS_OK;
 }
 
 __global__ void __launch_bounds__(256) prior_philox_kernel(float4* __restrict__ z, long long nvec, int groups,
@@ -456,11 +517,12 @@ int launch_f32_to_bf16(const float* src, __nv_bfloat16* dst, size_t count, cudaS
 // CondVAE decoder
 // ------------------------------------------------------------------------------------------------
 constexpr int DFC_IMGS = 8;
+template <typename TO>
 __global__ void __launch_bounds__(256) vae_dec_fc_kernel(const float* __restrict__ z, const int64_t* __restrict__ y_cat,
                                                         const float* __restrict__ y_cont, const float* __restrict__ z_mean,
                                                         const float* __restrict__ z_std, const float* __restrict__ w,
                                                         const float* __restrict__ b, int n, int zd, int n_types, int ycd,
-                                                        float* __restrict__ h0) {
+                                                        TO* __restrict__ h0) {
   __shared__ float v[DFC_IMGS][64];   // [z' | y_cont] per image
   __shared__ int cat[DFC_IMGS];
   const int img0 = blockIdx.x * DFC_IMGS, t = threadIdx.x;
@@ -503,15 +565,23 @@ __global__ void __launch_bounds__(256) vae_dec_fc_kernel(const float* __restrict
 #pragma unroll
     for (int im = 0; im < DFC_IMGS; ++im) {
       if (img0 + im >= n) break;
-      h0[(static_cast<size_t>(img0 + im) * 16 + p) * 256 + c] = acc[im] + __ldg(wr + zd + cat[im]);
+      const float val = acc[im] + __ldg(wr + zd + cat[im]);
+      if constexpr (sizeof(TO) == 4) h0[(static_cast<size_t>(img0 + im) * 16 + p) * 256 + c] = val;
+      else h0[(static_cast<size_t>(img0 + im) * 16 + p) * 256 + c] = __float2bfloat16(val);
     }
   }
 }
 int launch_vae_dec_fc(const float* z, const int64_t* y_cat, const float* y_cont, const float* z_mean, const float* z_std,
-                      const float* w, const float* b, int n, int zd, int n_types, int ycd, float* h0, cudaStream_t st) {
+                      const float* w, const float* b, int n, int zd, int n_types, int ycd, void* h0, int out_bf16,
+                      cudaStream_t st) {
   if (n < 1) return TCS_OK;
   if (zd + ycd > 64) return fail(TCS_ERR_UNSUPPORTED, "vae_dec_fc: z_dim + y_cont_dim must be <= 64");
-  vae_dec_fc_kernel<<<(n + DFC_IMGS - 1) / DFC_IMGS, 256, 0, st>>>(z, y_cat, y_cont, z_mean, z_std, w, b, n, zd, n_types, ycd, h0);
+  const dim3 grid((n + DFC_IMGS - 1) / DFC_IMGS);
+  if (out_bf16)
+    vae_dec_fc_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(z, y_cat, y_cont, z_mean, z_std, w, b, n, zd, n_types, ycd,
+                                                          static_cast<__nv_bfloat16*>(h0));
+  else
+    vae_dec_fc_kernel<float><<<grid, 256, 0, st>>>(z, y_cat, y_cont, z_mean, z_std, w, b, n, zd, n_types, ycd, static_cast<float*>(h0));
   TCS_CUDA(cudaGetLastError());
   return TCS_OK;
 }
@@ -544,7 +614,8 @@ int launch_vae_convt(const float* in, const float* wpacked, const float* bias, i
   return TCS_OK;
 }
 
-__global__ void __launch_bounds__(256) vae_convt_out_kernel(const float* __restrict__ in, const float* __restrict__ wpacked,
+template <typename TI>
+__global__ void __launch_bounds__(256) vae_convt_out_kernel(const TI* __restrict__ in, const float* __restrict__ wpacked,
                                                            float bias, long long total, float* __restrict__ x) {
   __shared__ __align__(16) float ws[4 * 4 * 32];
   for (int i = threadIdx.x; i < 512; i += 256) ws[i] = wpacked[i];
@@ -561,20 +632,38 @@ __global__ void __launch_bounds__(256) vae_convt_out_kernel(const float* __restr
     const int iy = i + (py == 0 ? (ty == 0 ? 0 : -1) : (ty == 0 ? 1 : 0));
     const int ix = j + (px == 0 ? (tx == 0 ? 0 : -1) : (tx == 0 ? 1 : 0));
     if (iy < 0 || iy >= 32 || ix < 0 || ix >= 32) continue;
-    const float4* p = reinterpret_cast<const float4*>(in + ((b * 32 + iy) * 32 + ix) * 32);
     const float4* wv = reinterpret_cast<const float4*>(ws + ((py * 2 + px) * 4 + tp) * 32);
+    if constexpr (sizeof(TI) == 4) {
+      const float4* p = reinterpret_cast<const float4*>(in + ((b * 32 + iy) * 32 + ix) * 32);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float4 a4 = __ldg(p + k), w4 = wv[k];
-      acc = fmaf(a4.x, w4.x, acc); acc = fmaf(a4.y, w4.y, acc); acc = fmaf(a4.z, w4.z, acc); acc = fmaf(a4.w, w4.w, acc);
+      for (int k = 0; k < 8; ++k) {
+        const float4 a4 = __ldg(p + k), w4 = wv[k];
+        acc = fmaf(a4.x, w4.x, acc); acc = fmaf(a4.y, w4.y, acc); acc = fmaf(a4.z, w4.z, acc); acc = fmaf(a4.w, w4.w, acc);
+      }
+    } else {
+      const uint4* p = reinterpret_cast<const uint4*>(in + ((b * 32 + iy) * 32 + ix) * 32);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint4 a8 = __ldg(p + k);
+        const uint32_t aw[4] = {a8.x, a8.y, a8.z, a8.w};
+        const float4 w0 = wv[2 * k], w1 = wv[2 * k + 1];
+        const float wf[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[e]));
+          acc = fmaf(f.x, wf[2 * e], acc); acc = fmaf(f.y, wf[2 * e + 1], acc);
+        }
+      }
     }
   }
   x[idx] = 1.0f / (1.0f + expf(-acc));
 }
-int launch_vae_convt_out(const float* in, const float* wpacked, float bias, int n, float* x, cudaStream_t st) {
+int launch_vae_convt_out(const void* in, int in_bf16, const float* wpacked, float bias, int n, float* x, cudaStream_t st) {
   if (n < 1) return TCS_OK;
   const long long total = static_cast<long long>(n) * 4096;
-  vae_convt_out_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(in, wpacked, bias, total, x);
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  if (in_bf16) vae_convt_out_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), wpacked, bias, total, x);
+  else vae_convt_out_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(in), wpacked, bias, total, x);
   TCS_CUDA(cudaGetLastError());
   return TCS_OK;
 }

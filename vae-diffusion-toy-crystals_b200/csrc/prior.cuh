@@ -73,13 +73,14 @@ int launch_f32_to_bf16(const float* src, __nv_bfloat16* dst, size_t count, cudaS
 // h0 NHWC [n,4,4,256] = dec_fc([z', onehot(y_cat), y_cont]),  z' = z * z_std + z_mean when z_mean/z_std are given
 int launch_vae_dec_fc(const float* z, const int64_t* y_cat, const float* y_cont, const float* z_mean, const float* z_std,
                       const float* w /*[4096, zd+n_types+ycd]*/, const float* b, int n, int zd, int n_types, int ycd,
-                      float* h0, cudaStream_t st);
+                      void* h0 /*fp32 or bf16*/, int out_bf16, cudaStream_t st);
 // ConvTranspose2d(k=4, s=2, p=1) + ReLU as four parity-class GEMMs: in NHWC [n,Hi,Hi,Ci] -> out NHWC [n,2Hi,2Hi,Co];
 // wpacked fp32 [4 parity][Co][4 taps * Ci]
 int launch_vae_convt(const float* in, const float* wpacked, const float* bias, int n, int Hi, int Ci, int Co, float* out,
                      cudaStream_t st);
 void vae_convt_pack_weights(const float* w /*[Ci,Co,4,4]*/, int Ci, int Co, float* out_host);
 // last layer: ConvTranspose2d(32 -> 1) + Sigmoid: in NHWC [n,32,32,32] -> x [n,64,64]; wpacked [4 parity][4 taps][32]
-int launch_vae_convt_out(const float* in, const float* wpacked, float bias, int n, float* x, cudaStream_t st);
+int launch_vae_convt_out(const void* in /*fp32 or bf16*/, int in_bf16, const float* wpacked, float bias, int n, float* x,
+                         cudaStream_t st);
 
 }  // namespace tcs

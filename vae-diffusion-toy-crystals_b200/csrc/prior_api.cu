@@ -112,7 +112,10 @@ struct tcs_vae {
   int64_t launches = 0;
   std::map<std::string, HostTensor> host_w;
   bool finalized = false;
-  DevBuf arena;
+  DevBuf arena, arena16;
+  bool bf16 = false;
+  int sm_count = 148;
+  const __nv_bfloat16* ct_w16[3] = {};
   const float *fc_w = nullptr, *fc_b = nullptr;
   const float* ct_w[4] = {};
   const float* ct_b[3] = {};
@@ -572,6 +575,59 @@ int tcs_prior_ddim_sample(tcs_prior* h, const tcs_ddim_args* args, void* stream)
   return leave_h(h, user);
 }
 
+int tcs_prior_profile(tcs_prior* h, int32_t n, int32_t reps, float* ms) {
+  TCS_CHECK(check_prior(h, "tcs_prior_profile"));
+  if (n < 1 || reps < 1 || !ms) return fail(TCS_ERR_BAD_ARGUMENT, "tcs_prior_profile: bad argument");
+  if (n > h->cap_n || h->cap_s < 1) return fail(TCS_ERR_STATE, "tcs_prior_profile: run tcs_prior_ddim_sample on >= n samples first");
+  TCS_CUDA(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = h->stream;
+  const int W = h->cfg.width, fld = h->cfg.n_blocks * 2 * W, of = h->bf16 ? 0 : LIN_OUT_F32;
+  cudaEvent_t ev[5];
+  for (auto& e : ev) TCS_CUDA(cudaEventCreate(&e));
+  TCS_CUDA(cudaMemsetAsync(h->step_ctr.p, 0, 4, st));
+  const std::string p = "blocks.0.";
+  auto fc1 = [&]() {
+    return dense(h, h->bf16, h->u.p, W, W, h->dw.at(p + "fc1.weight"), h->bf16 ? h->dw16.at(p + "fc1.weight") : nullptr, n, 4 * W, W,
+                 h->dw.at(p + "fc1.bias"), h->a.p, 4 * W, LIN_SILU | of, st);
+  };
+  auto fc2 = [&]() {
+    return dense(h, h->bf16, h->a.p, 4 * W, 4 * W, h->dw.at(p + "fc2.weight"), h->bf16 ? h->dw16.at(p + "fc2.weight") : nullptr, n, W,
+                 4 * W, h->dw.at(p + "fc2.bias"), h->h.p, W, LIN_OUT_F32 | LIN_ACCUM, st);
+  };
+  auto lnf = [&]() {
+    if (h->bf16)
+      return launch_ln_film<__nv_bfloat16>(h->h.as<float>(), n, W, h->dw.at(p + "norm.weight"), h->dw.at(p + "norm.bias"),
+                                           h->film.as<float>(), fld, h->tcond.as<float>(), fld, h->step_ctr.as<int>(), 0,
+                                           h->u.as<__nv_bfloat16>(), st);
+    return launch_ln_film<float>(h->h.as<float>(), n, W, h->dw.at(p + "norm.weight"), h->dw.at(p + "norm.bias"),
+                                 h->film.as<float>(), fld, h->tcond.as<float>(), fld, h->step_ctr.as<int>(), 0, h->u.as<float>(), st);
+  };
+  auto tail = [&]() {
+    PriorTailArgs ta = tail_args(h, TAIL_DDIM, n);
+    ta.z_out = h->z.as<float>();
+    ta.trace_n = n;
+    return launch_prior_tail(ta, st);
+  };
+  TCS_CHECK(launch_prior_tail(tail_args(h, TAIL_INIT, n), st));   // a sane residual stream from the current latents
+  TCS_CHECK(lnf()); TCS_CHECK(fc1()); TCS_CHECK(fc2()); TCS_CHECK(tail());   // warm-up
+  TCS_CUDA(cudaEventRecord(ev[0], st));
+  for (int r = 0; r < reps; ++r) TCS_CHECK(fc1());
+  TCS_CUDA(cudaEventRecord(ev[1], st));
+  for (int r = 0; r < reps; ++r) TCS_CHECK(fc2());
+  TCS_CUDA(cudaEventRecord(ev[2], st));
+  for (int r = 0; r < reps; ++r) TCS_CHECK(lnf());
+  TCS_CUDA(cudaEventRecord(ev[3], st));
+  for (int r = 0; r < reps; ++r) TCS_CHECK(tail());
+  TCS_CUDA(cudaEventRecord(ev[4], st));
+  TCS_CUDA(cudaStreamSynchronize(st));
+  for (int k = 0; k < 4; ++k) {
+    TCS_CUDA(cudaEventElapsedTime(ms + k, ev[k], ev[k + 1]));
+    ms[k] /= static_cast<float>(reps);
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return TCS_OK;
+}
+
 // ---- CondVAE decoder --------------------------------------------------------------------------------------
 int tcs_vae_create(tcs_vae** out, const tcs_vae_config* cfg) {
   if (!out || !cfg) return fail(TCS_ERR_BAD_ARGUMENT, "tcs_vae_create: null argument");
@@ -579,8 +635,15 @@ int tcs_vae_create(tcs_vae** out, const tcs_vae_config* cfg) {
   if (cfg->z_dim < 1 || cfg->z_dim > 32 || cfg->n_types < 1 || cfg->y_cont_dim < 0 || cfg->y_cont_dim > 16)
     return fail(TCS_ERR_UNSUPPORTED, "tcs_vae_create: need 1 <= z_dim <= 32, n_types >= 1, 0 <= y_cont_dim <= 16");
   TCS_CHECK(check_device(cfg->device));
+  if (cfg->precision != TCS_FP32 && cfg->precision != TCS_BF16) return fail(TCS_ERR_BAD_ARGUMENT, "tcs_vae_create: bad precision");
   std::unique_ptr<tcs_vae> h(new tcs_vae());
   h->cfg = *cfg;
+  h->bf16 = cfg->precision == TCS_BF16;
+  {
+    cudaDeviceProp prop;
+    TCS_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    h->sm_count = prop.multiProcessorCount;
+  }
   TCS_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   TCS_CUDA(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
   TCS_CUDA(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
@@ -636,6 +699,12 @@ int tcs_vae_finalize_weights(tcs_vae* h) {
   h->fc_w = base + o_fcw; h->fc_b = base + o_fcb;
   for (int i = 0; i < 4; ++i) h->ct_w[i] = base + o_w[i];
   for (int i = 0; i < 3; ++i) h->ct_b[i] = base + o_b[i];
+  if (h->bf16) {   // bf16 copies of the packed weights of the three tensor-core stages
+    TCS_CHECK(h->arena16.ensure(blob.size() * 2));
+    TCS_CHECK(launch_f32_to_bf16(base, h->arena16.as<__nv_bfloat16>(), blob.size(), h->stream));
+    TCS_CUDA(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < 3; ++i) h->ct_w16[i] = h->arena16.as<__nv_bfloat16>() + o_w[i];
+  }
   h->finalized = true;
   return TCS_OK;
 }
@@ -653,19 +722,29 @@ int tcs_vae_decode(tcs_vae* h, const float* z, const int64_t* y_cat, const float
   cudaStream_t st = h->stream;
   const int zd = h->cfg.z_dim, ycd = h->cfg.y_cont_dim;
   const size_t cap = n < VAE_CHUNK ? n : VAE_CHUNK;
-  TCS_CHECK(h->a0.ensure(cap * 16 * 256 * 4));
-  TCS_CHECK(h->a1.ensure(cap * 64 * 128 * 4));
-  TCS_CHECK(h->a2.ensure(cap * 256 * 64 * 4));
-  TCS_CHECK(h->a3.ensure(cap * 1024 * 32 * 4));
+  const size_t esz = h->bf16 ? 2 : 4;
+  TCS_CHECK(h->a0.ensure(cap * 16 * 256 * esz));
+  TCS_CHECK(h->a1.ensure(cap * 64 * 128 * esz));
+  TCS_CHECK(h->a2.ensure(cap * 256 * 64 * esz));
+  TCS_CHECK(h->a3.ensure(cap * 1024 * 32 * esz));
+  static const int kHi[3] = {4, 8, 16}, kCi[3] = {256, 128, 64}, kCo[3] = {128, 64, 32};
+  DevBuf* act[4] = {&h->a0, &h->a1, &h->a2, &h->a3};
   for (int i0 = 0; i0 < n; i0 += VAE_CHUNK) {
     const int m = n - i0 < VAE_CHUNK ? n - i0 : VAE_CHUNK;
     h->launches += 5;
     TCS_CHECK(launch_vae_dec_fc(z + static_cast<size_t>(i0) * zd, y_cat + i0, y_cont + static_cast<size_t>(i0) * ycd, z_mean, z_std,
-                                h->fc_w, h->fc_b, m, zd, h->cfg.n_types, ycd, h->a0.as<float>(), st));
-    TCS_CHECK(launch_vae_convt(h->a0.as<float>(), h->ct_w[0], h->ct_b[0], m, 4, 256, 128, h->a1.as<float>(), st));
-    TCS_CHECK(launch_vae_convt(h->a1.as<float>(), h->ct_w[1], h->ct_b[1], m, 8, 128, 64, h->a2.as<float>(), st));
-    TCS_CHECK(launch_vae_convt(h->a2.as<float>(), h->ct_w[2], h->ct_b[2], m, 16, 64, 32, h->a3.as<float>(), st));
-    TCS_CHECK(launch_vae_convt_out(h->a3.as<float>(), h->ct_w[3], h->out_bias, m, x_out + static_cast<size_t>(i0) * 4096, st));
+                                h->fc_w, h->fc_b, m, zd, h->cfg.n_types, ycd, h->a0.p, h->bf16 ? 1 : 0, st));
+    for (int l = 0; l < 3; ++l) {
+      if (h->bf16) {   // tcgen05: the four parity classes of the layer as GEMMs with K = 4 taps x C_in
+        LinearTcPlan pl;
+        TCS_CHECK(linear_tc_make_convt_plan(&pl, act[l]->as<__nv_bfloat16>(), h->ct_w16[l], h->ct_b[l], m, kHi[l], kCi[l], kCo[l],
+                                            act[l + 1]->as<__nv_bfloat16>(), h->sm_count));
+        TCS_CHECK(linear_tc_launch(pl, st));
+      } else {
+        TCS_CHECK(launch_vae_convt(act[l]->as<float>(), h->ct_w[l], h->ct_b[l], m, kHi[l], kCi[l], kCo[l], act[l + 1]->as<float>(), st));
+      }
+    }
+    TCS_CHECK(launch_vae_convt_out(h->a3.p, h->bf16 ? 1 : 0, h->ct_w[3], h->out_bias, m, x_out + static_cast<size_t>(i0) * 4096, st));
   }
   return leave_h(h, user);
 }

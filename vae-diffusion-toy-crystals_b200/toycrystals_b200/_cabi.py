@@ -43,7 +43,8 @@ class TcsDdimArgs(C.Structure):
 
 
 class TcsVaeConfig(C.Structure):
-    _fields_ = [("z_dim", C.c_int32), ("n_types", C.c_int32), ("y_cont_dim", C.c_int32), ("device", C.c_int32)]
+    _fields_ = [("z_dim", C.c_int32), ("n_types", C.c_int32), ("y_cont_dim", C.c_int32), ("device", C.c_int32),
+                ("precision", C.c_int32)]
 
 
 # every symbol include/tcs.h and include/tcs_prior.h declare: name -> (restype, argtypes)
@@ -90,6 +91,7 @@ SIGNATURES = {
     "tcs_vae_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p]),
     "tcs_vae_launch_count": (C.c_int64, [C.c_void_p]),
+    "tcs_prior_profile": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_float)]),
     "tcs_debug_linear": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "tcs_debug_conv": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

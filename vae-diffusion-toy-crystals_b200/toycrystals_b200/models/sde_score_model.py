@@ -193,7 +193,37 @@ class CondUNetTiny(nn.Module):
         return _score(self, x_t, t, y_cat, y_cont, 0.0)
 
 
+_adopted: "Dict[int, Tuple[object, CondUNetTiny]]" = {}
+
+
+def adopt(model: nn.Module, precision: Optional[str] = None) -> CondUNetTiny:
+    """Accept ANY module that carries the reference ``CondUNetTiny`` state dict (e.g. the training script's ``model`` /
+    ``ema_model``, scripts/train_sde_score_model.py:263-279) and return the libtcs-backed equivalent, so the training-time
+    sampling hook ``save_sde_samples(model=sample_model, ...)`` runs on the fast path unchanged.  The architecture is read
+    off the tensor shapes; the weights are re-read whenever the source module's parameters changed (EMA updates)."""
+    if isinstance(model, CondUNetTiny):
+        return model
+    sd = model.state_dict()
+    try:
+        arch = dict(n_types=int(sd["cond_emb.cat_emb.weight"].shape[0]) - 1,
+                    y_cont_dim=int(sd["cond_emb.cont_mlp.0.weight"].shape[1]),
+                    base_ch=int(sd["down1.net.3.weight"].shape[0]), emb_dim=int(sd["time_mlp.0.weight"].shape[0]),
+                    cond_ch=int(sd["to_cond_map.weight"].shape[0]), time_ch=int(sd["to_time_map.weight"].shape[0]))
+    except KeyError as e:
+        raise TypeError(f"model does not carry the CondUNetTiny state dict (missing {e})") from None
+    ver = tuple((k, v.data_ptr(), v._version) for k, v in sd.items())
+    hit = _adopted.get(id(model))
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    fast = hit[1] if hit is not None else CondUNetTiny(**arch, precision=precision)
+    fast.load_state_dict(sd)
+    fast = fast.to(next(iter(sd.values())).device).eval()
+    _adopted[id(model)] = (ver, fast)
+    return fast
+
+
 def _score(model: CondUNetTiny, x_t, t, y_cat, y_cont, guidance: float) -> torch.Tensor:
+    model = adopt(model)
     h = model.engine_handle()
     dev = next(model.parameters()).device
     B, Cc, H, W = x_t.shape
@@ -248,6 +278,7 @@ class SamplerTrace:
 
 def _sample(model: CondUNetTiny, sde: VPSDE, y_cat, y_cont, img_shape, n_steps, guidance_scale, t_end, sampler: int,
             x_init=None, noise=None, seed=None, global_index_offset=0, return_trace=False):
+    model = adopt(model)
     device = y_cat.device
     B, Cc, H, W = img_shape
     assert Cc == 1
@@ -331,6 +362,7 @@ def condition_grid(model: CondUNetTiny, n: int, theta_max: float, device, offset
     """y_cat[i] = i % n_types, y_cont[i] = [0, linspace(0, theta_max, n)[i], 0, ...] (reference :317-321),
     generated on the device by libtcs; (offset, n_total) select a shard of a larger grid."""
     device = torch.device(device)
+    model = adopt(model)
     h = model.engine_handle()
     n_total = n if n_total is None else n_total
     y_cat = torch.empty((n,), device=device, dtype=torch.int64)
@@ -361,11 +393,13 @@ def _write_grid_png(x: torch.Tensor, out_path: str, title: str) -> None:
 def save_sde_samples(model: CondUNetTiny, sde: VPSDE, out_path: str, device: torch.device, n: int = 36,
                      theta_max: float = math.pi / 3.0, steps: int = 200, cfg: float = 0.0, t_end: float = 1e-3,
                      sampler: str = "ode") -> None:
-    """Save a 6x6 grid: cycle lattice types, sweep theta in [0, theta_max]."""
+    """Save a 6x6 grid: cycle lattice types, sweep theta in [0, theta_max].  ``model`` may be the libtcs-backed
+    CondUNetTiny or any module with the reference state dict (the training script's hook passes its own)."""
     model.eval()
     device = torch.device(device)
     if sampler not in ("ode", "sde"):
         raise ValueError(f"Unknown sampler='{sampler}'. Use 'ode' or 'sde'.")
+    model = adopt(model)
     y_cat, y_cont = condition_grid(model, n, theta_max, device)
     fn = sample_probability_flow_ode if sampler == "ode" else sample_reverse_sde_euler_maruyama
     x = fn(model=model, sde=sde, y_cat=y_cat, y_cont=y_cont, img_shape=(n, 1, 64, 64), n_steps=steps,

@@ -9,6 +9,7 @@ scope of this package and raise.  No CPU path.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -18,9 +19,19 @@ from .. import _cabi
 from .sde_score_model import _as_f32, _ptr, _stream_ptr
 
 
+_PRECISIONS = {"fp32": _cabi.FP32, "bf16": _cabi.BF16}
+
+
 class CondVAE(nn.Module):
-    def __init__(self, z_dim: int = 16, n_types: int = 4, y_cont_dim: int = 4, cond_drop: float = 0.1) -> None:
+    """``precision`` (keyword-only addition): "bf16" = the three wide ConvTranspose2d stages on the tensor cores (tcgen05,
+    bf16 activations/weights, fp32 accumulation; default), "fp32" = FFMA kernels (parity mode).  TCS_PRECISION overrides."""
+
+    def __init__(self, z_dim: int = 16, n_types: int = 4, y_cont_dim: int = 4, cond_drop: float = 0.1, *,
+                 precision: Optional[str] = None) -> None:
         super().__init__()
+        self.precision = (precision or os.environ.get("TCS_PRECISION", "bf16")).lower()
+        if self.precision not in _PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}, got {self.precision!r}")
         self.z_dim = z_dim
         self.n_types = n_types
         self.y_cont_dim = y_cont_dim
@@ -63,13 +74,14 @@ class CondVAE(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("toycrystals_b200 runs on a CUDA (B200, sm_100a) device only; move the model with "
                                ".to('cuda') — there is no CPU fallback (use the reference package for --device cpu)")
-        key = (dev, tuple((p.data_ptr(), p._version) for p in ps))
+        key = (dev, self.precision, tuple((p.data_ptr(), p._version) for p in ps))
         if self._handle is not None and key == self._handle_key:
             return self._handle
         self._release()
         L = _cabi.lib()
         cfg = _cabi.TcsVaeConfig(int(self.z_dim), int(self.n_types), int(self.y_cont_dim),
-                                 dev.index if dev.index is not None else torch.cuda.current_device())
+                                 dev.index if dev.index is not None else torch.cuda.current_device(),
+                                 _PRECISIONS[self.precision])
         h = C.c_void_p()
         _cabi.check(L.tcs_vae_create(C.byref(h), C.byref(cfg)))
         try:
