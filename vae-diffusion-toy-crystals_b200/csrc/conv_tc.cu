@@ -21,13 +21,14 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 namespace tcs {
 
 
 constexpr int EPI_WARPS = 8;
-constexpr int TC_THREADS = 64 + 32 * EPI_WARPS;
+constexpr int TC_THREADS = 64 + 32 * EPI_WARPS + 32;   // + a second MMA-issuing warp (warp 10) for the MSUB = 2 tiles
 constexpr int MAX_STAGES = 8;
 constexpr uint32_t EPI_SLAB_BYTES = EPI_WARPS * 4096;   // one 32x32 fp32 slab per epilogue warp
 constexpr uint32_t EPI_BIAS_BYTES = 576 * 4;
@@ -181,7 +182,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   __shared__ TcBarriers bars;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler (uniform datapath)
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const int n_tiles = p.n_mtiles * p.n_ntiles;
@@ -200,10 +201,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     if (EPI != EPI_PLAIN && EPI != EPI_EPS) ptx::prefetch_tmap(&mapO);
     for (int s = 0; s < p.nstage; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bars.full[s]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bars.empty[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bars.empty[s]), p.issuers);     // one tcgen05.commit per issuing thread
     }
     for (int a = 0; a < 2; ++a) {
-      ptx::mbar_init(ptx::smem_u32(&bars.tmem_full[a]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bars.tmem_full[a]), p.issuers);
       ptx::mbar_init(ptx::smem_u32(&bars.tmem_empty[a]), 4 * CG);
     }
     ptx::fence_barrier_init();
@@ -237,6 +238,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           for (int kyg = 0; kyg < p.KYG; ++kyg)
             for (int kx = 0; kx < p.KW; ++kx, ++ks) {
               ptx::mbar_wait(ptx::smem_u32(&bars.empty[stage]), phase ^ 1);
+              if ((p.debug & 8) && (phase || tile != static_cast<int>(blockIdx.x))) {   // experiment: stale operands, no TMA
+                if (lane == 0 && (CG == 1 || cta_rank == 0)) ptx::mbar_arrive(ptx::smem_u32(&bars.full[stage]));
+                __syncwarp();
+                if (++stage == static_cast<uint32_t>(p.nstage)) { stage = 0; phase ^= 1; }
+                continue;
+              }
               if (lane == 0) {
                 const uint32_t full = ptx::smem_u32(&bars.full[stage]);
                 const uint32_t a_dst = smem_base + stage * p.stage_bytes;
@@ -265,52 +272,70 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             }
       }
     }
-  } else if (warp == 1 && cta_rank == 0) {
+  } else if ((warp == 1 || (warp == 2 + EPI_WARPS && p.issuers == 2)) && cta_rank == 0) {
     // ============================== MMA issuer (leader CTA only when CG == 2) ====
+    // The issue loop is the critical resource of this kernel: one thread needs ~60 cycles per tcgen05.mma (descriptor
+    // arithmetic on the uniform datapath + the elect loop the compiler wraps around UTCHMMA), more than the 48 tensor
+    // cycles an N = 96 MMA takes (measured: with the epilogue and the TMA loads switched off the N = 96 layers ran at
+    // 770 TFLOP/s with one issuing thread and 990 with two).  With p.issuers == 2 the two 128-row sub-tiles of a tile
+    // are issued by two warps (sub 0: warp 1, sub 1: warp 10); each commits its own MMAs, so the stage / accumulator
+    // barriers expect two arrivals.  The sub-tile range and the tap count are compile-time in mma_role.
     constexpr uint32_t idesc = make_idesc(128 * CG, N);
-    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
     const uint32_t row_shift = p.W * 64;  // one image row inside the window
     const uint32_t sub_stride = p.pair ? p.a_bytes / 2 : p.Rt * row_shift;  // second sub-tile: next window / next rows
     const uint32_t a_inc_j = row_shift >> 4, a_inc_sub = sub_stride >> 4;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      ptx::mbar_wait(ptx::smem_u32(&bars.tmem_empty[acc]), acc_phase ^ 1);
-      ptx::tc_fence_after();
-      for (int ks = 0; ks < p.kstages; ++ks) {
-        ptx::mbar_wait(ptx::smem_u32(&bars.full[stage]), phase);
+    auto run = [&](auto sub_lo_c, auto sub_hi_c) {
+      constexpr int SUB_LO = decltype(sub_lo_c)::value, SUB_HI = decltype(sub_hi_c)::value;
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(ptx::smem_u32(&bars.tmem_empty[acc]), acc_phase ^ 1);
         ptx::tc_fence_after();
-        if (lane == 0) {
-          // descriptors: one base per operand and stage, then 16-byte-unit increments (the issuing thread must
-          // sustain one MMA per 48 tensor cycles at N = 96, so the per-MMA scalar work is kept to a few adds)
-          const uint32_t a_base = smem_base + stage * p.stage_bytes;
-          const uint64_t adesc = make_desc_sw64(a_base), bdesc = make_desc_sw64(a_base + p.a_bytes);
-          const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
-          for (int j = 0; j < p.T; ++j) {
+        for (int ks = 0; ks < p.kstages; ++ks) {
+          ptx::mbar_wait(ptx::smem_u32(&bars.full[stage]), phase);
+          ptx::tc_fence_after();
+          if (lane == 0) {
+            // descriptors: one base per operand and stage, then 16-byte-unit increments
+            const uint32_t a_base = smem_base + stage * p.stage_bytes;
+            const uint64_t adesc = make_desc_sw64(a_base), bdesc = make_desc_sw64(a_base + p.a_bytes);
+            const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
+            for (int j = 0; j < p.T; ++j) {
 #pragma unroll
-            for (int sub = 0; sub < MSUB; ++sub) {
+              for (int sub = SUB_LO; sub < SUB_HI; ++sub) {
 #pragma unroll
-              for (int k = 0; k < 2; ++k) {
-                const uint64_t ad = adesc + (j * a_inc_j + sub * a_inc_sub + k * 2);
-                const uint64_t bd = bdesc + (j * ((NB * 64) >> 4) + k * 2);
-                const uint32_t accum = (ks | j | k) != 0 ? 1u : 0u;
-                if (CG == 2) ptx::umma_bf16_2sm(d_tmem + sub * N, ad, bd, idesc, accum);
-                else ptx::umma_bf16(d_tmem + sub * N, ad, bd, idesc, accum);
+                for (int k = 0; k < 2; ++k) {
+                  const uint64_t ad = adesc + (j * a_inc_j + sub * a_inc_sub + k * 2);
+                  const uint64_t bd = bdesc + (j * ((NB * 64) >> 4) + k * 2);
+                  const uint32_t accum = (ks | j | k) != 0 ? 1u : 0u;
+                  if (CG == 2) ptx::umma_bf16_2sm(d_tmem + sub * N, ad, bd, idesc, accum);
+                  else ptx::umma_bf16(d_tmem + sub * N, ad, bd, idesc, accum);
+                }
               }
             }
+            if (CG == 2) {
+              ptx::umma_commit_2sm(ptx::smem_u32(&bars.empty[stage]));
+              if (ks == p.kstages - 1) ptx::umma_commit_2sm(ptx::smem_u32(&bars.tmem_full[acc]));
+            } else {
+              ptx::umma_commit(ptx::smem_u32(&bars.empty[stage]));
+              if (ks == p.kstages - 1) ptx::umma_commit(ptx::smem_u32(&bars.tmem_full[acc]));
+            }
           }
-          if (CG == 2) {
-            ptx::umma_commit_2sm(ptx::smem_u32(&bars.empty[stage]));
-            if (ks == p.kstages - 1) ptx::umma_commit_2sm(ptx::smem_u32(&bars.tmem_full[acc]));
-          } else {
-            ptx::umma_commit(ptx::smem_u32(&bars.empty[stage]));
-            if (ks == p.kstages - 1) ptx::umma_commit(ptx::smem_u32(&bars.tmem_full[acc]));
-          }
+          __syncwarp();
+          if (++stage == static_cast<uint32_t>(p.nstage)) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == static_cast<uint32_t>(p.nstage)) { stage = 0; phase ^= 1; }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    };
+    using I0 = std::integral_constant<int, 0>;
+    using I1 = std::integral_constant<int, 1>;
+    using IM = std::integral_constant<int, MSUB>;
+    using IL = std::integral_constant<int, MSUB - 1>;
+    if (p.issuers == 2) {
+      if (warp == 1) run(I0{}, I1{});
+      else run(IL{}, IM{});
+    } else {
+      run(I0{}, IM{});
     }
-  } else if (warp >= 2) {
+  } else if (warp >= 2 && warp < 2 + EPI_WARPS) {
     // ============================== epilogue (2 groups x 4 warps) ================
     // Group grp = 0/1 owns TMEM accumulator set grp and therefore every second tile of this CTA; inside a
     // group warp q = warp % 4 reads TMEM lane quarter q: 32 pixel rows x all MSUB*N = 192 columns.  A group has
@@ -333,6 +358,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       ptx::mbar_wait(ptx::smem_u32(&bars.tmem_full[acc]), acc_phase);
       ptx::tc_fence_after();
 
+      if (p.debug & 16) {   // experiment: no epilogue work at all
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2) ptx::mbar_arrive_rank0(ptx::smem_u32(&bars.tmem_empty[acc]));
+          else ptx::mbar_arrive(ptx::smem_u32(&bars.tmem_empty[acc]));
+        }
+        continue;
+      }
       if constexpr (EPI == EPI_EPS) {
         // ---- 96 -> 1 output conv: column 0 of each sub-tile's accumulator is eps; CFG combine in registers
         float v0, v1;
@@ -349,6 +383,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           eo[static_cast<size_t>(mt) * 256 + 128 + row] = v1;
         }
       } else if constexpr (EPI == EPI_GN_FUSED) {
+        if (p.debug & 32) {   // experiment: the two TMEM passes alone (12 x tcgen05.ld.x32 per warp), nothing else
+          float vb[32], s = 0.f;
+#pragma unroll 1
+          for (int k = 0; k < 12; ++k) {
+            ptx::tmem_ld32(tbase + (k % 6) * 32, vb);
+            ptx::tmem_ld_wait();
+            s += vb[k];
+          }
+          if (s == 1.2345e-30f) static_cast<float*>(p.epi.out)[0] = s;
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (CG == 2) ptx::mbar_arrive_rank0(ptx::smem_u32(&bars.tmem_empty[acc]));
+            else ptx::mbar_arrive(ptx::smem_u32(&bars.tmem_empty[acc]));
+          }
+          continue;
+        }
         // ---- conv + bias + GroupNorm + SiLU without leaving TMEM ----------------------------------
         // The G = tiles_per_img CTAs with blockIdx % G == 0..G-1 hold one image between them and run it
         // in lock step.  pass 1: per-group sums of this CTA's pixels -> global, arrive on the image's
@@ -792,6 +843,10 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, con
   }
   if (g.H % (pl.msub * (128 / g.W))) return fail(TCS_ERR_UNSUPPORTED, "conv_tc: image height not a multiple of the tile");
   p.debug = getenv("TCS_DEBUG") ? atoi(getenv("TCS_DEBUG")) : 0;
+  {
+    const char* e = getenv("TCS_ISSUERS");   // 1 = a single MMA-issuing thread everywhere (A/B switch)
+    p.issuers = (pl.msub == 2 && !(e && atoi(e) == 1)) ? 2 : 1;
+  }
   stage_shape(g, &p.T, &p.KYG, &p.KW);
   p.H = g.H; p.W = g.W; p.Rt = 128 / g.W;
   p.stride = g.stride;

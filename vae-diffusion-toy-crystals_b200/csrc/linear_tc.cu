@@ -81,7 +81,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   constexpr int ACC_COLS = 256;
   extern __shared__ uint8_t smem_raw[];
   __shared__ LtBarriers bars;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const int n_tiles = p.n_mtiles * p.n_ntiles;
   constexpr int NB = LT_BN / CG;                 // W rows this CTA stages per K block
