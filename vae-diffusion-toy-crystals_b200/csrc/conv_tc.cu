@@ -19,6 +19,7 @@
 #include "conv_tc.cuh"
 #include "tc_ptx.cuh"
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <type_traits>
@@ -30,16 +31,13 @@ namespace tcs {
 constexpr int EPI_WARPS = 8;
 constexpr int TC_THREADS = 64 + 32 * EPI_WARPS + 32;   // + a second MMA-issuing warp (warp 10) for the MSUB = 2 tiles
 constexpr int MAX_STAGES = 8;
-constexpr uint32_t EPI_SLAB_BYTES = EPI_WARPS * 4096;   // one 32x32 fp32 slab per epilogue warp
+constexpr uint32_t EPI_SLAB_BYTES = EPI_WARPS * 6144;   // per epilogue warp: three 32 px x 32 ch bf16 blocks (or one 32x32 fp32 slab)
 constexpr uint32_t EPI_BIAS_BYTES = 576 * 4;
-struct EpiGroupSmem {          // per epilogue warp group (EPI_GN_FUSED)
-  float scale[192], shift[192];
-  float red[4][16];
-  float mean[8], rstd[8];
-};
 struct EpiFusedSmem {          // EPI_GN_FUSED scratch (lives right after the bias)
   float gamma[192], beta[192];
-  EpiGroupSmem grp[2];
+  float scale[192], shift[192];
+  float red[EPI_WARPS][16];    // per epilogue warp: (sum, sum of squares) of the 8 GroupNorm groups over its block
+  float mean[8], rstd[8];
 };
 constexpr uint32_t EPI_FUSED_BYTES = sizeof(EpiFusedSmem);
 
@@ -48,10 +46,18 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void st_relaxed_gpu_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
   asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void epi_bar_sync(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory"); }
+__device__ __forceinline__ void epi_bar_sync_all() { asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory"); }
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
@@ -89,6 +95,45 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
+}
+// Staged variant used by the 8-warp epilogue: a warp writes its THREE 32-pixel x 32-channel blocks of a tile into its
+// 6 KB slab (stage_padded_block), then pays the generic->async proxy fence once and issues all TMA stores
+// (flush_padded_blocks).  One fence per block made the stores ~800 cycles each (measured).
+__device__ __forceinline__ void stage_padded_block(bool use_tma, uint32_t slab, int k, int lane, __nv_bfloat16* obase,
+                                                   size_t pix, int wy, int wx, int Wp, int ldo, int ch, const uint32_t* pk) {
+  if (!use_tma) {
+    store_with_halo(obase, pix, wy, wx, Wp, ldo, ch, pk);
+    return;
+  }
+  const uint32_t dst = slab + k * 2048 + lane * 64;
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) st_shared_u4(dst + ((j ^ sw) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+  if (wx) {   // column halo (and the corner when this pixel is also on a border row)
+    uint4* d0 = reinterpret_cast<uint4*>(obase + (pix + wx) * ldo + ch);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d0[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+    if (wy) {
+      uint4* d1 = reinterpret_cast<uint4*>(obase + (pix + static_cast<long long>(wy) * Wp + wx) * ldo + ch);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) d1[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+    }
+  }
+}
+// ch0: channel of block 0 (blocks are 32 channels apart); lane 0 holds the first pixel (y, x) of the 32-pixel run
+__device__ __forceinline__ void flush_padded_blocks(const CUtensorMap* mapO, bool use_tma, uint32_t slab, int lane, int ch0,
+                                                    int img, int y, int x, int wy) {
+  if (!use_tma) return;
+  ptx::fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      tma_store_4d(mapO, slab + k * 2048, ch0 + k * 32, x + 1, y + 1, img);
+      if (wy) tma_store_4d(mapO, slab + k * 2048, ch0 + k * 32, x + 1, y + 1 + wy, img);
+    }
+    ptx::bulk_commit();
+  }
 }
 // 32 pixels (one per lane, consecutive in an image row) x 32 bf16 channels -> padded NHWC output.
 // W >= 32: the warp stages the 2 KB block in a SWIZZLE_64B slab and one lane TMA-stores it (plus the wrapped
@@ -205,7 +250,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(ptx::smem_u32(&bars.tmem_full[a]), p.issuers);
-      ptx::mbar_init(ptx::smem_u32(&bars.tmem_empty[a]), 4 * CG);
+      ptx::mbar_init(ptx::smem_u32(&bars.tmem_empty[a]), EPI_WARPS * CG);
     }
     ptx::fence_barrier_init();
   }
@@ -287,12 +332,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     auto run = [&](auto sub_lo_c, auto sub_hi_c) {
       constexpr int SUB_LO = decltype(sub_lo_c)::value, SUB_HI = decltype(sub_hi_c)::value;
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      const bool prof = (p.debug & 128) && blockIdx.x == 0 && warp == 1;
+      long long w_empty = 0, w_full = 0, t_begin = prof ? clock64() : 0;
+      int ntile = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        long long c0 = prof ? clock64() : 0;
         ptx::mbar_wait(ptx::smem_u32(&bars.tmem_empty[acc]), acc_phase ^ 1);
         ptx::tc_fence_after();
+        if (prof) { w_empty += clock64() - c0; ++ntile; }
         for (int ks = 0; ks < p.kstages; ++ks) {
+          c0 = prof ? clock64() : 0;
           ptx::mbar_wait(ptx::smem_u32(&bars.full[stage]), phase);
           ptx::tc_fence_after();
+          if (prof) w_full += clock64() - c0;
           if (lane == 0) {
             // descriptors: one base per operand and stage, then 16-byte-unit increments
             const uint32_t a_base = smem_base + stage * p.stage_bytes;
@@ -324,6 +376,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+      if (prof && lane == 0)
+        printf("[mma N=%d EPI=%d K=%d] tiles %d  cycles/tile %lld  wait tmem_empty %lld  wait full %lld\n", N, EPI, p.kstages, ntile,
+               (clock64() - t_begin) / (ntile ? ntile : 1), w_empty / (ntile ? ntile : 1), w_full / (ntile ? ntile : 1));
     };
     using I0 = std::integral_constant<int, 0>;
     using I1 = std::integral_constant<int, 1>;
@@ -336,317 +391,54 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       run(I0{}, IM{});
     }
   } else if (warp >= 2 && warp < 2 + EPI_WARPS) {
-    // ============================== epilogue (2 groups x 4 warps) ================
-    // Group grp = 0/1 owns TMEM accumulator set grp and therefore every second tile of this CTA; inside a
-    // group warp q = warp % 4 reads TMEM lane quarter q: 32 pixel rows x all MSUB*N = 192 columns.  A group has
-    // two tile periods for its epilogue, so the inter-CTA GroupNorm wait of one tile overlaps the other
-    // group's work instead of stalling the tensor pipe.
-    const int e = warp - 2, q = warp & 3, grp = e >> 2;
+    // ============================== epilogue (8 warps, every tile) ================
+    // Measured (TCS_DEBUG 16/32): reading accumulators out of TMEM stalls the tensor pipe (about 32 B/clk per SM), so an
+    // epilogue that reads them twice (GroupNorm statistics, then normalise) cost ~40 % of a K = 864 layer.  Now every
+    // accumulator element is read exactly ONCE: warp (q, h) = (TMEM lane quarter, unit) pulls its 32 rows x 96 columns
+    // into registers with three back-to-back tcgen05.ld, releases the accumulator set at once (the MMA warp can start
+    // tile i+2 while this tile's GroupNorm exchange is still in flight) and does everything else from registers.
+    // unit h: MSUB == 2 -> 128-row sub-tile h (all N = 96 channels); MSUB == 1 -> channel half h of the N = 192 tile.
+    const int e = warp - 2, q = warp & 3, h = e >> 2;
     const int row = q * 32 + lane;
     const int HW = p.H * p.W;
     const int Wp = p.W + 2, Hp = p.H + 2;
-    const uint32_t acc = grp;
-    uint32_t acc_phase = 0, slab_buf = 0;
-    (void)slab_buf;
-    EpiGroupSmem* gsm = &fs->grp[grp];
-    const uint32_t slab = slab_base + static_cast<uint32_t>(e) * 4096;      // this warp's 2 x 2 KB staging halves
+    uint32_t slab_buf = 0;
+    (void)slab_buf; (void)Hp; (void)Wp; (void)HW;
+    const uint32_t slab = slab_base + static_cast<uint32_t>(e) * 6144;      // this warp's 3 x 2 KB staging blocks
     const bool use_tma_out = p.W >= 32 && !(p.debug & 4);
-    for (int tile = blockIdx.x + grp * gridDim.x; tile < n_tiles; tile += 2 * gridDim.x, acc_phase ^= 1) {
+    (void)use_tma_out;
+    const int sub = (MSUB == 2) ? h : 0;
+    const int col0 = (MSUB == 2) ? 0 : h * 96;          // first channel (inside the N tile) of this warp's columns
+    uint32_t it = 0;
+    const bool prof = (p.debug & 128) && blockIdx.x == 0 && e == 0;
+    long long pw_full = 0, p_ld = 0, p_a = 0, p_b = 0, p_c = 0, pc0 = 0, pc1 = 0, q_post = 0, q_poll = 0, q_npoll = 0, r_ss = 0, r_math = 0, r_store = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       int mt, nt;
       tile_to_mn<CG>(tile, p.n_ntiles, mt, nt);
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_STRIDE;
+      if (prof) { pc1 = clock64(); if (it) p_c += pc1 - pc0; pc0 = pc1; }
       ptx::mbar_wait(ptx::smem_u32(&bars.tmem_full[acc]), acc_phase);
       ptx::tc_fence_after();
+      if (prof) { pc1 = clock64(); pw_full += pc1 - pc0; pc0 = pc1; }
 
-      if (p.debug & 16) {   // experiment: no epilogue work at all
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (CG == 2) ptx::mbar_arrive_rank0(ptx::smem_u32(&bars.tmem_empty[acc]));
-          else ptx::mbar_arrive(ptx::smem_u32(&bars.tmem_empty[acc]));
-        }
-        continue;
-      }
-      if constexpr (EPI == EPI_EPS) {
-        // ---- 96 -> 1 output conv: column 0 of each sub-tile's accumulator is eps; CFG combine in registers
-        float v0, v1;
-        ptx::tmem_ld1(tbase, &v0);
-        ptx::tmem_ld1(tbase + N, &v1);
-        ptx::tmem_ld_wait();
-        v0 += bias_s[0];
-        v1 += bias_s[0];
-        float* eo = static_cast<float*>(p.epi.out);
-        if (p.pair) {          // sub-tile 0 = conditional image 2i, sub-tile 1 = unconditional image 2i+1
-          eo[static_cast<size_t>(mt) * 128 + row] = v1 + p.guidance * (v0 - v1);
+      // ---- the only TMEM traffic of the tile ------------------------------------------------------------------
+      float v[96];
+      float e0 = 0.f, e1 = 0.f;
+      (void)e0; (void)e1;
+      if (!(p.debug & 16)) {
+        if constexpr (EPI == EPI_EPS) {
+          if (h == 0) {       // column 0 of each sub-tile's accumulator is eps
+            ptx::tmem_ld1(tbase, &e0);
+            ptx::tmem_ld1(tbase + N, &e1);
+            ptx::tmem_ld_wait();
+          }
         } else {
-          eo[static_cast<size_t>(mt) * 256 + row] = v0;
-          eo[static_cast<size_t>(mt) * 256 + 128 + row] = v1;
-        }
-      } else if constexpr (EPI == EPI_GN_FUSED) {
-        if (p.debug & 32) {   // experiment: the two TMEM passes alone (12 x tcgen05.ld.x32 per warp), nothing else
-          float vb[32], s = 0.f;
-#pragma unroll 1
-          for (int k = 0; k < 12; ++k) {
-            ptx::tmem_ld32(tbase + (k % 6) * 32, vb);
-            ptx::tmem_ld_wait();
-            s += vb[k];
-          }
-          if (s == 1.2345e-30f) static_cast<float*>(p.epi.out)[0] = s;
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (CG == 2) ptx::mbar_arrive_rank0(ptx::smem_u32(&bars.tmem_empty[acc]));
-            else ptx::mbar_arrive(ptx::smem_u32(&bars.tmem_empty[acc]));
-          }
-          continue;
-        }
-        // ---- conv + bias + GroupNorm + SiLU without leaving TMEM ----------------------------------
-        // The G = tiles_per_img CTAs with blockIdx % G == 0..G-1 hold one image between them and run it
-        // in lock step.  pass 1: per-group sums of this CTA's pixels -> global, arrive on the image's
-        // counter, wait for the other G-1 CTAs; pass 2: normalise + SiLU straight from TMEM.
-        constexpr int CPGN = N / 8;            // channels per group: 12 or 24
-        const int G = p.tiles_per_img;
-        const int img = mt / G;
-        float gs[8], gq[8];        // per group: (even-column, odd-column) partial sums kept packed
-        float gs1[8], gq1[8];
-#pragma unroll
-        for (int g = 0; g < 8; ++g) gs[g] = gq[g] = gs1[g] = gq1[g] = 0.f;
-        {
-          // six 32-column chunks (two 96-column units); the TMEM load of chunk k+1 is in flight while chunk k is
-          // reduced (tcgen05.wait::ld waits for everything outstanding, so it sits right before the next issue)
-          float vbuf[2][32];
-          ptx::tmem_ld32(tbase, vbuf[0]);
-#pragma unroll
-          for (int k = 0; k < 6; ++k) {
-            ptx::tmem_ld_wait();
-            if (k < 5) ptx::tmem_ld32(tbase + (k + 1) * 32, vbuf[(k + 1) & 1]);
-            const float* v = vbuf[k & 1];
-            const int cc = (MSUB == 2) ? (k % 3) * 32 : k * 32;     // channel of the chunk's first column
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + cc + i);
-              float t0, t1, t2, t3;
-              add2(t0, t1, v[i], v[i + 1], b4.x, b4.y);
-              add2(t2, t3, v[i + 2], v[i + 3], b4.z, b4.w);
-              const int g0 = (cc + i) / CPGN, g1 = (cc + i + 2) / CPGN;   // pairs never straddle a group
-              add2(gs[g0], gs1[g0], gs[g0], gs1[g0], t0, t1);
-              fma2(gq[g0], gq1[g0], t0, t1, t0, t1, gq[g0], gq1[g0]);
-              add2(gs[g1], gs1[g1], gs[g1], gs1[g1], t2, t3);
-              fma2(gq[g1], gq1[g1], t2, t3, t2, t3, gq[g1], gq1[g1]);
-            }
-          }
-        }
-        // lane reduction as a reduce-scatter: 16 values -> 8 -> 4 -> 2 -> 1 per lane (16 shuffles instead of 80);
-        // lane L ends with the warp total of value index bits(L>>1) for lanes with even L
-        float rv[16];
-#pragma unroll
-        for (int g = 0; g < 8; ++g) { rv[2 * g] = gs[g] + gs1[g]; rv[2 * g + 1] = gq[g] + gq1[g]; }
-#pragma unroll
-        for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
-          const bool hi = (lane & off) != 0;
-#pragma unroll
-          for (int i = 0; i < half; ++i) {
-            const float send = hi ? rv[i] : rv[i + half];
-            const float keep = hi ? rv[i + half] : rv[i];
-            rv[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-          }
-        }
-        rv[0] += __shfl_xor_sync(0xffffffffu, rv[0], 1);
-        if ((lane & 1) == 0) {
-          const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-          gsm->red[q][idx] = rv[0];
-        }
-        epi_bar_sync(grp);
-        if (q == 2) {   // warps 2 and 6 are the groups' leaders (warp % 4 == 2)
-          float* gpart = p.epi.partials + static_cast<size_t>(mt) * 16;
-          if (lane < 16) {
-            __stcg(gpart + lane, (gsm->red[0][lane] + gsm->red[1][lane]) + (gsm->red[2][lane] + gsm->red[3][lane]));
-            __threadfence();
-          }
-          __syncwarp();
-          if (lane == 0) {
-            red_release_gpu_add(p.epi.counters + img, 1);
-            const long long t0 = clock64();
-            while (!(p.debug & 1) && ld_acquire_gpu(p.epi.counters + img) < G) {
-              if (clock64() - t0 > 4000000000LL) __trap();
-            }
-          }
-          __syncwarp();
-          __threadfence();
-          // 16 values x G CTAs: lane l sums value (l & 15) over the CTAs of parity (l >> 4), fixed order
-          const float* ip = p.epi.partials + static_cast<size_t>(img) * G * 16 + (lane & 15);
-          float part = 0.f;
-          for (int k = lane >> 4; k < G; k += 2) part += __ldcg(ip + k * 16);
-          part += __shfl_xor_sync(0xffffffffu, part, 16);
-          const float qsum = __shfl_down_sync(0xffffffffu, part, 1);   // lane 2g: sum, lane 2g+1: sum of squares
-          if (lane < 16 && (lane & 1) == 0) {
-            const double cnt = static_cast<double>(HW) * CPGN;
-            const double mean = static_cast<double>(part) / cnt;
-            double var = static_cast<double>(qsum) / cnt - mean * mean;
-            var = var < 0.0 ? 0.0 : var;
-            gsm->mean[lane >> 1] = static_cast<float>(mean);
-            gsm->rstd[lane >> 1] = rsqrtf(static_cast<float>(var) + GN_EPS);
-          }
-        }
-        epi_bar_sync(grp);
-        for (int c = threadIdx.x - 64 - grp * 128; c < N; c += 128) {
-          const int g = c / CPGN;
-          const float sc = gsm->rstd[g] * fs->gamma[c];
-          gsm->scale[c] = 0.5f * sc;                                                  // h = y / 2 = v * scale + shift
-          gsm->shift[c] = 0.5f * ((bias_s[c] - gsm->mean[g]) * sc + fs->beta[c]);
-        }
-        epi_bar_sync(grp);
-        __nv_bfloat16* obase = static_cast<__nv_bfloat16*>(p.epi.out);
-        {
-          float vbuf[2][32];
-          ptx::tmem_ld32(tbase, vbuf[0]);
-#pragma unroll
-          for (int k = 0; k < 6; ++k) {
-            ptx::tmem_ld_wait();
-            if (k < 5) ptx::tmem_ld32(tbase + (k + 1) * 32, vbuf[(k + 1) & 1]);
-            const float* v = vbuf[k & 1];
-            const int sub = (MSUB == 2) ? k / 3 : 0;
-            const int cc = (MSUB == 2) ? (k % 3) * 32 : k * 32;
-            const int m = (mt * MSUB + sub) * 128 + row;
-            const int rem = m - img * HW;
-            const int y = rem / p.W, x = rem - y * p.W;
-            const int wy = (y == 0) ? p.H : ((y == p.H - 1) ? -p.H : 0);
-            const int wx = (x == 0) ? p.W : ((x == p.W - 1) ? -p.W : 0);
-            const size_t pix = (static_cast<size_t>(img) * Hp + (y + 1)) * Wp + (x + 1);
-            uint32_t pk[16];
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 s4 = *reinterpret_cast<const float4*>(gsm->scale + cc + i);
-              const float4 h4 = *reinterpret_cast<const float4*>(gsm->shift + cc + i);
-              float h0, h1, h2, h3, y0, y1, y2, y3;
-              fma2(h0, h1, v[i], v[i + 1], s4.x, s4.y, h4.x, h4.y);          // h = y/2
-              fma2(h2, h3, v[i + 2], v[i + 3], s4.z, s4.w, h4.z, h4.w);
-              fma2(y0, y1, h0, h1, tanh_fast(h0), tanh_fast(h1), h0, h1);    // SiLU(y) = h + h tanh(h)
-              fma2(y2, y3, h2, h3, tanh_fast(h2), tanh_fast(h3), h2, h3);
-              pk[i / 2] = pack_bf16x2(y0, y1);
-              pk[i / 2 + 1] = pack_bf16x2(y2, y3);
-            }
-            if (!(p.debug & 2))
-              store_padded_block(&mapO, use_tma_out, slab, slab_buf, lane, obase, pix, wy, wx, Wp, p.epi.ldo, cc, img, y, x, pk);
-            else if (pk[0] == 0x12345678u && pk[7] == 0x9abcdef0u) obase[0] = __float2bfloat16(0.f);
-          }
-        }
-      } else if constexpr (N >= 96) {
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int sub = (MSUB == 2) ? u : 0;
-          const int col0 = (MSUB == 2) ? 0 : u * 96;
-          const int n_off = nt * N + col0;                     // first output channel of this unit
-          const int m = (mt * MSUB + sub) * 128 + row;         // global pixel index (b, y, x)
-          const uint32_t taddr = tbase + u * 96;
-          if constexpr (EPI == EPI_RAW_STATS) {
-            // fp32 tile -> swizzled 32x32 slab in shared memory -> TMA store (full 128 B lines, no LSU), plus
-            // per-(warp, group) partial sums for a separate GroupNorm pass (the unfused A/B path)
-            constexpr int CPGN = N / 8;
-            constexpr int NG = 96 / CPGN;
-            float gs[NG], gq[NG];
-#pragma unroll
-            for (int g = 0; g < NG; ++g) gs[g] = gq[g] = 0.f;
-            const int m_base = (mt * MSUB + sub) * 128 + q * 32;
-#pragma unroll
-            for (int c0 = 0; c0 < 96; c0 += 32) {
-              float v[32];
-              ptx::tmem_ld32(taddr + c0, v);
-              ptx::tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n_off + c0 + i);
-                v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
-              }
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                gs[(c0 + i) / CPGN] += v[i];
-                gq[(c0 + i) / CPGN] += v[i] * v[i];
-              }
-              if (lane == 0) ptx::bulk_wait_read<0>();   // the previous store has finished reading the slab
-              __syncwarp();
-              const uint32_t dst = slab + lane * 128;
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                ptx::st_shared_v4(dst + ((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-              ptx::fence_proxy_async();
-              __syncwarp();
-              if (lane == 0) {
-                ptx::tma_store_2d(&mapO, slab, n_off + c0, m_base);
-                ptx::bulk_commit();
-              }
-            }
-#pragma unroll
-            for (int g = 0; g < NG; ++g) {
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) {
-                gs[g] += __shfl_xor_sync(0xffffffffu, gs[g], o);
-                gq[g] += __shfl_xor_sync(0xffffffffu, gq[g], o);
-              }
-            }
-            if (lane == 0) {
-              // slot layout [image][tile-in-image*MSUB + sub][quarter]; with MSUB == 1 the two column halves
-              // write disjoint groups of the same slot
-              const int b = m / HW;
-              const int slot = ((mt * MSUB + sub) % (p.tiles_per_img * MSUB)) * 4 + q;
-              float* dst = p.epi.partials + (static_cast<size_t>(b) * p.epi.slots + slot) * 16 + 2 * (col0 / CPGN);
-#pragma unroll
-              for (int g = 0; g < NG; ++g) { dst[2 * g] = gs[g]; dst[2 * g + 1] = gq[g]; }
-            }
-          } else if constexpr (EPI == EPI_PADDED) {
-            const int b = m / HW, rem = m - b * HW;
-            const int y = rem / p.W, x = rem - y * p.W;
-            const int wy = (y == 0) ? p.H : ((y == p.H - 1) ? -p.H : 0);
-            const int wx = (x == 0) ? p.W : ((x == p.W - 1) ? -p.W : 0);
-            __nv_bfloat16* obase = static_cast<__nv_bfloat16*>(p.epi.out);
-            const size_t pix = (static_cast<size_t>(b) * Hp + (y + 1)) * Wp + (x + 1);
-            const __nv_bfloat16* rrow =
-                p.epi.residual ? static_cast<const __nv_bfloat16*>(p.epi.residual) + pix * p.ntot + n_off : nullptr;
-#pragma unroll
-            for (int c0 = 0; c0 < 96; c0 += 32) {
-              float v[32];
-              ptx::tmem_ld32(taddr + c0, v);
-              ptx::tmem_ld_wait();
-              if (rrow) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const uint4 rr = *reinterpret_cast<const uint4*>(rrow + c0 + i * 8);
-                  const uint32_t w4[4] = {rr.x, rr.y, rr.z, rr.w};
-#pragma unroll
-                  for (int k = 0; k < 4; ++k) {
-                    const float2 rf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[k]));
-                    v[i * 8 + 2 * k] += rf.x;
-                    v[i * 8 + 2 * k + 1] += rf.y;
-                  }
-                }
-              }
-              uint32_t pk[16];
-#pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n_off + c0 + i);
-                pk[i / 2] = pack_bf16x2(v[i] + b4.x, v[i + 1] + b4.y);
-                pk[i / 2 + 1] = pack_bf16x2(v[i + 2] + b4.z, v[i + 3] + b4.w);
-              }
-              store_padded_block(&mapO, use_tma_out, slab, slab_buf, lane, obase, pix, wy, wx, Wp, p.epi.ldo, n_off + c0, b, y, x,
-                                 pk);
-            }
-          } else {  // EPI_PLAIN
-            __nv_bfloat16* orow = static_cast<__nv_bfloat16*>(p.epi.out) + static_cast<size_t>(m) * p.epi.ldo + n_off;
-#pragma unroll
-            for (int c0 = 0; c0 < 96; c0 += 32) {
-              float v[32];
-              ptx::tmem_ld32(taddr + c0, v);
-              ptx::tmem_ld_wait();
-              uint4* dst = reinterpret_cast<uint4*>(orow + c0);
-#pragma unroll
-              for (int i = 0; i < 32; i += 8) {
-                const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n_off + c0 + i);
-                const float4 b5 = *reinterpret_cast<const float4*>(bias_s + n_off + c0 + i + 4);
-                dst[i / 8] = make_uint4(pack_bf16x2(v[i] + b4.x, v[i + 1] + b4.y), pack_bf16x2(v[i + 2] + b4.z, v[i + 3] + b4.w),
-                                        pack_bf16x2(v[i + 4] + b5.x, v[i + 5] + b5.y), pack_bf16x2(v[i + 6] + b5.z, v[i + 7] + b5.w));
-              }
-            }
-          }
+          const uint32_t taddr = tbase + h * 96;
+          ptx::tmem_ld32(taddr, v);
+          ptx::tmem_ld32(taddr + 32, v + 32);
+          ptx::tmem_ld32(taddr + 64, v + 64);
+          ptx::tmem_ld_wait();
         }
       }
       ptx::tc_fence_before();
@@ -655,7 +447,286 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         if (CG == 2) ptx::mbar_arrive_rank0(ptx::smem_u32(&bars.tmem_empty[acc]));   // the leader's MMA warp waits on it
         else ptx::mbar_arrive(ptx::smem_u32(&bars.tmem_empty[acc]));
       }
+      if (p.debug & 16) continue;   // experiment: no epilogue work at all
+      if (prof) { pc1 = clock64(); p_ld += pc1 - pc0; pc0 = pc1; }
+
+      if constexpr (EPI == EPI_EPS) {
+        // ---- 96 -> 1 output conv + CFG combine in registers
+        if (h == 0) {
+          e0 += bias_s[0];
+          e1 += bias_s[0];
+          float* eo = static_cast<float*>(p.epi.out);
+          if (p.pair) {          // sub-tile 0 = conditional image 2i, sub-tile 1 = unconditional image 2i+1
+            eo[static_cast<size_t>(mt) * 128 + row] = e1 + p.guidance * (e0 - e1);
+          } else {
+            eo[static_cast<size_t>(mt) * 256 + row] = e0;
+            eo[static_cast<size_t>(mt) * 256 + 128 + row] = e1;
+          }
+        }
+      } else if constexpr (EPI == EPI_GN_FUSED) {
+        // ---- conv + bias + GroupNorm + SiLU ------------------------------------------------------------------
+        // The G = tiles_per_img CTAs with blockIdx % G == 0..G-1 hold one image between them and run it in lock
+        // step: per-group sums of this CTA's pixels -> global, arrive on the image's counter, wait for the other
+        // G-1 CTAs, then normalise + SiLU from the registers.
+        constexpr int CPGN = N / 8;            // channels per group: 12 or 24
+        constexpr int NGL = 96 / CPGN;         // groups inside this warp's 96 columns: 8 or 4
+        const int G = p.tiles_per_img;
+        const int img = mt / G;
+        float rv[2 * NGL];                     // (sum, sum of squares) per local group
+        {
+          float gs[NGL], gq[NGL], gs1[NGL], gq1[NGL];   // even / odd column partial sums kept packed
+#pragma unroll
+          for (int g = 0; g < NGL; ++g) gs[g] = gq[g] = gs1[g] = gq1[g] = 0.f;
+#pragma unroll
+          for (int i = 0; i < 96; i += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + col0 + i);
+            float t0, t1, t2, t3;
+            add2(t0, t1, v[i], v[i + 1], b4.x, b4.y);
+            add2(t2, t3, v[i + 2], v[i + 3], b4.z, b4.w);
+            const int g0 = i / CPGN, g1 = (i + 2) / CPGN;   // pairs never straddle a group (CPGN is even)
+            add2(gs[g0], gs1[g0], gs[g0], gs1[g0], t0, t1);
+            fma2(gq[g0], gq1[g0], t0, t1, t0, t1, gq[g0], gq1[g0]);
+            add2(gs[g1], gs1[g1], gs[g1], gs1[g1], t2, t3);
+            fma2(gq[g1], gq1[g1], t2, t3, t2, t3, gq[g1], gq1[g1]);
+          }
+#pragma unroll
+          for (int g = 0; g < NGL; ++g) { rv[2 * g] = gs[g] + gs1[g]; rv[2 * g + 1] = gq[g] + gq1[g]; }
+        }
+        // lane reduction as a reduce-scatter (2*NGL values -> 1 per lane), then plain butterflies for the rest
+#pragma unroll
+        for (int half = NGL, off = 16; half >= 1; half >>= 1, off >>= 1) {
+          const bool hi = (lane & off) != 0;
+#pragma unroll
+          for (int i = 0; i < half; ++i) {
+            const float send = hi ? rv[i] : rv[i + half];
+            const float keep = hi ? rv[i + half] : rv[i];
+            rv[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+          }
+        }
+        int idx;
+        if (NGL == 8) {          // 16 values: bits 4..1 of the lane select the value, bit 0 still to be summed
+          rv[0] += __shfl_xor_sync(0xffffffffu, rv[0], 1);
+          idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+        } else {                 // 8 values: bits 4..2 select, bits 1..0 still to be summed
+          rv[0] += __shfl_xor_sync(0xffffffffu, rv[0], 2);
+          rv[0] += __shfl_xor_sync(0xffffffffu, rv[0], 1);
+          idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1) + h * 8;
+        }
+        if (NGL == 4 && lane < 16) fs->red[e][lane] = 0.f;   // the other channel half contributes nothing to these slots
+        __syncwarp();
+        if ((lane & (NGL == 8 ? 1 : 3)) == 0) fs->red[e][idx] = rv[0];
+        epi_bar_sync_all();
+        if (prof) { pc1 = clock64(); p_a += pc1 - pc0; pc0 = pc1; }
+        if (e == 0) {
+          // Exchange between the G CTAs of the image, one L2 round trip each way: every (value, flag) pair is ONE 64-bit
+          // word (the flag travels with the data, as in NCCL's LL protocol), so there is no separate counter, no fence and
+          // no second read.  The buffer is zeroed before the launch; flag 1 = valid.
+          unsigned long long* ll = reinterpret_cast<unsigned long long*>(p.epi.partials);
+          if (lane < 16) {
+            float tot = 0.f;
+#pragma unroll
+            for (int w = 0; w < EPI_WARPS; ++w) tot += fs->red[w][lane];
+            st_relaxed_gpu_u64(ll + static_cast<size_t>(mt) * 16 + lane, (1ULL << 32) | __float_as_uint(tot));
+          }
+          if (prof) { pc1 = clock64(); q_post += pc1 - pc0; }
+          // 16 values x G CTAs: lane l sums value (l & 15) over the CTAs of parity (l >> 4), fixed order
+          const unsigned long long* ip = ll + static_cast<size_t>(img) * G * 16 + (lane & 15);
+          float part = 0.f;
+          {
+            const long long t0 = clock64();
+            int polls = 0;
+            unsigned long long w[8];        // G <= 16: at most 8 words per lane, all loads in flight together
+            bool ready;
+            do {
+              ready = true;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int k = (lane >> 4) + 2 * i;
+                w[i] = k < G ? ld_relaxed_gpu_u64(ip + k * 16) : (1ULL << 32);
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) ready = ready && ((w[i] >> 32) == 1ULL);
+              if (p.debug & 1) ready = true;
+              if (!ready) {
+                ++polls;
+                if (clock64() - t0 > 4000000000LL) __trap();
+              }
+            } while (!ready);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) part += __uint_as_float(static_cast<uint32_t>(w[i]));   // zeros for k >= G
+            if (prof) { q_poll += clock64() - pc1; q_npoll += polls; }
+          }
+          part += __shfl_xor_sync(0xffffffffu, part, 16);
+          const float qsum = __shfl_down_sync(0xffffffffu, part, 1);   // lane 2g: sum, lane 2g+1: sum of squares
+          if (lane < 16 && (lane & 1) == 0) {
+            // no double-precision DIVIDE here: on this part it is a long software routine on the critical path of the
+            // whole image group (measured: ~4k cycles per tile); 1/count comes from the host
+            const double mean = static_cast<double>(part) * p.gn_inv_cnt;
+            double var = fma(-mean, mean, static_cast<double>(qsum) * p.gn_inv_cnt);
+            var = var < 0.0 ? 0.0 : var;
+            fs->mean[lane >> 1] = static_cast<float>(mean);
+            fs->rstd[lane >> 1] = rsqrtf(static_cast<float>(var) + GN_EPS);
+          }
+        }
+        epi_bar_sync_all();
+        if (prof) { pc1 = clock64(); p_b += pc1 - pc0; pc0 = pc1; }
+        for (int c = threadIdx.x - 64; c < N; c += 32 * EPI_WARPS) {
+          const int g = c / CPGN;
+          const float sc = fs->rstd[g] * fs->gamma[c];
+          fs->scale[c] = 0.5f * sc;                                                  // h = y / 2 = v * scale + shift
+          fs->shift[c] = 0.5f * ((bias_s[c] - fs->mean[g]) * sc + fs->beta[c]);
+        }
+        epi_bar_sync_all();
+        if (prof) { pc1 = clock64(); r_ss += pc1 - pc0; }
+        if (use_tma_out) {
+          if (lane == 0) ptx::bulk_wait_read<0>();   // the previous tile's stores have read the slab
+          __syncwarp();
+        }
+        __nv_bfloat16* obase = static_cast<__nv_bfloat16*>(p.epi.out);
+        const int m = (mt * MSUB + sub) * 128 + row;
+        const int rem = m - img * HW;
+        const int y = rem / p.W, x = rem - y * p.W;
+        const int wy = (y == 0) ? p.H : ((y == p.H - 1) ? -p.H : 0);
+        const int wx = (x == 0) ? p.W : ((x == p.W - 1) ? -p.W : 0);
+        const size_t pix = (static_cast<size_t>(img) * Hp + (y + 1)) * Wp + (x + 1);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int cc = col0 + k * 32;
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 s4 = *reinterpret_cast<const float4*>(fs->scale + cc + i);
+            const float4 h4 = *reinterpret_cast<const float4*>(fs->shift + cc + i);
+            float h0, h1, h2, h3, y0, y1, y2, y3;
+            fma2(h0, h1, v[k * 32 + i], v[k * 32 + i + 1], s4.x, s4.y, h4.x, h4.y);          // h = y/2
+            fma2(h2, h3, v[k * 32 + i + 2], v[k * 32 + i + 3], s4.z, s4.w, h4.z, h4.w);
+            fma2(y0, y1, h0, h1, tanh_fast(h0), tanh_fast(h1), h0, h1);    // SiLU(y) = h + h tanh(h)
+            fma2(y2, y3, h2, h3, tanh_fast(h2), tanh_fast(h3), h2, h3);
+            pk[i / 2] = pack_bf16x2(y0, y1);
+            pk[i / 2 + 1] = pack_bf16x2(y2, y3);
+          }
+          long long ps0 = prof ? clock64() : 0;
+          if (!(p.debug & 2)) stage_padded_block(use_tma_out, slab, k, lane, obase, pix, wy, wx, Wp, p.epi.ldo, cc, pk);
+          else if (pk[0] == 0x12345678u && pk[7] == 0x9abcdef0u) obase[0] = __float2bfloat16(0.f);
+          if (prof) r_store += clock64() - ps0;
+        }
+        {
+          long long ps0 = prof ? clock64() : 0;
+          if (!(p.debug & 2)) flush_padded_blocks(&mapO, use_tma_out, slab, lane, col0, img, y, x, wy);
+          if (prof) r_store += clock64() - ps0;
+        }
+        if (prof) r_math += clock64() - pc1;
+      } else if constexpr (N >= 96) {
+        const int n_off = nt * N + col0;                     // first output channel of this warp's columns
+        const int m = (mt * MSUB + sub) * 128 + row;         // global pixel index (b, y, x)
+        if constexpr (EPI == EPI_RAW_STATS) {
+          // fp32 tile -> swizzled 32x32 slab in shared memory -> TMA store (full 128 B lines, no LSU), plus
+          // per-(warp, group) partial sums for a separate GroupNorm pass (the unfused A/B path)
+          constexpr int CPGN = N / 8;
+          constexpr int NG = 96 / CPGN;
+          float gs[NG], gq[NG];
+#pragma unroll
+          for (int g = 0; g < NG; ++g) gs[g] = gq[g] = 0.f;
+          const int m_base = (mt * MSUB + sub) * 128 + q * 32;
+#pragma unroll
+          for (int c0 = 0; c0 < 96; c0 += 32) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n_off + c0 + i);
+              v[c0 + i] += b4.x; v[c0 + i + 1] += b4.y; v[c0 + i + 2] += b4.z; v[c0 + i + 3] += b4.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              gs[(c0 + i) / CPGN] += v[c0 + i];
+              gq[(c0 + i) / CPGN] += v[c0 + i] * v[c0 + i];
+            }
+            if (lane == 0) ptx::bulk_wait_read<0>();   // the previous store has finished reading the slab
+            __syncwarp();
+            const uint32_t dst = slab + lane * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              ptx::st_shared_v4(dst + ((j ^ (lane & 7)) << 4), v[c0 + 4 * j], v[c0 + 4 * j + 1], v[c0 + 4 * j + 2], v[c0 + 4 * j + 3]);
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              ptx::tma_store_2d(&mapO, slab, n_off + c0, m_base);
+              ptx::bulk_commit();
+            }
+          }
+#pragma unroll
+          for (int g = 0; g < NG; ++g) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              gs[g] += __shfl_xor_sync(0xffffffffu, gs[g], o);
+              gq[g] += __shfl_xor_sync(0xffffffffu, gq[g], o);
+            }
+          }
+          if (lane == 0) {
+            // slot layout [image][tile-in-image*MSUB + sub][quarter]; with MSUB == 1 the two column halves
+            // write disjoint groups of the same slot
+            const int b = m / HW;
+            const int slot = ((mt * MSUB + sub) % (p.tiles_per_img * MSUB)) * 4 + q;
+            float* dst = p.epi.partials + (static_cast<size_t>(b) * p.epi.slots + slot) * 16 + 2 * (col0 / CPGN);
+#pragma unroll
+            for (int g = 0; g < NG; ++g) { dst[2 * g] = gs[g]; dst[2 * g + 1] = gq[g]; }
+          }
+        } else if constexpr (EPI == EPI_PADDED) {
+          const int b = m / HW, rem = m - b * HW;
+          const int y = rem / p.W, x = rem - y * p.W;
+          const int wy = (y == 0) ? p.H : ((y == p.H - 1) ? -p.H : 0);
+          const int wx = (x == 0) ? p.W : ((x == p.W - 1) ? -p.W : 0);
+          __nv_bfloat16* obase = static_cast<__nv_bfloat16*>(p.epi.out);
+          const size_t pix = (static_cast<size_t>(b) * Hp + (y + 1)) * Wp + (x + 1);
+          const __nv_bfloat16* rrow =
+              p.epi.residual ? static_cast<const __nv_bfloat16*>(p.epi.residual) + pix * p.ntot + n_off : nullptr;
+          if (use_tma_out) {
+            if (lane == 0) ptx::bulk_wait_read<0>();   // the previous tile's stores have read the slab
+            __syncwarp();
+          }
+#pragma unroll
+          for (int c0 = 0; c0 < 96; c0 += 32) {
+            if (rrow) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint4 rr = *reinterpret_cast<const uint4*>(rrow + c0 + i * 8);
+                const uint32_t w4[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float2 rf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[k]));
+                  v[c0 + i * 8 + 2 * k] += rf.x;
+                  v[c0 + i * 8 + 2 * k + 1] += rf.y;
+                }
+              }
+            }
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n_off + c0 + i);
+              pk[i / 2] = pack_bf16x2(v[c0 + i] + b4.x, v[c0 + i + 1] + b4.y);
+              pk[i / 2 + 1] = pack_bf16x2(v[c0 + i + 2] + b4.z, v[c0 + i + 3] + b4.w);
+            }
+            stage_padded_block(use_tma_out, slab, c0 / 32, lane, obase, pix, wy, wx, Wp, p.epi.ldo, n_off + c0, pk);
+          }
+          flush_padded_blocks(&mapO, use_tma_out, slab, lane, n_off, b, y, x, wy);
+        } else {  // EPI_PLAIN
+          __nv_bfloat16* orow = static_cast<__nv_bfloat16*>(p.epi.out) + static_cast<size_t>(m) * p.epi.ldo + n_off;
+#pragma unroll
+          for (int c0 = 0; c0 < 96; c0 += 32) {
+            uint4* dst = reinterpret_cast<uint4*>(orow + c0);
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n_off + c0 + i);
+              const float4 b5 = *reinterpret_cast<const float4*>(bias_s + n_off + c0 + i + 4);
+              dst[i / 8] = make_uint4(pack_bf16x2(v[c0 + i] + b4.x, v[c0 + i + 1] + b4.y), pack_bf16x2(v[c0 + i + 2] + b4.z, v[c0 + i + 3] + b4.w),
+                                      pack_bf16x2(v[c0 + i + 4] + b5.x, v[c0 + i + 5] + b5.y), pack_bf16x2(v[c0 + i + 6] + b5.z, v[c0 + i + 7] + b5.w));
+            }
+          }
+        }
+      }
     }
+    if (prof && lane == 0 && it > 1)
+      printf("[epi N=%d EPI=%d] per tile: wait tmem_full %lld  tmem ld %lld  stats+barA %lld  exchange+barB %lld (post %lld, poll %lld, polls %lld)  rest(pass2+stores) %lld (scale/shift+barC %lld, pass2 %lld of which stores %lld)\n",
+             N, EPI, pw_full / it, p_ld / it, p_a / it, p_b / it, q_post / it, q_poll / it, q_npoll / it, p_c / (it - 1), r_ss / it, r_math / it, r_store / it);
     if (lane == 0) ptx::bulk_wait_all();   // staged TMA stores have left shared memory
   }
 
@@ -779,8 +850,8 @@ static int launch_t(const ConvTcPlan& pl, cudaStream_t st) {
     TCS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
     attr_done = true;
   }
-  if (EPI == EPI_GN_FUSED)   // the CTAs of an image group wait on one another: zero the arrival counters
-    TCS_CUDA(cudaMemsetAsync(pl.p.epi.counters, 0, sizeof(int) * (pl.p.n_mtiles / pl.p.tiles_per_img), st));
+  if (EPI == EPI_GN_FUSED)   // the CTAs of an image group exchange (value, flag) words: flag 0 = not written yet
+    TCS_CUDA(cudaMemsetAsync(pl.p.epi.partials, 0, sizeof(unsigned long long) * 16 * pl.p.n_mtiles, st));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(pl.grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = pl.smem; cfg.stream = st;
   cudaLaunchAttribute at[2];
@@ -843,6 +914,7 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, con
   }
   if (g.H % (pl.msub * (128 / g.W))) return fail(TCS_ERR_UNSUPPORTED, "conv_tc: image height not a multiple of the tile");
   p.debug = getenv("TCS_DEBUG") ? atoi(getenv("TCS_DEBUG")) : 0;
+  p.gn_inv_cnt = 1.0 / (static_cast<double>(g.H) * g.W * (pl.N / 8));
   {
     const char* e = getenv("TCS_ISSUERS");   // 1 = a single MMA-issuing thread everywhere (A/B switch)
     p.issuers = (pl.msub == 2 && !(e && atoi(e) == 1)) ? 2 : 1;

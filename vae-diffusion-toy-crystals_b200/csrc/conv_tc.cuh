@@ -20,6 +20,7 @@ struct ConvTcParams {
   uint32_t a_bytes, stage_bytes;
   int pair;                 // EPI_EPS: 1 = the two sub-tiles are the same pixels of images 2i (cond) and 2i+1 (uncond)
   float guidance;           // EPI_EPS with pair: eps = e_u + guidance (e_c - e_u)
+  double gn_inv_cnt;        // EPI_GN_FUSED: 1 / (H * W * channels per group)
   int issuers;              // MMA-issuing warps: 2 = one per 128-row sub-tile (MSUB == 2), 1 otherwise
   int debug;                // TCS_DEBUG bits (timing experiments only): 1 = no inter-CTA wait, 2 = no pass-2 stores
   EpiArgs epi;
