@@ -28,10 +28,13 @@
 namespace tcs {
 
 
-constexpr int EPI_WARPS = 8;
-constexpr int TC_THREADS = 64 + 32 * EPI_WARPS + 32;   // + a second MMA-issuing warp (warp 10) for the MSUB = 2 tiles
+constexpr int EPI_WARPS = 16;
+constexpr int UC = 768 / EPI_WARPS;    // accumulator columns per epilogue warp (4 lane quarters x EPI_WARPS/4 column units cover 192)
+constexpr int BLK = UC / 3;            // channels per staged output block (three blocks per warp and tile)
+constexpr int TC_THREADS = 64 + 32 * EPI_WARPS + 32;   // + a second MMA-issuing warp for the MSUB = 2 tiles
 constexpr int MAX_STAGES = 8;
-constexpr uint32_t EPI_SLAB_BYTES = EPI_WARPS * 6144;   // per epilogue warp: three 32 px x 32 ch bf16 blocks (or one 32x32 fp32 slab)
+constexpr uint32_t EPI_WARP_SLAB = 3 * 32 * BLK * 2;    // per epilogue warp: three 32 px x BLK ch bf16 blocks
+constexpr uint32_t EPI_SLAB_BYTES = EPI_WARPS * EPI_WARP_SLAB;
 constexpr uint32_t EPI_BIAS_BYTES = 576 * 4;
 struct EpiFusedSmem {          // EPI_GN_FUSED scratch (lives right after the bias)
   float gamma[192], beta[192];
@@ -96,31 +99,32 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
-// Staged variant used by the 8-warp epilogue: a warp writes its THREE 32-pixel x 32-channel blocks of a tile into its
-// 6 KB slab (stage_padded_block), then pays the generic->async proxy fence once and issues all TMA stores
-// (flush_padded_blocks).  One fence per block made the stores ~800 cycles each (measured).
+// A warp writes its THREE 32-pixel x BLK-channel blocks of a tile into its slab (stage_padded_block), then pays the
+// generic->async proxy fence once and issues all TMA stores (flush_padded_blocks); only the lanes on the left/right
+// image border write their column-halo copy themselves.  W == 16: plain per-lane stores (the 16x16 layers are small).
+// Slab rows are BLK*2 bytes, swizzled like the tensor map (SWIZZLE_64B for BLK = 32, SWIZZLE_32B for BLK = 16).
 __device__ __forceinline__ void stage_padded_block(bool use_tma, uint32_t slab, int k, int lane, __nv_bfloat16* obase,
                                                    size_t pix, int wy, int wx, int Wp, int ldo, int ch, const uint32_t* pk) {
   if (!use_tma) {
     store_with_halo(obase, pix, wy, wx, Wp, ldo, ch, pk);
     return;
   }
-  const uint32_t dst = slab + k * 2048 + lane * 64;
-  const int sw = (lane >> 1) & 3;
+  const uint32_t dst = slab + k * (32 * BLK * 2) + lane * (BLK * 2);
+  const int sw = BLK == 32 ? ((lane >> 1) & 3) : ((lane >> 2) & 1);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) st_shared_u4(dst + ((j ^ sw) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+  for (int j = 0; j < BLK / 8; ++j) st_shared_u4(dst + ((j ^ sw) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
   if (wx) {   // column halo (and the corner when this pixel is also on a border row)
     uint4* d0 = reinterpret_cast<uint4*>(obase + (pix + wx) * ldo + ch);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) d0[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+    for (int i = 0; i < BLK / 8; ++i) d0[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
     if (wy) {
       uint4* d1 = reinterpret_cast<uint4*>(obase + (pix + static_cast<long long>(wy) * Wp + wx) * ldo + ch);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) d1[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+      for (int i = 0; i < BLK / 8; ++i) d1[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
     }
   }
 }
-// ch0: channel of block 0 (blocks are 32 channels apart); lane 0 holds the first pixel (y, x) of the 32-pixel run
+// ch0: channel of block 0 (blocks are BLK channels apart); lane 0 holds the first pixel (y, x) of the 32-pixel run
 __device__ __forceinline__ void flush_padded_blocks(const CUtensorMap* mapO, bool use_tma, uint32_t slab, int lane, int ch0,
                                                     int img, int y, int x, int wy) {
   if (!use_tma) return;
@@ -129,51 +133,13 @@ __device__ __forceinline__ void flush_padded_blocks(const CUtensorMap* mapO, boo
   if (lane == 0) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      tma_store_4d(mapO, slab + k * 2048, ch0 + k * 32, x + 1, y + 1, img);
-      if (wy) tma_store_4d(mapO, slab + k * 2048, ch0 + k * 32, x + 1, y + 1 + wy, img);
+      tma_store_4d(mapO, slab + k * (32 * BLK * 2), ch0 + k * BLK, x + 1, y + 1, img);
+      if (wy) tma_store_4d(mapO, slab + k * (32 * BLK * 2), ch0 + k * BLK, x + 1, y + 1 + wy, img);
     }
     ptx::bulk_commit();
   }
 }
-// 32 pixels (one per lane, consecutive in an image row) x 32 bf16 channels -> padded NHWC output.
-// W >= 32: the warp stages the 2 KB block in a SWIZZLE_64B slab and one lane TMA-stores it (plus the wrapped
-// row copy); only the lanes on the left/right image border write their column-halo copy themselves.
-// W == 16: plain per-lane 16-byte stores (the 16x16 layers are small).
-__device__ __forceinline__ void store_padded_block(const CUtensorMap* mapO, bool use_tma, uint32_t slab, uint32_t& slab_buf,
-                                                   int lane, __nv_bfloat16* obase, size_t pix, int wy, int wx, int Wp,
-                                                   int ldo, int ch, int img, int y, int x, const uint32_t* pk) {
-  if (!use_tma) {
-    store_with_halo(obase, pix, wy, wx, Wp, ldo, ch, pk);
-    return;
-  }
-  if (lane == 0) ptx::bulk_wait_read<1>();   // the slab half written two blocks ago has been read
-  __syncwarp();
-  const uint32_t base = slab + slab_buf * 2048;
-  const uint32_t dst = base + lane * 64;
-  const int sw = (lane >> 1) & 3;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) st_shared_u4(dst + ((j ^ sw) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-  ptx::fence_proxy_async();
-  __syncwarp();
-  if (lane == 0) {   // lane 0 holds the first pixel of the block: (y, x) -> padded (y+1, x+1)
-    tma_store_4d(mapO, base, ch, x + 1, y + 1, img);
-    if (wy) tma_store_4d(mapO, base, ch, x + 1, y + 1 + wy, img);
-    ptx::bulk_commit();
-  }
-  slab_buf ^= 1;
-  if (wx) {   // column halo (and the corner when this pixel is also on a border row)
-    uint4* d0 = reinterpret_cast<uint4*>(obase + (pix + wx) * ldo + ch);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) d0[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-    if (wy) {
-      uint4* d1 = reinterpret_cast<uint4*>(obase + (pix + static_cast<long long>(wy) * Wp + wx) * ldo + ch);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) d1[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-    }
-  }
-}
-
-// 32 bf16 channels of one pixel -> padded NHWC tensor, duplicated onto the circular halo where needed
+// BLK bf16 channels of one pixel -> padded NHWC tensor, duplicated onto the circular halo where needed
 __device__ __forceinline__ void store_with_halo(__nv_bfloat16* obase, size_t pix, int wy, int wx, int Wp, int ldo,
                                                 int ch, const uint32_t* pk) {
 #pragma unroll
@@ -185,7 +151,7 @@ __device__ __forceinline__ void store_with_halo(__nv_bfloat16* obase, size_t pix
       const size_t dp = pix + static_cast<long long>(cy ? wy : 0) * Wp + (cx ? wx : 0);
       uint4* dst = reinterpret_cast<uint4*>(obase + dp * ldo + ch);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+      for (int i = 0; i < BLK / 8; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
     }
   }
 }
@@ -391,24 +357,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       run(I0{}, IM{});
     }
   } else if (warp >= 2 && warp < 2 + EPI_WARPS) {
-    // ============================== epilogue (8 warps, every tile) ================
-    // Measured (TCS_DEBUG 16/32): reading accumulators out of TMEM stalls the tensor pipe (about 32 B/clk per SM), so an
-    // epilogue that reads them twice (GroupNorm statistics, then normalise) cost ~40 % of a K = 864 layer.  Now every
-    // accumulator element is read exactly ONCE: warp (q, h) = (TMEM lane quarter, unit) pulls its 32 rows x 96 columns
-    // into registers with three back-to-back tcgen05.ld, releases the accumulator set at once (the MMA warp can start
-    // tile i+2 while this tile's GroupNorm exchange is still in flight) and does everything else from registers.
-    // unit h: MSUB == 2 -> 128-row sub-tile h (all N = 96 channels); MSUB == 1 -> channel half h of the N = 192 tile.
-    const int e = warp - 2, q = warp & 3, h = e >> 2;
+    // ============================== epilogue (EPI_WARPS warps, every tile) ================
+    // Measured (TCS_DEBUG 16/32/128): TMEM reads stall the tensor pipe and the epilogue is a chain of latencies (TMEM
+    // load, the GroupNorm exchange between the CTAs of an image, MUFU, TMA stores), not of instruction issue.  So every
+    // accumulator element is read exactly ONCE into registers, the accumulator set is released at once (the MMA warps run
+    // up to two tiles ahead) and the tile is spread over 16 warps: warp (q, u) = (TMEM lane quarter, column unit) owns
+    // 32 rows x UC = 48 of the 192 accumulator columns.
+    //   MSUB == 2 (N = 96): unit u -> 128-row sub-tile u / 2, channels (u % 2) * 48 ...;  MSUB == 1 (N = 192): channels u * 48 ...
+    const int e = warp - 2, q = warp & 3, u = e >> 2;
     const int row = q * 32 + lane;
     const int HW = p.H * p.W;
     const int Wp = p.W + 2, Hp = p.H + 2;
-    uint32_t slab_buf = 0;
-    (void)slab_buf; (void)Hp; (void)Wp; (void)HW;
-    const uint32_t slab = slab_base + static_cast<uint32_t>(e) * 6144;      // this warp's 3 x 2 KB staging blocks
+    (void)Hp; (void)Wp; (void)HW;
+    const uint32_t slab = slab_base + static_cast<uint32_t>(e) * EPI_WARP_SLAB;      // this warp's 3 staging blocks
     const bool use_tma_out = p.W >= 32 && !(p.debug & 4);
-    (void)use_tma_out;
-    const int sub = (MSUB == 2) ? h : 0;
-    const int col0 = (MSUB == 2) ? 0 : h * 96;          // first channel (inside the N tile) of this warp's columns
+    (void)use_tma_out; (void)slab;
+    constexpr int UPS = (96 / UC);                       // column units per 96 channels
+    const int sub = (MSUB == 2) ? u / UPS : 0;
+    const int col0 = (MSUB == 2) ? (u % UPS) * UC : u * UC;   // first channel (inside the N tile) of this warp's columns
     uint32_t it = 0;
     const bool prof = (p.debug & 128) && blockIdx.x == 0 && e == 0;
     long long pw_full = 0, p_ld = 0, p_a = 0, p_b = 0, p_c = 0, pc0 = 0, pc1 = 0, q_post = 0, q_poll = 0, q_npoll = 0, r_ss = 0, r_math = 0, r_store = 0;
@@ -423,21 +389,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       if (prof) { pc1 = clock64(); pw_full += pc1 - pc0; pc0 = pc1; }
 
       // ---- the only TMEM traffic of the tile ------------------------------------------------------------------
-      float v[96];
+      float v[UC];
       float e0 = 0.f, e1 = 0.f;
       (void)e0; (void)e1;
       if (!(p.debug & 16)) {
         if constexpr (EPI == EPI_EPS) {
-          if (h == 0) {       // column 0 of each sub-tile's accumulator is eps
+          if (u == 0) {       // column 0 of each sub-tile's accumulator is eps
             ptx::tmem_ld1(tbase, &e0);
             ptx::tmem_ld1(tbase + N, &e1);
             ptx::tmem_ld_wait();
           }
         } else {
-          const uint32_t taddr = tbase + h * 96;
+          const uint32_t taddr = tbase + u * UC;
           ptx::tmem_ld32(taddr, v);
-          ptx::tmem_ld32(taddr + 32, v + 32);
-          ptx::tmem_ld32(taddr + 64, v + 64);
+          if (UC == 96) { ptx::tmem_ld32(taddr + 32, v + 32); ptx::tmem_ld32(taddr + 64, v + 64); }
+          else ptx::tmem_ld16(taddr + 32, v + 32);
           ptx::tmem_ld_wait();
         }
       }
@@ -452,7 +418,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 
       if constexpr (EPI == EPI_EPS) {
         // ---- 96 -> 1 output conv + CFG combine in registers
-        if (h == 0) {
+        if (u == 0) {
           e0 += bias_s[0];
           e1 += bias_s[0];
           float* eo = static_cast<float*>(p.epi.out);
@@ -466,10 +432,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       } else if constexpr (EPI == EPI_GN_FUSED) {
         // ---- conv + bias + GroupNorm + SiLU ------------------------------------------------------------------
         // The G = tiles_per_img CTAs with blockIdx % G == 0..G-1 hold one image between them and run it in lock
-        // step: per-group sums of this CTA's pixels -> global, arrive on the image's counter, wait for the other
-        // G-1 CTAs, then normalise + SiLU from the registers.
+        // step: per-group sums of this CTA's pixels -> global, wait for the other G-1 CTAs, then normalise + SiLU
+        // from the registers.
         constexpr int CPGN = N / 8;            // channels per group: 12 or 24
-        constexpr int NGL = 96 / CPGN;         // groups inside this warp's 96 columns: 8 or 4
+        constexpr int NGL = UC / CPGN;         // groups inside this warp's columns: 4 or 2 (8 or 4 with UC = 96)
+        static_assert(UC % CPGN == 0, "a warp's columns must hold whole GroupNorm groups");
         const int G = p.tiles_per_img;
         const int img = mt / G;
         float rv[2 * NGL];                     // (sum, sum of squares) per local group
@@ -478,7 +445,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 #pragma unroll
           for (int g = 0; g < NGL; ++g) gs[g] = gq[g] = gs1[g] = gq1[g] = 0.f;
 #pragma unroll
-          for (int i = 0; i < 96; i += 4) {
+          for (int i = 0; i < UC; i += 4) {
             const float4 b4 = *reinterpret_cast<const float4*>(bias_s + col0 + i);
             float t0, t1, t2, t3;
             add2(t0, t1, v[i], v[i + 1], b4.x, b4.y);
@@ -492,9 +459,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 #pragma unroll
           for (int g = 0; g < NGL; ++g) { rv[2 * g] = gs[g] + gs1[g]; rv[2 * g + 1] = gq[g] + gq1[g]; }
         }
-        // lane reduction as a reduce-scatter (2*NGL values -> 1 per lane), then plain butterflies for the rest
+        // lane reduction: a reduce-scatter over the top lane bits (2*NGL values -> 1 per lane), butterflies for the rest
+        constexpr int NV = 2 * NGL;            // 4, 8 or 16
+        constexpr int SC_STEPS = NV == 16 ? 4 : (NV == 8 ? 3 : 2);
+        int idx = 0;
 #pragma unroll
-        for (int half = NGL, off = 16; half >= 1; half >>= 1, off >>= 1) {
+        for (int st = 0; st < SC_STEPS; ++st) {
+          const int half = NV >> (st + 1), off = 16 >> st;
           const bool hi = (lane & off) != 0;
 #pragma unroll
           for (int i = 0; i < half; ++i) {
@@ -502,19 +473,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const float keep = hi ? rv[i + half] : rv[i];
             rv[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
           }
+          idx |= hi ? half : 0;
         }
-        int idx;
-        if (NGL == 8) {          // 16 values: bits 4..1 of the lane select the value, bit 0 still to be summed
-          rv[0] += __shfl_xor_sync(0xffffffffu, rv[0], 1);
-          idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-        } else {                 // 8 values: bits 4..2 select, bits 1..0 still to be summed
-          rv[0] += __shfl_xor_sync(0xffffffffu, rv[0], 2);
-          rv[0] += __shfl_xor_sync(0xffffffffu, rv[0], 1);
-          idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1) + h * 8;
-        }
-        if (NGL == 4 && lane < 16) fs->red[e][lane] = 0.f;   // the other channel half contributes nothing to these slots
+#pragma unroll
+        for (int off = 16 >> SC_STEPS; off >= 1; off >>= 1) rv[0] += __shfl_xor_sync(0xffffffffu, rv[0], off);
+        if (lane < 16) fs->red[e][lane] = 0.f;   // the slots of the groups this warp does not cover
         __syncwarp();
-        if ((lane & (NGL == 8 ? 1 : 3)) == 0) fs->red[e][idx] = rv[0];
+        if ((lane & ((32 >> SC_STEPS) - 1)) == 0) fs->red[e][2 * (col0 / CPGN) + idx] = rv[0];
         epi_bar_sync_all();
         if (prof) { pc1 = clock64(); p_a += pc1 - pc0; pc0 = pc1; }
         if (e == 0) {
@@ -591,15 +556,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const size_t pix = (static_cast<size_t>(img) * Hp + (y + 1)) * Wp + (x + 1);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-          const int cc = col0 + k * 32;
-          uint32_t pk[16];
+          const int cc = col0 + k * BLK;
+          uint32_t pk[BLK / 2];
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
+          for (int i = 0; i < BLK; i += 4) {
             const float4 s4 = *reinterpret_cast<const float4*>(fs->scale + cc + i);
             const float4 h4 = *reinterpret_cast<const float4*>(fs->shift + cc + i);
             float h0, h1, h2, h3, y0, y1, y2, y3;
-            fma2(h0, h1, v[k * 32 + i], v[k * 32 + i + 1], s4.x, s4.y, h4.x, h4.y);          // h = y/2
-            fma2(h2, h3, v[k * 32 + i + 2], v[k * 32 + i + 3], s4.z, s4.w, h4.z, h4.w);
+            fma2(h0, h1, v[k * BLK + i], v[k * BLK + i + 1], s4.x, s4.y, h4.x, h4.y);          // h = y/2
+            fma2(h2, h3, v[k * BLK + i + 2], v[k * BLK + i + 3], s4.z, s4.w, h4.z, h4.w);
             fma2(y0, y1, h0, h1, tanh_fast(h0), tanh_fast(h1), h0, h1);    // SiLU(y) = h + h tanh(h)
             fma2(y2, y3, h2, h3, tanh_fast(h2), tanh_fast(h3), h2, h3);
             pk[i / 2] = pack_bf16x2(y0, y1);
@@ -607,7 +572,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           }
           long long ps0 = prof ? clock64() : 0;
           if (!(p.debug & 2)) stage_padded_block(use_tma_out, slab, k, lane, obase, pix, wy, wx, Wp, p.epi.ldo, cc, pk);
-          else if (pk[0] == 0x12345678u && pk[7] == 0x9abcdef0u) obase[0] = __float2bfloat16(0.f);
+          else if (pk[0] == 0x12345678u && pk[BLK / 2 - 1] == 0x9abcdef0u) obase[0] = __float2bfloat16(0.f);
           if (prof) r_store += clock64() - ps0;
         }
         {
@@ -620,38 +585,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int n_off = nt * N + col0;                     // first output channel of this warp's columns
         const int m = (mt * MSUB + sub) * 128 + row;         // global pixel index (b, y, x)
         if constexpr (EPI == EPI_RAW_STATS) {
-          // fp32 tile -> swizzled 32x32 slab in shared memory -> TMA store (full 128 B lines, no LSU), plus
-          // per-(warp, group) partial sums for a separate GroupNorm pass (the unfused A/B path)
+          // fp32 output (one row per lane, plain stores) plus per-(warp, group) partial sums for a separate GroupNorm
+          // pass: the unfused A/B path (TCS_FUSE_GN=0) and the per-layer tests; not on the production path
           constexpr int CPGN = N / 8;
-          constexpr int NG = 96 / CPGN;
+          constexpr int NG = UC / CPGN;
           float gs[NG], gq[NG];
 #pragma unroll
           for (int g = 0; g < NG; ++g) gs[g] = gq[g] = 0.f;
-          const int m_base = (mt * MSUB + sub) * 128 + q * 32;
+          float* orow = static_cast<float*>(p.epi.out) + static_cast<size_t>(m) * p.epi.ldo + n_off;
 #pragma unroll
-          for (int c0 = 0; c0 < 96; c0 += 32) {
+          for (int i = 0; i < UC; i += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n_off + i);
+            v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+            *reinterpret_cast<float4*>(orow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          }
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n_off + c0 + i);
-              v[c0 + i] += b4.x; v[c0 + i + 1] += b4.y; v[c0 + i + 2] += b4.z; v[c0 + i + 3] += b4.w;
-            }
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              gs[(c0 + i) / CPGN] += v[c0 + i];
-              gq[(c0 + i) / CPGN] += v[c0 + i] * v[c0 + i];
-            }
-            if (lane == 0) ptx::bulk_wait_read<0>();   // the previous store has finished reading the slab
-            __syncwarp();
-            const uint32_t dst = slab + lane * 128;
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              ptx::st_shared_v4(dst + ((j ^ (lane & 7)) << 4), v[c0 + 4 * j], v[c0 + 4 * j + 1], v[c0 + 4 * j + 2], v[c0 + 4 * j + 3]);
-            ptx::fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-              ptx::tma_store_2d(&mapO, slab, n_off + c0, m_base);
-              ptx::bulk_commit();
-            }
+          for (int i = 0; i < UC; ++i) {
+            gs[i / CPGN] += v[i];
+            gq[i / CPGN] += v[i] * v[i];
           }
 #pragma unroll
           for (int g = 0; g < NG; ++g) {
@@ -662,8 +613,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             }
           }
           if (lane == 0) {
-            // slot layout [image][tile-in-image*MSUB + sub][quarter]; with MSUB == 1 the two column halves
-            // write disjoint groups of the same slot
+            // slot layout [image][tile-in-image*MSUB + sub][quarter]; the column units of a row block write disjoint
+            // groups of the same slot
             const int b = m / HW;
             const int slot = ((mt * MSUB + sub) % (p.tiles_per_img * MSUB)) * 4 + q;
             float* dst = p.epi.partials + (static_cast<size_t>(b) * p.epi.slots + slot) * 16 + 2 * (col0 / CPGN);
@@ -684,42 +635,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             __syncwarp();
           }
 #pragma unroll
-          for (int c0 = 0; c0 < 96; c0 += 32) {
+          for (int k = 0; k < 3; ++k) {
+            const int c0 = k * BLK;
             if (rrow) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
+              for (int i = 0; i < BLK / 8; ++i) {
                 const uint4 rr = *reinterpret_cast<const uint4*>(rrow + c0 + i * 8);
                 const uint32_t w4[4] = {rr.x, rr.y, rr.z, rr.w};
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const float2 rf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[k]));
-                  v[c0 + i * 8 + 2 * k] += rf.x;
-                  v[c0 + i * 8 + 2 * k + 1] += rf.y;
+                for (int kk = 0; kk < 4; ++kk) {
+                  const float2 rf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[kk]));
+                  v[c0 + i * 8 + 2 * kk] += rf.x;
+                  v[c0 + i * 8 + 2 * kk + 1] += rf.y;
                 }
               }
             }
-            uint32_t pk[16];
+            uint32_t pk[BLK / 2];
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
+            for (int i = 0; i < BLK; i += 4) {
               const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n_off + c0 + i);
               pk[i / 2] = pack_bf16x2(v[c0 + i] + b4.x, v[c0 + i + 1] + b4.y);
               pk[i / 2 + 1] = pack_bf16x2(v[c0 + i + 2] + b4.z, v[c0 + i + 3] + b4.w);
             }
-            stage_padded_block(use_tma_out, slab, c0 / 32, lane, obase, pix, wy, wx, Wp, p.epi.ldo, n_off + c0, pk);
+            stage_padded_block(use_tma_out, slab, k, lane, obase, pix, wy, wx, Wp, p.epi.ldo, n_off + c0, pk);
           }
           flush_padded_blocks(&mapO, use_tma_out, slab, lane, n_off, b, y, x, wy);
         } else {  // EPI_PLAIN
           __nv_bfloat16* orow = static_cast<__nv_bfloat16*>(p.epi.out) + static_cast<size_t>(m) * p.epi.ldo + n_off;
 #pragma unroll
-          for (int c0 = 0; c0 < 96; c0 += 32) {
-            uint4* dst = reinterpret_cast<uint4*>(orow + c0);
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n_off + c0 + i);
-              const float4 b5 = *reinterpret_cast<const float4*>(bias_s + n_off + c0 + i + 4);
-              dst[i / 8] = make_uint4(pack_bf16x2(v[c0 + i] + b4.x, v[c0 + i + 1] + b4.y), pack_bf16x2(v[c0 + i + 2] + b4.z, v[c0 + i + 3] + b4.w),
-                                      pack_bf16x2(v[c0 + i + 4] + b5.x, v[c0 + i + 5] + b5.y), pack_bf16x2(v[c0 + i + 6] + b5.z, v[c0 + i + 7] + b5.w));
-            }
+          for (int i = 0; i < UC; i += 8) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n_off + i);
+            const float4 b5 = *reinterpret_cast<const float4*>(bias_s + n_off + i + 4);
+            *reinterpret_cast<uint4*>(orow + i) =
+                make_uint4(pack_bf16x2(v[i] + b4.x, v[i + 1] + b4.y), pack_bf16x2(v[i + 2] + b4.z, v[i + 3] + b4.w),
+                           pack_bf16x2(v[i + 4] + b5.x, v[i + 5] + b5.y), pack_bf16x2(v[i + 6] + b5.z, v[i + 7] + b5.w));
           }
         }
       }
@@ -976,24 +925,14 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, con
     if (r != CUDA_SUCCESS) return fail(TCS_ERR_CUDA, "cuTensorMapEncodeTiled(W) failed: " + std::to_string(r));
   }
   pl.mapO = pl.mapW;
-  if (epi == EPI_RAW_STATS) {   // fp32 [M, ldo] output written by TMA store in 32x32 boxes
-    cuuint64_t dims[2] = {static_cast<cuuint64_t>(ea.ldo), static_cast<cuuint64_t>(g.B) * g.H * g.W};
-    cuuint64_t strides[1] = {static_cast<cuuint64_t>(ea.ldo) * 4};
-    cuuint32_t box[2] = {32, 32};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(&pl.mapO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ea.out, dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(TCS_ERR_CUDA, "cuTensorMapEncodeTiled(O) failed: " + std::to_string(r));
-  }
   if ((epi == EPI_GN_FUSED || epi == EPI_PADDED) && g.W >= 32) {   // bf16 padded output, 32-pixel x 32-channel boxes
     const cuuint64_t C = static_cast<cuuint64_t>(ea.ldo);
     cuuint64_t dims[4] = {C, static_cast<cuuint64_t>(g.W + 2), static_cast<cuuint64_t>(g.H + 2), static_cast<cuuint64_t>(g.B)};
     cuuint64_t strides[3] = {C * 2, C * 2 * (g.W + 2), C * 2 * (g.W + 2) * (g.H + 2)};
-    cuuint32_t box[4] = {32, 32, 1, 1};
+    cuuint32_t box[4] = {BLK, 32, 1, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = encode(&pl.mapO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ea.out, dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, BLK == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(TCS_ERR_CUDA, "cuTensorMapEncodeTiled(O padded) failed: " + std::to_string(r));
   }

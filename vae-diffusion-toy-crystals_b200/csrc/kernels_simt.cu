@@ -236,28 +236,43 @@ __global__ void __launch_bounds__(384, 2) first_conv_gn_kernel(const float* __re
   }
   constexpr int PO = IMG + 2;
   const int p_begin = band * (IMG_PIX / FC_SPLIT), p_end = p_begin + IMG_PIX / FC_SPLIT;
-  for (int p = p_begin + pg; p < p_end; p += 8) {
+  // runs of 4 horizontally adjacent pixels: 18 shared-memory loads feed 72 FMAs (the one-pixel version was LDS-bound)
+  (void)p_end;
+  for (int qd = pg; qd < IMG_PIX / FC_SPLIT / 4; qd += 8) {
+    const int p = p_begin + qd * 4;
     const int yy = p >> 6, xx = p & 63;
-    float c0 = 0.f, c1 = 0.f;
+    float xv[3][6];
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const float xv = xs[yy + 1 + ky][xx + 1 + kx];
-        c0 = fmaf(w0[ky * 3 + kx], xv, c0);
-        c1 = fmaf(w1[ky * 3 + kx], xv, c1);
-      }
-    const int wy = halo_wrap(yy, IMG), wx = halo_wrap(xx, IMG);
+      for (int k = 0; k < 6; ++k) xv[ky][k] = xs[yy + 1 + ky][xx + 1 + k];
+    float c[4][2];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (u >= dup) break;
-      const float y0 = silu_f<FAST>(fmaf(c0, sc0[u], sh0[u]));
-      const float y1 = silu_f<FAST>(fmaf(c1, sc1[u], sh1[u]));
-      const size_t base = ((static_cast<size_t>(i) * dup + u) * PO + yy + 1) * PO + xx + 1;
-      store_pair<T>(out + base * 96 + oc, y0, y1);
-      if (wy) store_pair<T>(out + (base + static_cast<long long>(wy) * PO) * 96 + oc, y0, y1);
-      if (wx) store_pair<T>(out + (base + wx) * 96 + oc, y0, y1);
-      if (wy && wx) store_pair<T>(out + (base + static_cast<long long>(wy) * PO + wx) * 96 + oc, y0, y1);
+    for (int j = 0; j < 4; ++j) c[j][0] = c[j][1] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          c[j][0] = fmaf(w0[ky * 3 + kx], xv[ky][j + kx], c[j][0]);
+          c[j][1] = fmaf(w1[ky * 3 + kx], xv[ky][j + kx], c[j][1]);
+        }
+    const int wy = halo_wrap(yy, IMG);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int wx = halo_wrap(xx + j, IMG);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (u >= dup) break;
+        const float y0 = silu_f<FAST>(fmaf(c[j][0], sc0[u], sh0[u]));
+        const float y1 = silu_f<FAST>(fmaf(c[j][1], sc1[u], sh1[u]));
+        const size_t base = ((static_cast<size_t>(i) * dup + u) * PO + yy + 1) * PO + xx + j + 1;
+        store_pair<T>(out + base * 96 + oc, y0, y1);
+        if (wy) store_pair<T>(out + (base + static_cast<long long>(wy) * PO) * 96 + oc, y0, y1);
+        if (wx) store_pair<T>(out + (base + wx) * 96 + oc, y0, y1);
+        if (wy && wx) store_pair<T>(out + (base + static_cast<long long>(wy) * PO + wx) * 96 + oc, y0, y1);
+      }
     }
   }
 }
