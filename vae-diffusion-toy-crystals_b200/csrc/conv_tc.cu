@@ -28,19 +28,23 @@
 namespace tcs {
 
 
-constexpr int EPI_WARPS = 16;
-constexpr int UC = 768 / EPI_WARPS;    // accumulator columns per epilogue warp (4 lane quarters x EPI_WARPS/4 column units cover 192)
-constexpr int BLK = UC / 3;            // channels per staged output block (three blocks per warp and tile)
+constexpr int EPI_WARPS = 16;          // two groups of 8: group g owns TMEM accumulator set g, i.e. every second tile
+constexpr int GRP_WARPS = EPI_WARPS / 2;
+constexpr int UC = 96;                 // accumulator columns per epilogue warp (4 lane quarters x 2 column units cover 192)
+constexpr int BLK = 32;                // channels per staged output block (three blocks per warp and tile)
 constexpr int TC_THREADS = 64 + 32 * EPI_WARPS + 32;   // + a second MMA-issuing warp for the MSUB = 2 tiles
 constexpr int MAX_STAGES = 8;
-constexpr uint32_t EPI_WARP_SLAB = 3 * 32 * BLK * 2;    // per epilogue warp: three 32 px x BLK ch bf16 blocks
+constexpr uint32_t EPI_WARP_SLAB = 2 * 32 * BLK * 2;    // per epilogue warp: two 32 px x BLK ch bf16 blocks (double buffer)
 constexpr uint32_t EPI_SLAB_BYTES = EPI_WARPS * EPI_WARP_SLAB;
 constexpr uint32_t EPI_BIAS_BYTES = 576 * 4;
+struct EpiGroupSmem {          // per epilogue warp group (EPI_GN_FUSED)
+  float scale[192], shift[192];
+  float red[GRP_WARPS][16];    // per warp: (sum, sum of squares) of the 8 GroupNorm groups over its block
+  float mean[8], rstd[8];
+};
 struct EpiFusedSmem {          // EPI_GN_FUSED scratch (lives right after the bias)
   float gamma[192], beta[192];
-  float scale[192], shift[192];
-  float red[EPI_WARPS][16];    // per epilogue warp: (sum, sum of squares) of the 8 GroupNorm groups over its block
-  float mean[8], rstd[8];
+  EpiGroupSmem grp[2];
 };
 constexpr uint32_t EPI_FUSED_BYTES = sizeof(EpiFusedSmem);
 
@@ -60,7 +64,7 @@ __device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned 
 __device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
   asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void epi_bar_sync_all() { asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory"); }
+__device__ __forceinline__ void epi_bar_sync(int grp) { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(32 * GRP_WARPS) : "memory"); }
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
@@ -99,46 +103,44 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
-// A warp writes its THREE 32-pixel x BLK-channel blocks of a tile into its slab (stage_padded_block), then pays the
-// generic->async proxy fence once and issues all TMA stores (flush_padded_blocks); only the lanes on the left/right
-// image border write their column-halo copy themselves.  W == 16: plain per-lane stores (the 16x16 layers are small).
-// Slab rows are BLK*2 bytes, swizzled like the tensor map (SWIZZLE_64B for BLK = 32, SWIZZLE_32B for BLK = 16).
-__device__ __forceinline__ void stage_padded_block(bool use_tma, uint32_t slab, int k, int lane, __nv_bfloat16* obase,
-                                                   size_t pix, int wy, int wx, int Wp, int ldo, int ch, const uint32_t* pk) {
+// 32 pixels (one per lane, consecutive in an image row) x 32 bf16 channels -> padded NHWC output.
+// W >= 32: the warp stages the 2 KB block in a SWIZZLE_64B slab (two halves, double buffered) and one lane TMA-stores it
+// (plus the wrapped row copy); only the lanes on the left/right image border write their column-halo copy themselves.
+// W == 16: plain per-lane 16-byte stores (the 16x16 layers are small).
+__device__ __forceinline__ void store_padded_block(const CUtensorMap* mapO, bool use_tma, uint32_t slab, uint32_t& slab_buf,
+                                                   int lane, __nv_bfloat16* obase, size_t pix, int wy, int wx, int Wp,
+                                                   int ldo, int ch, int img, int y, int x, const uint32_t* pk) {
   if (!use_tma) {
     store_with_halo(obase, pix, wy, wx, Wp, ldo, ch, pk);
     return;
   }
-  const uint32_t dst = slab + k * (32 * BLK * 2) + lane * (BLK * 2);
-  const int sw = BLK == 32 ? ((lane >> 1) & 3) : ((lane >> 2) & 1);
+  if (lane == 0) ptx::bulk_wait_read<1>();   // the slab half written two blocks ago has been read
+  __syncwarp();
+  const uint32_t base = slab + slab_buf * 2048;
+  const uint32_t dst = base + lane * 64;
+  const int sw = (lane >> 1) & 3;
 #pragma unroll
-  for (int j = 0; j < BLK / 8; ++j) st_shared_u4(dst + ((j ^ sw) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+  for (int j = 0; j < 4; ++j) st_shared_u4(dst + ((j ^ sw) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+  ptx::fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) {   // lane 0 holds the first pixel of the block: (y, x) -> padded (y+1, x+1)
+    tma_store_4d(mapO, base, ch, x + 1, y + 1, img);
+    if (wy) tma_store_4d(mapO, base, ch, x + 1, y + 1 + wy, img);
+    ptx::bulk_commit();
+  }
+  slab_buf ^= 1;
   if (wx) {   // column halo (and the corner when this pixel is also on a border row)
     uint4* d0 = reinterpret_cast<uint4*>(obase + (pix + wx) * ldo + ch);
 #pragma unroll
-    for (int i = 0; i < BLK / 8; ++i) d0[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+    for (int i = 0; i < 4; ++i) d0[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
     if (wy) {
       uint4* d1 = reinterpret_cast<uint4*>(obase + (pix + static_cast<long long>(wy) * Wp + wx) * ldo + ch);
 #pragma unroll
-      for (int i = 0; i < BLK / 8; ++i) d1[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+      for (int i = 0; i < 4; ++i) d1[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
     }
   }
 }
-// ch0: channel of block 0 (blocks are BLK channels apart); lane 0 holds the first pixel (y, x) of the 32-pixel run
-__device__ __forceinline__ void flush_padded_blocks(const CUtensorMap* mapO, bool use_tma, uint32_t slab, int lane, int ch0,
-                                                    int img, int y, int x, int wy) {
-  if (!use_tma) return;
-  ptx::fence_proxy_async();
-  __syncwarp();
-  if (lane == 0) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      tma_store_4d(mapO, slab + k * (32 * BLK * 2), ch0 + k * BLK, x + 1, y + 1, img);
-      if (wy) tma_store_4d(mapO, slab + k * (32 * BLK * 2), ch0 + k * BLK, x + 1, y + 1 + wy, img);
-    }
-    ptx::bulk_commit();
-  }
-}
+
 // BLK bf16 channels of one pixel -> padded NHWC tensor, duplicated onto the circular halo where needed
 __device__ __forceinline__ void store_with_halo(__nv_bfloat16* obase, size_t pix, int wy, int wx, int Wp, int ldo,
                                                 int ch, const uint32_t* pk) {
@@ -216,7 +218,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(ptx::smem_u32(&bars.tmem_full[a]), p.issuers);
-      ptx::mbar_init(ptx::smem_u32(&bars.tmem_empty[a]), EPI_WARPS * CG);
+      ptx::mbar_init(ptx::smem_u32(&bars.tmem_empty[a]), GRP_WARPS * CG);
     }
     ptx::fence_barrier_init();
   }
@@ -357,68 +359,63 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       run(I0{}, IM{});
     }
   } else if (warp >= 2 && warp < 2 + EPI_WARPS) {
-    // ============================== epilogue (EPI_WARPS warps, every tile) ================
-    // Measured (TCS_DEBUG 16/32/128): TMEM reads stall the tensor pipe and the epilogue is a chain of latencies (TMEM
-    // load, the GroupNorm exchange between the CTAs of an image, MUFU, TMA stores), not of instruction issue.  So every
-    // accumulator element is read exactly ONCE into registers, the accumulator set is released at once (the MMA warps run
-    // up to two tiles ahead) and the tile is spread over 16 warps: warp (q, u) = (TMEM lane quarter, column unit) owns
-    // 32 rows x UC = 48 of the 192 accumulator columns.
-    //   MSUB == 2 (N = 96): unit u -> 128-row sub-tile u / 2, channels (u % 2) * 48 ...;  MSUB == 1 (N = 192): channels u * 48 ...
-    const int e = warp - 2, q = warp & 3, u = e >> 2;
+    // ============================== epilogue (2 groups x 8 warps) ================
+    // What the clock64 profile (TCS_DEBUG=128) showed: the epilogue of a tile is a chain of latencies (TMEM loads of
+    // ~1k cycles each while the MMAs run, the GroupNorm exchange between the CTAs of an image, MUFU, proxy fence + TMA
+    // stores: ~12k cycles on a K = 864 layer), not of instruction issue, and it does not shrink when the tile is spread
+    // over more warps.  So two tiles are kept in flight: group g = 0/1 owns TMEM accumulator set g and therefore every
+    // second tile of this CTA, and inside a group warp (q, h) = (TMEM lane quarter, unit) streams its 32 rows x 96
+    // columns through registers 32 columns at a time with the next tcgen05.ld already in flight (pass 1: statistics,
+    // pass 2: normalise + store).  A group has two tile periods for its epilogue.
+    // unit h: MSUB == 2 -> 128-row sub-tile h (all N = 96 channels); MSUB == 1 -> channel half h of the N = 192 tile.
+    const int e = warp - 2, grp = e / GRP_WARPS, ew = e % GRP_WARPS, q = warp & 3, h = ew >> 2;
     const int row = q * 32 + lane;
     const int HW = p.H * p.W;
     const int Wp = p.W + 2, Hp = p.H + 2;
     (void)Hp; (void)Wp; (void)HW;
-    const uint32_t slab = slab_base + static_cast<uint32_t>(e) * EPI_WARP_SLAB;      // this warp's 3 staging blocks
+    const uint32_t acc = grp;
+    uint32_t acc_phase = 0, slab_buf = 0;
+    (void)slab_buf;
+    EpiGroupSmem* gsm = &fs->grp[grp];
+    (void)gsm;
+    const uint32_t slab = slab_base + static_cast<uint32_t>(e) * EPI_WARP_SLAB;      // this warp's 2 x 2 KB staging halves
     const bool use_tma_out = p.W >= 32 && !(p.debug & 4);
     (void)use_tma_out; (void)slab;
-    constexpr int UPS = (96 / UC);                       // column units per 96 channels
-    const int sub = (MSUB == 2) ? u / UPS : 0;
-    const int col0 = (MSUB == 2) ? (u % UPS) * UC : u * UC;   // first channel (inside the N tile) of this warp's columns
+    const int sub = (MSUB == 2) ? h : 0;
+    const int col0 = (MSUB == 2) ? 0 : h * UC;   // first channel (inside the N tile) of this warp's columns
     uint32_t it = 0;
     const bool prof = (p.debug & 128) && blockIdx.x == 0 && e == 0;
     long long pw_full = 0, p_ld = 0, p_a = 0, p_b = 0, p_c = 0, pc0 = 0, pc1 = 0, q_post = 0, q_poll = 0, q_npoll = 0, r_ss = 0, r_math = 0, r_store = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-      int mt, nt;
-      tile_to_mn<CG>(tile, p.n_ntiles, mt, nt);
-      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_STRIDE;
-      if (prof) { pc1 = clock64(); if (it) p_c += pc1 - pc0; pc0 = pc1; }
-      ptx::mbar_wait(ptx::smem_u32(&bars.tmem_full[acc]), acc_phase);
-      ptx::tc_fence_after();
-      if (prof) { pc1 = clock64(); pw_full += pc1 - pc0; pc0 = pc1; }
-
-      // ---- the only TMEM traffic of the tile ------------------------------------------------------------------
-      float v[UC];
-      float e0 = 0.f, e1 = 0.f;
-      (void)e0; (void)e1;
-      if (!(p.debug & 16)) {
-        if constexpr (EPI == EPI_EPS) {
-          if (u == 0) {       // column 0 of each sub-tile's accumulator is eps
-            ptx::tmem_ld1(tbase, &e0);
-            ptx::tmem_ld1(tbase + N, &e1);
-            ptx::tmem_ld_wait();
-          }
-        } else {
-          const uint32_t taddr = tbase + u * UC;
-          ptx::tmem_ld32(taddr, v);
-          if (UC == 96) { ptx::tmem_ld32(taddr + 32, v + 32); ptx::tmem_ld32(taddr + 64, v + 64); }
-          else ptx::tmem_ld16(taddr + 32, v + 32);
-          ptx::tmem_ld_wait();
-        }
-      }
+    (void)p_ld; (void)r_store;
+    auto release_tmem = [&]() {
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         if (CG == 2) ptx::mbar_arrive_rank0(ptx::smem_u32(&bars.tmem_empty[acc]));   // the leader's MMA warp waits on it
         else ptx::mbar_arrive(ptx::smem_u32(&bars.tmem_empty[acc]));
       }
-      if (p.debug & 16) continue;   // experiment: no epilogue work at all
-      if (prof) { pc1 = clock64(); p_ld += pc1 - pc0; pc0 = pc1; }
+    };
+    for (int tile = blockIdx.x + grp * gridDim.x; tile < n_tiles; tile += 2 * gridDim.x, acc_phase ^= 1, ++it) {
+      int mt, nt;
+      tile_to_mn<CG>(tile, p.n_ntiles, mt, nt);
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_STRIDE;
+      const uint32_t taddr = tbase + h * UC;
+      if (prof) { pc1 = clock64(); if (it) p_c += pc1 - pc0; pc0 = pc1; }
+      ptx::mbar_wait(ptx::smem_u32(&bars.tmem_full[acc]), acc_phase);
+      ptx::tc_fence_after();
+      if (prof) { pc1 = clock64(); pw_full += pc1 - pc0; pc0 = pc1; }
+      if (p.debug & 16) { release_tmem(); continue; }   // experiment: no epilogue work at all
 
       if constexpr (EPI == EPI_EPS) {
-        // ---- 96 -> 1 output conv + CFG combine in registers
-        if (u == 0) {
+        // ---- 96 -> 1 output conv: column 0 of each sub-tile's accumulator is eps; CFG combine in registers
+        float e0 = 0.f, e1 = 0.f;
+        if (h == 0) {
+          ptx::tmem_ld1(tbase, &e0);
+          ptx::tmem_ld1(tbase + N, &e1);
+          ptx::tmem_ld_wait();
+        }
+        release_tmem();
+        if (h == 0) {
           e0 += bias_s[0];
           e1 += bias_s[0];
           float* eo = static_cast<float*>(p.epi.out);
@@ -430,13 +427,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           }
         }
       } else if constexpr (EPI == EPI_GN_FUSED) {
-        // ---- conv + bias + GroupNorm + SiLU ------------------------------------------------------------------
+        // ---- conv + bias + GroupNorm + SiLU without leaving TMEM ------------------------------------------------
         // The G = tiles_per_img CTAs with blockIdx % G == 0..G-1 hold one image between them and run it in lock
         // step: per-group sums of this CTA's pixels -> global, wait for the other G-1 CTAs, then normalise + SiLU
-        // from the registers.
+        // straight from TMEM.
         constexpr int CPGN = N / 8;            // channels per group: 12 or 24
-        constexpr int NGL = UC / CPGN;         // groups inside this warp's columns: 4 or 2 (8 or 4 with UC = 96)
-        static_assert(UC % CPGN == 0, "a warp's columns must hold whole GroupNorm groups");
+        constexpr int NGL = UC / CPGN;         // groups inside this warp's columns: 8 or 4
         const int G = p.tiles_per_img;
         const int img = mt / G;
         float rv[2 * NGL];                     // (sum, sum of squares) per local group
@@ -444,24 +440,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           float gs[NGL], gq[NGL], gs1[NGL], gq1[NGL];   // even / odd column partial sums kept packed
 #pragma unroll
           for (int g = 0; g < NGL; ++g) gs[g] = gq[g] = gs1[g] = gq1[g] = 0.f;
+          float vbuf[2][32];
+          ptx::tmem_ld32(taddr, vbuf[0]);
 #pragma unroll
-          for (int i = 0; i < UC; i += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + col0 + i);
-            float t0, t1, t2, t3;
-            add2(t0, t1, v[i], v[i + 1], b4.x, b4.y);
-            add2(t2, t3, v[i + 2], v[i + 3], b4.z, b4.w);
-            const int g0 = i / CPGN, g1 = (i + 2) / CPGN;   // pairs never straddle a group (CPGN is even)
-            add2(gs[g0], gs1[g0], gs[g0], gs1[g0], t0, t1);
-            fma2(gq[g0], gq1[g0], t0, t1, t0, t1, gq[g0], gq1[g0]);
-            add2(gs[g1], gs1[g1], gs[g1], gs1[g1], t2, t3);
-            fma2(gq[g1], gq1[g1], t2, t3, t2, t3, gq[g1], gq1[g1]);
+          for (int k = 0; k < 3; ++k) {
+            ptx::tmem_ld_wait();
+            if (k < 2) ptx::tmem_ld32(taddr + (k + 1) * 32, vbuf[(k + 1) & 1]);
+            const float* v = vbuf[k & 1];
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + col0 + k * 32 + i);
+              float t0, t1, t2, t3;
+              add2(t0, t1, v[i], v[i + 1], b4.x, b4.y);
+              add2(t2, t3, v[i + 2], v[i + 3], b4.z, b4.w);
+              const int g0 = (k * 32 + i) / CPGN, g1 = (k * 32 + i + 2) / CPGN;   // pairs never straddle a group
+              add2(gs[g0], gs1[g0], gs[g0], gs1[g0], t0, t1);
+              fma2(gq[g0], gq1[g0], t0, t1, t0, t1, gq[g0], gq1[g0]);
+              add2(gs[g1], gs1[g1], gs[g1], gs1[g1], t2, t3);
+              fma2(gq[g1], gq1[g1], t2, t3, t2, t3, gq[g1], gq1[g1]);
+            }
           }
 #pragma unroll
           for (int g = 0; g < NGL; ++g) { rv[2 * g] = gs[g] + gs1[g]; rv[2 * g + 1] = gq[g] + gq1[g]; }
         }
         // lane reduction: a reduce-scatter over the top lane bits (2*NGL values -> 1 per lane), butterflies for the rest
-        constexpr int NV = 2 * NGL;            // 4, 8 or 16
-        constexpr int SC_STEPS = NV == 16 ? 4 : (NV == 8 ? 3 : 2);
+        constexpr int NV = 2 * NGL;            // 8 or 16
+        constexpr int SC_STEPS = NV == 16 ? 4 : 3;
         int idx = 0;
 #pragma unroll
         for (int st = 0; st < SC_STEPS; ++st) {
@@ -477,12 +481,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         }
 #pragma unroll
         for (int off = 16 >> SC_STEPS; off >= 1; off >>= 1) rv[0] += __shfl_xor_sync(0xffffffffu, rv[0], off);
-        if (lane < 16) fs->red[e][lane] = 0.f;   // the slots of the groups this warp does not cover
+        if (lane < 16) gsm->red[ew][lane] = 0.f;   // the slots of the groups this warp does not cover
         __syncwarp();
-        if ((lane & ((32 >> SC_STEPS) - 1)) == 0) fs->red[e][2 * (col0 / CPGN) + idx] = rv[0];
-        epi_bar_sync_all();
+        if ((lane & ((32 >> SC_STEPS) - 1)) == 0) gsm->red[ew][2 * (col0 / CPGN) + idx] = rv[0];
+        epi_bar_sync(grp);
         if (prof) { pc1 = clock64(); p_a += pc1 - pc0; pc0 = pc1; }
-        if (e == 0) {
+        if (ew == 0) {
           // Exchange between the G CTAs of the image, one L2 round trip each way: every (value, flag) pair is ONE 64-bit
           // word (the flag travels with the data, as in NCCL's LL protocol), so there is no separate counter, no fence and
           // no second read.  The buffer is zeroed before the launch; flag 1 = valid.
@@ -490,7 +494,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           if (lane < 16) {
             float tot = 0.f;
 #pragma unroll
-            for (int w = 0; w < EPI_WARPS; ++w) tot += fs->red[w][lane];
+            for (int w = 0; w < GRP_WARPS; ++w) tot += gsm->red[w][lane];
             st_relaxed_gpu_u64(ll + static_cast<size_t>(mt) * 16 + lane, (1ULL << 32) | __float_as_uint(tot));
           }
           if (prof) { pc1 = clock64(); q_post += pc1 - pc0; }
@@ -529,24 +533,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const double mean = static_cast<double>(part) * p.gn_inv_cnt;
             double var = fma(-mean, mean, static_cast<double>(qsum) * p.gn_inv_cnt);
             var = var < 0.0 ? 0.0 : var;
-            fs->mean[lane >> 1] = static_cast<float>(mean);
-            fs->rstd[lane >> 1] = rsqrtf(static_cast<float>(var) + GN_EPS);
+            gsm->mean[lane >> 1] = static_cast<float>(mean);
+            gsm->rstd[lane >> 1] = rsqrtf(static_cast<float>(var) + GN_EPS);
           }
         }
-        epi_bar_sync_all();
+        epi_bar_sync(grp);
         if (prof) { pc1 = clock64(); p_b += pc1 - pc0; pc0 = pc1; }
-        for (int c = threadIdx.x - 64; c < N; c += 32 * EPI_WARPS) {
+        for (int c = threadIdx.x - 64 - grp * (32 * GRP_WARPS); c < N; c += 32 * GRP_WARPS) {
           const int g = c / CPGN;
-          const float sc = fs->rstd[g] * fs->gamma[c];
-          fs->scale[c] = 0.5f * sc;                                                  // h = y / 2 = v * scale + shift
-          fs->shift[c] = 0.5f * ((bias_s[c] - fs->mean[g]) * sc + fs->beta[c]);
+          const float sc = gsm->rstd[g] * fs->gamma[c];
+          gsm->scale[c] = 0.5f * sc;                                                  // h = y / 2 = v * scale + shift
+          gsm->shift[c] = 0.5f * ((bias_s[c] - gsm->mean[g]) * sc + fs->beta[c]);
         }
-        epi_bar_sync_all();
+        epi_bar_sync(grp);
         if (prof) { pc1 = clock64(); r_ss += pc1 - pc0; }
-        if (use_tma_out) {
-          if (lane == 0) ptx::bulk_wait_read<0>();   // the previous tile's stores have read the slab
-          __syncwarp();
-        }
         __nv_bfloat16* obase = static_cast<__nv_bfloat16*>(p.epi.out);
         const int m = (mt * MSUB + sub) * 128 + row;
         const int rem = m - img * HW;
@@ -554,36 +554,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int wy = (y == 0) ? p.H : ((y == p.H - 1) ? -p.H : 0);
         const int wx = (x == 0) ? p.W : ((x == p.W - 1) ? -p.W : 0);
         const size_t pix = (static_cast<size_t>(img) * Hp + (y + 1)) * Wp + (x + 1);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const int cc = col0 + k * BLK;
-          uint32_t pk[BLK / 2];
-#pragma unroll
-          for (int i = 0; i < BLK; i += 4) {
-            const float4 s4 = *reinterpret_cast<const float4*>(fs->scale + cc + i);
-            const float4 h4 = *reinterpret_cast<const float4*>(fs->shift + cc + i);
-            float h0, h1, h2, h3, y0, y1, y2, y3;
-            fma2(h0, h1, v[k * BLK + i], v[k * BLK + i + 1], s4.x, s4.y, h4.x, h4.y);          // h = y/2
-            fma2(h2, h3, v[k * BLK + i + 2], v[k * BLK + i + 3], s4.z, s4.w, h4.z, h4.w);
-            fma2(y0, y1, h0, h1, tanh_fast(h0), tanh_fast(h1), h0, h1);    // SiLU(y) = h + h tanh(h)
-            fma2(y2, y3, h2, h3, tanh_fast(h2), tanh_fast(h3), h2, h3);
-            pk[i / 2] = pack_bf16x2(y0, y1);
-            pk[i / 2 + 1] = pack_bf16x2(y2, y3);
-          }
-          long long ps0 = prof ? clock64() : 0;
-          if (!(p.debug & 2)) stage_padded_block(use_tma_out, slab, k, lane, obase, pix, wy, wx, Wp, p.epi.ldo, cc, pk);
-          else if (pk[0] == 0x12345678u && pk[BLK / 2 - 1] == 0x9abcdef0u) obase[0] = __float2bfloat16(0.f);
-          if (prof) r_store += clock64() - ps0;
-        }
         {
-          long long ps0 = prof ? clock64() : 0;
-          if (!(p.debug & 2)) flush_padded_blocks(&mapO, use_tma_out, slab, lane, col0, img, y, x, wy);
-          if (prof) r_store += clock64() - ps0;
+          float vbuf[2][32];
+          ptx::tmem_ld32(taddr, vbuf[0]);
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            ptx::tmem_ld_wait();
+            if (k < 2) ptx::tmem_ld32(taddr + (k + 1) * 32, vbuf[(k + 1) & 1]);
+            else release_tmem();   // the accumulator set is free as soon as its last column block is in registers
+            const float* v = vbuf[k & 1];
+            const int cc = col0 + k * 32;
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 s4 = *reinterpret_cast<const float4*>(gsm->scale + cc + i);
+              const float4 h4 = *reinterpret_cast<const float4*>(gsm->shift + cc + i);
+              float h0, h1, h2, h3, y0, y1, y2, y3;
+              fma2(h0, h1, v[i], v[i + 1], s4.x, s4.y, h4.x, h4.y);          // h = y/2
+              fma2(h2, h3, v[i + 2], v[i + 3], s4.z, s4.w, h4.z, h4.w);
+              fma2(y0, y1, h0, h1, tanh_fast(h0), tanh_fast(h1), h0, h1);    // SiLU(y) = h + h tanh(h)
+              fma2(y2, y3, h2, h3, tanh_fast(h2), tanh_fast(h3), h2, h3);
+              pk[i / 2] = pack_bf16x2(y0, y1);
+              pk[i / 2 + 1] = pack_bf16x2(y2, y3);
+            }
+            if (!(p.debug & 2))
+              store_padded_block(&mapO, use_tma_out, slab, slab_buf, lane, obase, pix, wy, wx, Wp, p.epi.ldo, cc, img, y, x, pk);
+            else if (pk[0] == 0x12345678u && pk[7] == 0x9abcdef0u) obase[0] = __float2bfloat16(0.f);
+          }
         }
         if (prof) r_math += clock64() - pc1;
       } else if constexpr (N >= 96) {
         const int n_off = nt * N + col0;                     // first output channel of this warp's columns
         const int m = (mt * MSUB + sub) * 128 + row;         // global pixel index (b, y, x)
+        float vbuf[2][32];
+        ptx::tmem_ld32(taddr, vbuf[0]);
         if constexpr (EPI == EPI_RAW_STATS) {
           // fp32 output (one row per lane, plain stores) plus per-(warp, group) partial sums for a separate GroupNorm
           // pass: the unfused A/B path (TCS_FUSE_GN=0) and the per-layer tests; not on the production path
@@ -594,15 +598,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           for (int g = 0; g < NG; ++g) gs[g] = gq[g] = 0.f;
           float* orow = static_cast<float*>(p.epi.out) + static_cast<size_t>(m) * p.epi.ldo + n_off;
 #pragma unroll
-          for (int i = 0; i < UC; i += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n_off + i);
-            v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
-            *reinterpret_cast<float4*>(orow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-          }
+          for (int k = 0; k < 3; ++k) {
+            ptx::tmem_ld_wait();
+            if (k < 2) ptx::tmem_ld32(taddr + (k + 1) * 32, vbuf[(k + 1) & 1]);
+            else release_tmem();
+            float* v = vbuf[k & 1];
 #pragma unroll
-          for (int i = 0; i < UC; ++i) {
-            gs[i / CPGN] += v[i];
-            gq[i / CPGN] += v[i] * v[i];
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n_off + k * 32 + i);
+              v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+              *reinterpret_cast<float4*>(orow + k * 32 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              gs[(k * 32 + i) / CPGN] += v[i];
+              gq[(k * 32 + i) / CPGN] += v[i] * v[i];
+            }
           }
 #pragma unroll
           for (int g = 0; g < NG; ++g) {
@@ -630,51 +641,57 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           const size_t pix = (static_cast<size_t>(b) * Hp + (y + 1)) * Wp + (x + 1);
           const __nv_bfloat16* rrow =
               p.epi.residual ? static_cast<const __nv_bfloat16*>(p.epi.residual) + pix * p.ntot + n_off : nullptr;
-          if (use_tma_out) {
-            if (lane == 0) ptx::bulk_wait_read<0>();   // the previous tile's stores have read the slab
-            __syncwarp();
-          }
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
-            const int c0 = k * BLK;
+            const int c0 = k * 32;
+            ptx::tmem_ld_wait();
+            if (k < 2) ptx::tmem_ld32(taddr + (k + 1) * 32, vbuf[(k + 1) & 1]);
+            else release_tmem();
+            float* v = vbuf[k & 1];
             if (rrow) {
 #pragma unroll
-              for (int i = 0; i < BLK / 8; ++i) {
+              for (int i = 0; i < 4; ++i) {
                 const uint4 rr = *reinterpret_cast<const uint4*>(rrow + c0 + i * 8);
                 const uint32_t w4[4] = {rr.x, rr.y, rr.z, rr.w};
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
                   const float2 rf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[kk]));
-                  v[c0 + i * 8 + 2 * kk] += rf.x;
-                  v[c0 + i * 8 + 2 * kk + 1] += rf.y;
+                  v[i * 8 + 2 * kk] += rf.x;
+                  v[i * 8 + 2 * kk + 1] += rf.y;
                 }
               }
             }
-            uint32_t pk[BLK / 2];
+            uint32_t pk[16];
 #pragma unroll
-            for (int i = 0; i < BLK; i += 4) {
+            for (int i = 0; i < 32; i += 4) {
               const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n_off + c0 + i);
-              pk[i / 2] = pack_bf16x2(v[c0 + i] + b4.x, v[c0 + i + 1] + b4.y);
-              pk[i / 2 + 1] = pack_bf16x2(v[c0 + i + 2] + b4.z, v[c0 + i + 3] + b4.w);
+              pk[i / 2] = pack_bf16x2(v[i] + b4.x, v[i + 1] + b4.y);
+              pk[i / 2 + 1] = pack_bf16x2(v[i + 2] + b4.z, v[i + 3] + b4.w);
             }
-            stage_padded_block(use_tma_out, slab, k, lane, obase, pix, wy, wx, Wp, p.epi.ldo, n_off + c0, pk);
+            store_padded_block(&mapO, use_tma_out, slab, slab_buf, lane, obase, pix, wy, wx, Wp, p.epi.ldo, n_off + c0, b, y, x, pk);
           }
-          flush_padded_blocks(&mapO, use_tma_out, slab, lane, n_off, b, y, x, wy);
         } else {  // EPI_PLAIN
           __nv_bfloat16* orow = static_cast<__nv_bfloat16*>(p.epi.out) + static_cast<size_t>(m) * p.epi.ldo + n_off;
 #pragma unroll
-          for (int i = 0; i < UC; i += 8) {
-            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n_off + i);
-            const float4 b5 = *reinterpret_cast<const float4*>(bias_s + n_off + i + 4);
-            *reinterpret_cast<uint4*>(orow + i) =
-                make_uint4(pack_bf16x2(v[i] + b4.x, v[i + 1] + b4.y), pack_bf16x2(v[i + 2] + b4.z, v[i + 3] + b4.w),
-                           pack_bf16x2(v[i + 4] + b5.x, v[i + 5] + b5.y), pack_bf16x2(v[i + 6] + b5.z, v[i + 7] + b5.w));
+          for (int k = 0; k < 3; ++k) {
+            ptx::tmem_ld_wait();
+            if (k < 2) ptx::tmem_ld32(taddr + (k + 1) * 32, vbuf[(k + 1) & 1]);
+            else release_tmem();
+            const float* v = vbuf[k & 1];
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n_off + k * 32 + i);
+              const float4 b5 = *reinterpret_cast<const float4*>(bias_s + n_off + k * 32 + i + 4);
+              *reinterpret_cast<uint4*>(orow + k * 32 + i) =
+                  make_uint4(pack_bf16x2(v[i] + b4.x, v[i + 1] + b4.y), pack_bf16x2(v[i + 2] + b4.z, v[i + 3] + b4.w),
+                             pack_bf16x2(v[i + 4] + b5.x, v[i + 5] + b5.y), pack_bf16x2(v[i + 6] + b5.z, v[i + 7] + b5.w));
+            }
           }
         }
       }
     }
     if (prof && lane == 0 && it > 1)
-      printf("[epi N=%d EPI=%d] per tile: wait tmem_full %lld  tmem ld %lld  stats+barA %lld  exchange+barB %lld (post %lld, poll %lld, polls %lld)  rest(pass2+stores) %lld (scale/shift+barC %lld, pass2 %lld of which stores %lld)\n",
+      printf("[epi N=%d EPI=%d] per tile: wait tmem_full %lld  tmem ld %lld  stats+barA %lld  exchange+barB %lld (post %lld, poll %lld, polls %lld)  rest(pass2+stores) %lld (scale/shift+barC %lld, pass2 %lld, %lld)\n",
              N, EPI, pw_full / it, p_ld / it, p_a / it, p_b / it, q_post / it, q_poll / it, q_npoll / it, p_c / (it - 1), r_ss / it, r_math / it, r_store / it);
     if (lane == 0) ptx::bulk_wait_all();   // staged TMA stores have left shared memory
   }
