@@ -109,13 +109,16 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
 // W == 16: plain per-lane 16-byte stores (the 16x16 layers are small).
 __device__ __forceinline__ void store_padded_block(const CUtensorMap* mapO, bool use_tma, uint32_t slab, uint32_t& slab_buf,
                                                    int lane, __nv_bfloat16* obase, size_t pix, int wy, int wx, int Wp,
-                                                   int ldo, int ch, int img, int y, int x, const uint32_t* pk) {
+                                                   int ldo, int ch, int img, int y, int x, const uint32_t* pk,
+                                                   long long* tacc = nullptr) {
   if (!use_tma) {
     store_with_halo(obase, pix, wy, wx, Wp, ldo, ch, pk);
     return;
   }
+  long long c0 = tacc ? clock64() : 0;
   if (lane == 0) ptx::bulk_wait_read<1>();   // the slab half written two blocks ago has been read
   __syncwarp();
+  if (tacc) { const long long c1 = clock64(); tacc[0] += c1 - c0; c0 = c1; }
   const uint32_t base = slab + slab_buf * 2048;
   const uint32_t dst = base + lane * 64;
   const int sw = (lane >> 1) & 3;
@@ -123,11 +126,14 @@ __device__ __forceinline__ void store_padded_block(const CUtensorMap* mapO, bool
   for (int j = 0; j < 4; ++j) st_shared_u4(dst + ((j ^ sw) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
   ptx::fence_proxy_async();
   __syncwarp();
+  if (tacc) { const long long c1 = clock64(); tacc[1] += c1 - c0; c0 = c1; }
   if (lane == 0) {   // lane 0 holds the first pixel of the block: (y, x) -> padded (y+1, x+1)
     tma_store_4d(mapO, base, ch, x + 1, y + 1, img);
     if (wy) tma_store_4d(mapO, base, ch, x + 1, y + 1 + wy, img);
     ptx::bulk_commit();
   }
+  __syncwarp();
+  if (tacc) { const long long c1 = clock64(); tacc[2] += c1 - c0; c0 = c1; }
   slab_buf ^= 1;
   if (wx) {   // column halo (and the corner when this pixel is also on a border row)
     uint4* d0 = reinterpret_cast<uint4*>(obase + (pix + wx) * ldo + ch);
@@ -387,6 +393,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const bool prof = (p.debug & 128) && blockIdx.x == 0 && e == 0;
     long long pw_full = 0, p_ld = 0, p_a = 0, p_b = 0, p_c = 0, pc0 = 0, pc1 = 0, q_post = 0, q_poll = 0, q_npoll = 0, r_ss = 0, r_math = 0, r_store = 0;
     (void)p_ld; (void)r_store;
+    long long tacc[3] = {0, 0, 0};
     auto release_tmem = [&]() {
       ptx::tc_fence_before();
       __syncwarp();
@@ -578,7 +585,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
               pk[i / 2 + 1] = pack_bf16x2(y2, y3);
             }
             if (!(p.debug & 2))
-              store_padded_block(&mapO, use_tma_out, slab, slab_buf, lane, obase, pix, wy, wx, Wp, p.epi.ldo, cc, img, y, x, pk);
+              store_padded_block(&mapO, use_tma_out, slab, slab_buf, lane, obase, pix, wy, wx, Wp, p.epi.ldo, cc, img, y, x, pk,
+                                 prof ? tacc : nullptr);
             else if (pk[0] == 0x12345678u && pk[7] == 0x9abcdef0u) obase[0] = __float2bfloat16(0.f);
           }
         }
@@ -691,8 +699,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       }
     }
     if (prof && lane == 0 && it > 1)
-      printf("[epi N=%d EPI=%d] per tile: wait tmem_full %lld  tmem ld %lld  stats+barA %lld  exchange+barB %lld (post %lld, poll %lld, polls %lld)  rest(pass2+stores) %lld (scale/shift+barC %lld, pass2 %lld, %lld)\n",
-             N, EPI, pw_full / it, p_ld / it, p_a / it, p_b / it, q_post / it, q_poll / it, q_npoll / it, p_c / (it - 1), r_ss / it, r_math / it, r_store / it);
+      printf("[epi N=%d EPI=%d] per tile: wait tmem_full %lld  tmem ld %lld  stats+barA %lld  exchange+barB %lld (post %lld, poll %lld, polls %lld)  rest(pass2+stores) %lld (scale/shift+barC %lld, pass2 %lld: wait_read %lld, sts+fence %lld, tma issue %lld)\n",
+             N, EPI, pw_full / it, p_ld / it, p_a / it, p_b / it, q_post / it, q_poll / it, q_npoll / it, p_c / (it - 1), r_ss / it, r_math / it, tacc[0] / it, tacc[1] / it, tacc[2] / it);
     if (lane == 0) ptx::bulk_wait_all();   // staged TMA stores have left shared memory
   }
 
