@@ -74,6 +74,15 @@ def max_over_ranks(value: float, device) -> float:
     return float(t.item())
 
 
+def quiet_nccl():
+    """Keep stdout to the one JSON line: any NCCL_DEBUG level (even WARN) prints 'NCCL version ...' on stdout.
+    TCS_NCCL_DEBUG=INFO re-enables NCCL's log (e.g. to see NVLS) at the price of extra stdout lines."""
+    if "TCS_NCCL_DEBUG" in os.environ:
+        os.environ["NCCL_DEBUG"] = os.environ["TCS_NCCL_DEBUG"]
+    else:
+        os.environ.pop("NCCL_DEBUG", None)
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -269,7 +278,7 @@ def run_gpu_prior(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("TCS_NCCL_DEBUG", "WARN")
+        quiet_nccl()
         dist.init_process_group("nccl", device_id=dev)
     n = args.n or 4096
     n_total = n * world
@@ -438,7 +447,7 @@ def run_gpu(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("TCS_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+        quiet_nccl()
         dist.init_process_group("nccl", device_id=dev)
     n = args.n or 1024
     n_total = n * world
