@@ -561,7 +561,7 @@ int tcs_create(tcs_handle** out, const tcs_config* cfg) {
     h->fuse_gn = h->use_tc && !(e && atoi(e) == 0);
     h->fuse_first = !(e && atoi(e) == 0);
   }
-  h->chunk = cfg->chunk > 0 ? cfg->chunk : 512;
+  h->chunk = cfg->chunk > 0 ? cfg->chunk : 2048;
   if (h->chunk % 2) h->chunk += 1;
   TCS_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   TCS_CUDA(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
