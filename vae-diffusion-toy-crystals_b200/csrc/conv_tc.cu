@@ -34,7 +34,8 @@ constexpr int UC = 96;                 // accumulator columns per epilogue warp 
 constexpr int BLK = 32;                // channels per staged output block (three blocks per warp and tile)
 constexpr int TC_THREADS = 64 + 32 * EPI_WARPS + 32;   // + a second MMA-issuing warp for the MSUB = 2 tiles
 constexpr int MAX_STAGES = 8;
-constexpr uint32_t EPI_WARP_SLAB = 2 * 32 * BLK * 2;    // per epilogue warp: two 32 px x BLK ch bf16 blocks (double buffer)
+constexpr int SLAB_BUFS = 2;                            // staging blocks per epilogue warp (1 frees an operand stage: measured no gain)
+constexpr uint32_t EPI_WARP_SLAB = SLAB_BUFS * 32 * BLK * 2;    // per epilogue warp: 32 px x BLK ch bf16 blocks
 constexpr uint32_t EPI_SLAB_BYTES = EPI_WARPS * EPI_WARP_SLAB;
 constexpr uint32_t EPI_BIAS_BYTES = 576 * 4;
 struct EpiGroupSmem {          // per epilogue warp group (EPI_GN_FUSED)
@@ -116,10 +117,10 @@ __device__ __forceinline__ void store_padded_block(const CUtensorMap* mapO, bool
     return;
   }
   long long c0 = tacc ? clock64() : 0;
-  if (lane == 0) ptx::bulk_wait_read<1>();   // the slab half written two blocks ago has been read
+  if (lane == 0) ptx::bulk_wait_read<SLAB_BUFS - 1>();   // the staging block about to be overwritten has been read
   __syncwarp();
   if (tacc) { const long long c1 = clock64(); tacc[0] += c1 - c0; c0 = c1; }
-  const uint32_t base = slab + slab_buf * 2048;
+  const uint32_t base = slab + (SLAB_BUFS == 2 ? slab_buf * 2048 : 0);
   const uint32_t dst = base + lane * 64;
   const int sw = (lane >> 1) & 3;
 #pragma unroll
@@ -324,18 +325,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const uint32_t a_base = smem_base + stage * p.stage_bytes;
             const uint64_t adesc = make_desc_sw64(a_base), bdesc = make_desc_sw64(a_base + p.a_bytes);
             const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
+            // running 64-bit descriptors: one uniform 64-bit add per operand and MMA (the issuing thread is the
+            // bottleneck of this kernel, every instruction in this loop costs ~10 cycles of issue time per MMA)
+            uint64_t adj = adesc + static_cast<uint64_t>(SUB_LO * a_inc_sub), bdj = bdesc;
+            const uint64_t a_step = a_inc_j, a_sub = a_inc_sub;
             for (int j = 0; j < p.T; ++j) {
+              uint64_t ad = adj;
 #pragma unroll
               for (int sub = SUB_LO; sub < SUB_HI; ++sub) {
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                  const uint64_t ad = adesc + (j * a_inc_j + sub * a_inc_sub + k * 2);
-                  const uint64_t bd = bdesc + (j * ((NB * 64) >> 4) + k * 2);
-                  const uint32_t accum = (ks | j | k) != 0 ? 1u : 0u;
-                  if (CG == 2) ptx::umma_bf16_2sm(d_tmem + sub * N, ad, bd, idesc, accum);
-                  else ptx::umma_bf16(d_tmem + sub * N, ad, bd, idesc, accum);
+                const uint32_t first = (ks | j) != 0 ? 1u : 0u;
+                if (CG == 2) {
+                  ptx::umma_bf16_2sm(d_tmem + sub * N, ad, bdj, idesc, first);
+                  ptx::umma_bf16_2sm(d_tmem + sub * N, ad + 2, bdj + 2, idesc, 1u);
+                } else {
+                  ptx::umma_bf16(d_tmem + sub * N, ad, bdj, idesc, first);
+                  ptx::umma_bf16(d_tmem + sub * N, ad + 2, bdj + 2, idesc, 1u);
                 }
+                ad += a_sub;
               }
+              adj += a_step;
+              bdj += (NB * 64) >> 4;
             }
             if (CG == 2) {
               ptx::umma_commit_2sm(ptx::smem_u32(&bars.empty[stage]));
