@@ -513,9 +513,85 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const T* __restrict__ i
     }
   }
 }
+// Tiled variant: a block stages UP_BR + 2 (edge-clamped) input rows of one image in shared memory, so every input value
+// is read from L2 1.5 times instead of 9 (the plain kernel was bound by its L2 read traffic: 9 x 16 B per thread).
+constexpr int UP_BR = 4;
+template <typename T>
+__global__ void __launch_bounds__(256) upsample2x_tiled_kernel(const T* __restrict__ in, int h, int w, int C,
+                                                              T* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char up_smem[];
+  T* tile = reinterpret_cast<T*>(up_smem);            // [UP_BR + 2][w][C]
+  const int bands = h / UP_BR;
+  const int b = blockIdx.x / bands, iy0 = (blockIdx.x - b * bands) * UP_BR;
+  const int cv = C / 8, wp = w + 2, hp = h + 2;
+  const T* ib = in + static_cast<size_t>(b) * hp * wp * C;
+  const int row_vecs = w * cv;
+  for (int e = threadIdx.x; e < (UP_BR + 2) * row_vecs; e += 256) {
+    const int j = e / row_vecs, r = e - j * row_vecs;          // r = x * cv + channel vector
+    const int ys = min(max(iy0 - 1 + j, 0), h - 1);
+    Vec8<T> v;
+    v.load(ib + (static_cast<size_t>(ys + 1) * wp + 1) * C + static_cast<size_t>(r) * 8);
+    v.store(tile + static_cast<size_t>(e) * 8);
+  }
+  __syncthreads();
+  const int H = 2 * h, W = 2 * w, Wp = W + 2, Hp = H + 2;
+  for (int e = threadIdx.x; e < UP_BR * row_vecs; e += 256) {
+    const int jr = e / row_vecs, r = e - jr * row_vecs;
+    const int ix = r / cv, c = (r - ix * cv) * 8;
+    const int iy = iy0 + jr;
+    const int xs[3] = {max(ix - 1, 0), ix, min(ix + 1, w - 1)};
+    float hl[3][8], hr[3][8];   // horizontal lerps for output columns 2ix (left) and 2ix+1 (right), per input row
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const T* trow = tile + (static_cast<size_t>(jr + j) * w) * C + c;   // tile row jr + j = input row iy - 1 + j (clamped)
+      Vec8<T> v0, v1, v2;
+      v0.load(trow + static_cast<size_t>(xs[0]) * C);
+      v1.load(trow + static_cast<size_t>(xs[1]) * C);
+      v2.load(trow + static_cast<size_t>(xs[2]) * C);
+      float f0[8], f1[8], f2[8];
+      v0.get(f0); v1.get(f1); v2.get(f2);
+      const float wl0 = ix == 0 ? 1.0f : 0.25f, wl1 = ix == 0 ? 0.0f : 0.75f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        hl[j][k] = ix == 0 ? f1[k] : (wl0 * f0[k] + wl1 * f1[k]);
+        hr[j][k] = 0.75f * f1[k] + 0.25f * f2[k];
+      }
+    }
+#pragma unroll
+    for (int py = 0; py < 2; ++py) {
+      const int y = 2 * iy + py;
+#pragma unroll
+      for (int px = 0; px < 2; ++px) {
+        const int x = 2 * ix + px;
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float t0 = px ? hr[0][k] : hl[0][k], t1 = px ? hr[1][k] : hl[1][k], t2 = px ? hr[2][k] : hl[2][k];
+          if (py == 0) o[k] = iy == 0 ? t1 : (0.25f * t0 + 0.75f * t1);
+          else o[k] = 0.75f * t1 + 0.25f * t2;
+        }
+        Vec8<T> ov;
+        ov.set(o);
+        const int wy = halo_wrap(y, H), wx = halo_wrap(x, W);
+        const size_t base = (static_cast<size_t>(b) * Hp + y + 1) * Wp + x + 1;
+        ov.store(out + base * C + c);
+        if (wy) ov.store(out + (base + static_cast<long long>(wy) * Wp) * C + c);
+        if (wx) ov.store(out + (base + wx) * C + c);
+        if (wy && wx) ov.store(out + (base + static_cast<long long>(wy) * Wp + wx) * C + c);
+      }
+    }
+  }
+}
+
 template <typename T>
 int launch_upsample2x(const T* in, int B, int h, int w, int C, T* out, cudaStream_t st) {
   if (B <= 0) return TCS_OK;
+  const size_t tile_bytes = static_cast<size_t>(UP_BR + 2) * w * C * sizeof(T);
+  if (h % UP_BR == 0 && C % 8 == 0 && tile_bytes <= 48 * 1024) {
+    upsample2x_tiled_kernel<T><<<static_cast<unsigned>(B * (h / UP_BR)), 256, tile_bytes, st>>>(in, h, w, C, out);
+    TCS_CUDA(cudaGetLastError());
+    return TCS_OK;
+  }
   const long long total = static_cast<long long>(B) * h * w * (C / 8);
   upsample2x_kernel<T><<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(in, h, w, C, out, total);
   TCS_CUDA(cudaGetLastError());
