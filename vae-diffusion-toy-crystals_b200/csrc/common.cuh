@@ -56,6 +56,8 @@ struct ConvGeom {
   int csrc[2];    // channels per source (multiples of 32)
   int in_pad[2];  // 1 = source is a padded tensor, 0 = plain
   int ntot;       // total output channels
+  int kx_in_n = 0; // 96 -> 1 output conv only: the three kx taps are three GEMM columns sharing ONE (unshifted) window per
+                   // channel block; the epilogue sums column kx of pixel x + kx - 1 (circular in x)
 };
 
 struct EpiArgs {

@@ -271,17 +271,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 if (CG == 2) {
                   // both CTAs' loads complete on the LEADER's full barrier; the leader arms it for both
                   if (cta_rank == 0) ptx::mbar_expect_tx(full, 2 * (p.a_bytes + p.T * NB * 64));
-                  ptx::tma_load_4d_2sm(a_dst, mapA, full, cb * 32, kx + p.base_off[src],
+                  ptx::tma_load_4d_2sm(a_dst, mapA, full, cb * 32, kx + p.kxn + p.base_off[src],
                                        p.stride * y0 + kyg + p.base_off[src], b);
                   for (int j = 0; j < p.T; ++j)
                     ptx::tma_load_2d_2sm(b_dst + j * NB * 64, &mapW, full, 0,
                                          (ks * p.T + j) * p.ntot + nt * N + static_cast<int>(cta_rank) * NB);
                 } else {
                   ptx::mbar_expect_tx(full, p.a_bytes + p.T * N * 64);
-                  ptx::tma_load_4d(a_dst, mapA, full, cb * 32, kx + p.base_off[src],
+                  ptx::tma_load_4d(a_dst, mapA, full, cb * 32, kx + p.kxn + p.base_off[src],
                                    p.stride * y0 + kyg + p.base_off[src], b);
                   if (p.pair)
-                    ptx::tma_load_4d(a_dst + p.a_bytes / 2, mapA, full, cb * 32, kx + p.base_off[src],
+                    ptx::tma_load_4d(a_dst + p.a_bytes / 2, mapA, full, cb * 32, kx + p.kxn + p.base_off[src],
                                      p.stride * y0 + kyg + p.base_off[src], b + 1);
                   for (int j = 0; j < p.T; ++j)
                     ptx::tma_load_2d(b_dst + j * N * 64, &mapW, full, 0, (ks * p.T + j) * p.ntot + nt * N);
@@ -426,11 +426,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         // ---- 96 -> 1 output conv: column 0 of each sub-tile's accumulator is eps; CFG combine in registers
         float e0 = 0.f, e1 = 0.f;
         if (h == 0) {
-          ptx::tmem_ld1(tbase, &e0);
-          ptx::tmem_ld1(tbase + N, &e1);
-          ptx::tmem_ld_wait();
+          if (p.kxn) {
+            // columns 0..2 = the kx taps evaluated at THIS pixel's window; eps(x) = c0(x-1) + c1(x) + c2(x+1), circular in
+            // x.  A warp holds 32 consecutive pixels of a 64-pixel image row, its partner (q ^ 1) the other half.
+            float a0[4], a1[4];
+            ptx::tmem_ld4(tbase, a0);
+            ptx::tmem_ld4(tbase + N, a1);
+            ptx::tmem_ld_wait();
+            release_tmem();
+            float* xch = reinterpret_cast<float*>(fs) + grp * 32;   // [4 warps][4] exchange slots (EPI_EPS never uses fs otherwise)
+            const int qq = q;   // pixel position inside the sub-tile follows the TMEM lane quarter
+            if (lane == 31) { xch[qq * 4 + 0] = a0[0]; xch[qq * 4 + 1] = a1[0]; }
+            if (lane == 0) { xch[qq * 4 + 2] = a0[2]; xch[qq * 4 + 3] = a1[2]; }
+            asm volatile("bar.sync %0, 128;" ::"r"(3 + grp) : "memory");
+            float l0 = __shfl_up_sync(0xffffffffu, a0[0], 1), l1 = __shfl_up_sync(0xffffffffu, a1[0], 1);
+            float r0 = __shfl_down_sync(0xffffffffu, a0[2], 1), r1 = __shfl_down_sync(0xffffffffu, a1[2], 1);
+            const int pq = qq ^ 1;
+            if (lane == 0) { l0 = xch[pq * 4 + 0]; l1 = xch[pq * 4 + 1]; }
+            if (lane == 31) { r0 = xch[pq * 4 + 2]; r1 = xch[pq * 4 + 3]; }
+            e0 = (l0 + a0[1]) + r0;
+            e1 = (l1 + a1[1]) + r1;
+            asm volatile("bar.sync %0, 128;" ::"r"(3 + grp) : "memory");   // slots are free for the next tile
+          } else {
+            ptx::tmem_ld1(tbase, &e0);
+            ptx::tmem_ld1(tbase + N, &e1);
+            ptx::tmem_ld_wait();
+            release_tmem();
+          }
+        } else {
+          release_tmem();
         }
-        release_tmem();
         if (h == 0) {
           e0 += bias_s[0];
           e1 += bias_s[0];
@@ -727,7 +752,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 // host side
 // ---------------------------------------------------------------------------------------
 static void stage_shape(const ConvGeom& g, int* T, int* KYG, int* KW) {
-  *KW = g.ksize;
+  *KW = g.kx_in_n ? 1 : g.ksize;
   if (g.ksize == 4) { *T = 2; *KYG = 2; }
   else if (g.ksize == 3) { *T = 3; *KYG = 1; }
   else { *T = 1; *KYG = 1; }
@@ -764,7 +789,9 @@ void conv_tc_pack_weights(const ConvGeom& g, const float* w, __nv_bfloat16* out)
             for (int n = 0; n < g.ntot; ++n)
               for (int c = 0; c < 32; ++c) {
                 const int ci = coff + cb * 32 + c;
-                const float v = w[((static_cast<size_t>(n) * cin_tot + ci) * k + ky) * k + kx];
+                float v;
+                if (g.kx_in_n) v = n < k ? w[((static_cast<size_t>(0) * cin_tot + ci) * k + ky) * k + n] : 0.f;   // column n = tap kx
+                else v = w[((static_cast<size_t>(n) * cin_tot + ci) * k + ky) * k + kx];
                 out[((ks * T + j) * g.ntot + n) * 32 + c] = __float2bfloat16(v);
               }
           }
@@ -906,6 +933,7 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, con
   p.H = g.H; p.W = g.W; p.Rt = 128 / g.W;
   p.stride = g.stride;
   p.pair = 0;
+  p.kxn = g.kx_in_n ? 1 : 0;
   p.guidance = 0.f;
   p.WR = p.Rt * pl.msub + p.T - 1;
   p.nsrc = g.nsrc;

@@ -19,6 +19,7 @@ struct ConvTcParams {
   int nstage;               // smem ring depth
   uint32_t a_bytes, stage_bytes;
   int pair;                 // EPI_EPS: 1 = the two sub-tiles are the same pixels of images 2i (cond) and 2i+1 (uncond)
+  int kxn;                  // EPI_EPS: 1 = kx taps live in accumulator columns 0..2 (ConvGeom::kx_in_n)
   float guidance;           // EPI_EPS with pair: eps = e_u + guidance (e_c - e_u)
   double gn_inv_cnt;        // EPI_GN_FUSED: 1 / (H * W * channels per group)
   int issuers;              // MMA-issuing warps: 2 = one per 128-row sub-tile (MSUB == 2), 1 otherwise

@@ -175,6 +175,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld1(uint32_t taddr, float* v) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=f"(*v) : "r"(taddr) : "memory");
 }

@@ -123,7 +123,7 @@ struct tcs_handle {
   ConvTcPlan plan_eps, plan_eps_pair;     // 96 -> 1 output conv on the tensor pipe (N padded to 16)
   DevBuf wpack_out;
   const float* d_bias16 = nullptr;
-  bool tc_out = false;
+  bool tc_out = false, eps_kxn = true;
 
   // per-call state
   DevBuf cvec, tvec, tvals, coef, x, xpred, d0, eps, step_ctr, ycat_tmp, ycont_tmp;
@@ -255,6 +255,7 @@ static int build_plans(tcs_handle* h) {
     h->tc_out = !(e && atoi(e) == 0);
     ConvGeom g = geom_of(C_U1B, h->chunk, 1);
     g.ntot = 16;
+    g.kx_in_n = h->eps_kxn ? 1 : 0;
     EpiArgs ea{};
     ea.bias = h->d_bias16; ea.out = nullptr; ea.ldo = 1;
     TCS_CHECK(conv_tc_make_plan(&h->plan_eps, g, h->p64_b.p, nullptr, h->wpack_out.as<__nv_bfloat16>(), EPI_EPS, ea, h->sm_count));
@@ -673,6 +674,11 @@ int tcs_finalize_weights(tcs_handle* h) {
   if (h->use_tc) {   // out conv as a 16-channel GEMM: row 0 = out.weight, rows 1..15 zero
     ConvGeom g = geom_of(C_U1B, 1, 1);
     g.ntot = 16;
+    {
+      const char* e = getenv("TCS_EPS_KXN");   // 0 = one window per kx tap (A/B switch)
+      h->eps_kxn = !(e && atoi(e) == 0);
+    }
+    g.kx_in_n = h->eps_kxn ? 1 : 0;
     std::vector<float> w16(16 * 96 * 9, 0.f);
     for (int k = 0; k < 96 * 9; ++k) w16[k] = wo.v[k];
     std::vector<__nv_bfloat16> pk(conv_tc_packed_elems(g));
