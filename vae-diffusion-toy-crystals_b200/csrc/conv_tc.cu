@@ -25,6 +25,12 @@
 #include <type_traits>
 #include <vector>
 
+// -DTCS_KERNEL_PROFILE=1 compiles the in-kernel clock64 phase profiler in (printed per layer with TCS_DEBUG=128);
+// the default build leaves it out so that it costs no registers
+#ifndef TCS_KERNEL_PROFILE
+#define TCS_KERNEL_PROFILE 0
+#endif
+
 namespace tcs {
 
 
@@ -307,7 +313,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     auto run = [&](auto sub_lo_c, auto sub_hi_c) {
       constexpr int SUB_LO = decltype(sub_lo_c)::value, SUB_HI = decltype(sub_hi_c)::value;
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      const bool prof = (p.debug & 128) && blockIdx.x == 0 && warp == 1;
+      const bool prof = TCS_KERNEL_PROFILE && (p.debug & 128) && blockIdx.x == 0 && warp == 1;
       long long w_empty = 0, w_full = 0, t_begin = prof ? clock64() : 0;
       int ntile = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -399,7 +405,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const int sub = (MSUB == 2) ? h : 0;
     const int col0 = (MSUB == 2) ? 0 : h * UC;   // first channel (inside the N tile) of this warp's columns
     uint32_t it = 0;
-    const bool prof = (p.debug & 128) && blockIdx.x == 0 && e == 0;
+    const bool prof = TCS_KERNEL_PROFILE && (p.debug & 128) && blockIdx.x == 0 && e == 0;
     long long pw_full = 0, p_ld = 0, p_a = 0, p_b = 0, p_c = 0, pc0 = 0, pc1 = 0, q_post = 0, q_poll = 0, q_npoll = 0, r_ss = 0, r_math = 0, r_store = 0;
     (void)p_ld; (void)r_store;
     long long tacc[3] = {0, 0, 0};
