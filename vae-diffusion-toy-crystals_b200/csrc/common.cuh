@@ -63,13 +63,12 @@ struct ConvGeom {
 struct EpiArgs {
   const float* bias;      // [ntot]
   void* out;              // see Epilogue
-  float* partials;        // EPI_RAW_STATS: [B][slots][8][2]
+  float* partials;        // EPI_RAW_STATS: [B][slots][8][2]; EPI_GN_FUSED: the (value, flag) exchange words, 16 x 8 B per M tile
   const void* residual;   // EPI_PADDED optional: padded T [B,H+2,W+2,ntot]
   int ldo;                // channel pitch of `out`
   int slots;              // partial slots per image
   const float* gamma;     // EPI_GN_FUSED: GroupNorm affine [ntot]
   const float* beta;
-  int* counters;          // EPI_GN_FUSED: per-image arrival counters [B], zeroed before the launch
 };
 
 // device buffer that only ever grows (cudaMalloc / cudaFree outside the hot loop)

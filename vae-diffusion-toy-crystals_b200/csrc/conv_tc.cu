@@ -13,8 +13,9 @@
 //   is fetched T times less often than tap-by-tap;
 // * operands sit in shared memory in the K-major SWIZZLE_64B canonical layout (one 64 B row
 //   per pixel / per output channel), accumulators in TMEM (fp32), double buffered;
-// * warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one elected lane), warps 2..5 =
-//   epilogue (tcgen05.ld -> bias / GroupNorm partial sums / halo writes);
+// * warp 0 = TMA producer, warps 1 and 18 = tcgen05.mma issuers (one elected lane each), warps 2..17 = epilogue in two
+//   groups of 8, one per TMEM accumulator set (tcgen05.ld -> bias / GroupNorm + SiLU / halo writes via TMA stores);
+// * CTA pairs (cluster of 2, cta_group::2): the weight tile is split across the two CTAs' shared memory;
 // * persistent grid: one CTA per SM looping over M tiles.
 #include "conv_tc.cuh"
 #include "tc_ptx.cuh"
@@ -55,11 +56,6 @@ struct EpiFusedSmem {          // EPI_GN_FUSED scratch (lives right after the bi
 };
 constexpr uint32_t EPI_FUSED_BYTES = sizeof(EpiFusedSmem);
 
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ void st_relaxed_gpu_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -67,9 +63,6 @@ __device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned 
   unsigned long long v;
   asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
-}
-__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
-  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void epi_bar_sync(int grp) { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(32 * GRP_WARPS) : "memory"); }
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {

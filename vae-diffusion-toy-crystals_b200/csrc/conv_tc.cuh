@@ -30,7 +30,7 @@ struct ConvTcParams {
 struct ConvTcPlan {
   CUtensorMap mapA[2];
   CUtensorMap mapW;
-  CUtensorMap mapO;   // EPI_RAW_STATS: fp32 output, TMA-stored
+  CUtensorMap mapO;   // EPI_PADDED / EPI_GN_FUSED: padded bf16 output, TMA-stored in 32-pixel x 32-channel boxes
   ConvTcParams p;
   int N;       // N tile (96 or 192)
   int epi;     // Epilogue

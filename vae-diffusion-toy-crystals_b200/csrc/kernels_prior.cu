@@ -248,9 +248,17 @@ __device__ __forceinline__ void warp_layernorm(const float* __restrict__ row, in
   }
 }
 
+__device__ __forceinline__ float4 load4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 load4(const __nv_bfloat16* p) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
 template <int NV, typename TO>
 __global__ void __launch_bounds__(256) ln_film_kernel(const float* __restrict__ h, int n, const float* __restrict__ ln_w,
-                                                     const float* __restrict__ ln_b, const float* __restrict__ film_row,
+                                                     const float* __restrict__ ln_b, const TO* __restrict__ film_row,
                                                      int film_ld, const float* __restrict__ film_step, int film_step_ld,
                                                      const int* __restrict__ step_ptr, int off, TO* __restrict__ out) {
   constexpr int W = 128 * NV;
@@ -258,14 +266,14 @@ __global__ void __launch_bounds__(256) ln_film_kernel(const float* __restrict__ 
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (r >= n) return;
   // the FiLM rows are independent of the LayerNorm result: issue their loads first so that both DRAM round trips overlap
-  const float* fr = film_row ? film_row + static_cast<size_t>(r) * film_ld + off : nullptr;
+  const TO* fr = film_row ? film_row + static_cast<size_t>(r) * film_ld + off : nullptr;
   const float* fs = film_step ? film_step + static_cast<size_t>(step_ptr ? *step_ptr : 0) * film_step_ld + off : nullptr;
   float4 g[NV], b[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = i * 128 + lane * 4;
-    g[i] = fr ? __ldg(reinterpret_cast<const float4*>(fr + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    b[i] = fr ? __ldg(reinterpret_cast<const float4*>(fr + W + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    g[i] = fr ? load4(fr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    b[i] = fr ? load4(fr + W + c) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   float4 u[NV];
   warp_layernorm<NV>(h + static_cast<size_t>(r) * W, lane, ln_w, ln_b, u);
@@ -290,7 +298,7 @@ __global__ void __launch_bounds__(256) ln_film_kernel(const float* __restrict__ 
 }
 
 template <typename TO>
-int launch_ln_film(const float* h, int n, int W, const float* ln_w, const float* ln_b, const float* film_row, int film_ld,
+int launch_ln_film(const float* h, int n, int W, const float* ln_w, const float* ln_b, const TO* film_row, int film_ld,
                    const float* film_step, int film_step_ld, const int* step_ptr, int off, TO* out, cudaStream_t st) {
   if (n < 1) return TCS_OK;
   const dim3 grid((n + 7) / 8);
@@ -309,7 +317,7 @@ int launch_ln_film(const float* h, int n, int W, const float* ln_w, const float*
 }
 template int launch_ln_film<float>(const float*, int, int, const float*, const float*, const float*, int, const float*, int,
                                    const int*, int, float*, cudaStream_t);
-template int launch_ln_film<__nv_bfloat16>(const float*, int, int, const float*, const float*, const float*, int,
+template int launch_ln_film<__nv_bfloat16>(const float*, int, int, const float*, const float*, const __nv_bfloat16*, int,
                                            const float*, int, const int*, int, __nv_bfloat16*, cudaStream_t);
 
 // ------------------------------------------------------------------------------------------------

@@ -29,9 +29,10 @@ int launch_prior_time_features(const void* t, int t_is_i32, const float* freqs, 
 
 // ---- LayerNorm + FiLM: u = LN(h) (1 + gamma) + beta  (FiLMResBlock.forward :49-52) ------------------------------
 // gamma = film_row[r][off + c] (+ film_step[step][off + c]),  beta = the same at off + W + c,  off = blk * 2W.
-// film_row may be null (all-step tables only) and film_step may be null (per-row FiLM only).
+// film_row (stored like the output: bf16 in bf16 mode, it is the dominant HBM stream of the kernel) may be null (all-step
+// tables only) and film_step (fp32) may be null (per-row FiLM only).
 template <typename TO>
-int launch_ln_film(const float* h, int n, int W, const float* ln_w, const float* ln_b, const float* film_row, int film_ld,
+int launch_ln_film(const float* h, int n, int W, const float* ln_w, const float* ln_b, const TO* film_row, int film_ld,
                    const float* film_step, int film_step_ld, const int* step_ptr, int off, TO* out, cudaStream_t st);
 
 // ---- end of a network evaluation: out_norm + out_proj (:125-126), the DDIM update (:228-250) and in_proj of the next

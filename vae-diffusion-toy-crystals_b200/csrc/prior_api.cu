@@ -251,17 +251,18 @@ static int y_chain(tcs_prior* h, const int64_t* y_cat, const float* y_cont, int 
 }
 
 // the FiLM blocks over h (fp32 [n, W]); film_row [n, B*2W] and/or film_step [S, B*2W]
-static int run_blocks(tcs_prior* h, int n, const float* film_row, const float* film_step, const int* step_ptr, cudaStream_t st) {
+static int run_blocks(tcs_prior* h, int n, const void* film_row, const float* film_step, const int* step_ptr, cudaStream_t st) {
   const int W = h->cfg.width, B = h->cfg.n_blocks, fld = B * 2 * W;
   for (int b = 0; b < B; ++b) {
     const std::string p = "blocks." + std::to_string(b) + ".";
     ++h->launches;
     if (h->bf16)
       TCS_CHECK(launch_ln_film<__nv_bfloat16>(h->h.as<float>(), n, W, h->dw.at(p + "norm.weight"), h->dw.at(p + "norm.bias"),
-                                              film_row, fld, film_step, fld, step_ptr, b * 2 * W, h->u.as<__nv_bfloat16>(), st));
+                                              static_cast<const __nv_bfloat16*>(film_row), fld, film_step, fld, step_ptr, b * 2 * W,
+                                              h->u.as<__nv_bfloat16>(), st));
     else
-      TCS_CHECK(launch_ln_film<float>(h->h.as<float>(), n, W, h->dw.at(p + "norm.weight"), h->dw.at(p + "norm.bias"), film_row,
-                                      fld, film_step, fld, step_ptr, b * 2 * W, h->u.as<float>(), st));
+      TCS_CHECK(launch_ln_film<float>(h->h.as<float>(), n, W, h->dw.at(p + "norm.weight"), h->dw.at(p + "norm.bias"),
+                                      static_cast<const float*>(film_row), fld, film_step, fld, step_ptr, b * 2 * W, h->u.as<float>(), st));
     const int of = h->bf16 ? 0 : LIN_OUT_F32;
     TCS_CHECK(dense(h, h->bf16, h->u.p, W, W, h->dw.at(p + "fc1.weight"), h->bf16 ? h->dw16.at(p + "fc1.weight") : nullptr,
                     n, 4 * W, W, h->dw.at(p + "fc1.bias"), h->a.p, 4 * W, LIN_SILU | of, st));
@@ -316,7 +317,7 @@ static int ddim_chunk(tcs_prior* h, const tcs_ddim_args& A, int row0, int n, con
   // ---- y-chain and the step-invariant half of every FiLM projection ------------------------------------------
   TCS_CHECK(y_chain(h, A.y_cat + row0, A.y_cont + static_cast<size_t>(row0) * h->cfg.y_cont_dim, n, h->yfeat.p, W, st));
   TCS_CHECK(dense(h, h->bf16, h->yfeat.p, W, 2 * W, h->cond_w + W, h->bf16 ? h->cond_w16 + W : nullptr, n, fld, W, nullptr,
-                  h->film.p, fld, LIN_OUT_F32, st));
+                  h->film.p, fld, h->bf16 ? 0 : LIN_OUT_F32, st));
   // ---- initial state ------------------------------------------------------------------------------------------
   ++h->launches;
   if (A.z_init)
@@ -327,7 +328,7 @@ static int ddim_chunk(tcs_prior* h, const tcs_ddim_args& A, int row0, int n, con
   TCS_CHECK(launch_prior_tail(tail_args(h, TAIL_INIT, n), st));
 
   auto enqueue_step = [&]() -> int {
-    TCS_CHECK(run_blocks(h, n, h->film.as<float>(), h->tcond.as<float>(), h->step_ctr.as<int>(), st));
+    TCS_CHECK(run_blocks(h, n, h->film.p, h->tcond.as<float>(), h->step_ctr.as<int>(), st));
     PriorTailArgs ta = tail_args(h, TAIL_DDIM, n);
     ta.z_out = A.z0_out + static_cast<size_t>(row0) * zd;
     // traces are [S, n_total, zd]: this chunk's rows start at row0
@@ -525,12 +526,12 @@ int tcs_prior_eps(tcs_prior* h, const float* z_t, const int64_t* t, const int64_
     TCS_CHECK(y_chain(h, y_cat + row0, y_cont + static_cast<size_t>(row0) * h->cfg.y_cont_dim, m,
                       static_cast<uint8_t*>(h->condin.p) + static_cast<size_t>(W) * esz, 2 * W, st));
     TCS_CHECK(dense(h, h->bf16, h->condin.p, 2 * W, 2 * W, h->cond_w, h->cond_w16, m, fld, 2 * W, h->cond_b, h->film.p, fld,
-                    LIN_OUT_F32, st));
+                    h->bf16 ? 0 : LIN_OUT_F32, st));
     PriorTailArgs ia = tail_args(h, TAIL_INIT, m);
     ia.z = const_cast<float*>(z_t) + static_cast<size_t>(row0) * zd;
     ++h->launches;
     TCS_CHECK(launch_prior_tail(ia, st));
-    TCS_CHECK(run_blocks(h, m, h->film.as<float>(), nullptr, nullptr, st));
+    TCS_CHECK(run_blocks(h, m, h->film.p, nullptr, nullptr, st));
     PriorTailArgs ea = tail_args(h, TAIL_EPS, m);
     ea.eps_out = eps_out + static_cast<size_t>(row0) * zd;
     ++h->launches;
@@ -597,7 +598,7 @@ int tcs_prior_profile(tcs_prior* h, int32_t n, int32_t reps, float* ms) {
   auto lnf = [&]() {
     if (h->bf16)
       return launch_ln_film<__nv_bfloat16>(h->h.as<float>(), n, W, h->dw.at(p + "norm.weight"), h->dw.at(p + "norm.bias"),
-                                           h->film.as<float>(), fld, h->tcond.as<float>(), fld, h->step_ctr.as<int>(), 0,
+                                           h->film.as<__nv_bfloat16>(), fld, h->tcond.as<float>(), fld, h->step_ctr.as<int>(), 0,
                                            h->u.as<__nv_bfloat16>(), st);
     return launch_ln_film<float>(h->h.as<float>(), n, W, h->dw.at(p + "norm.weight"), h->dw.at(p + "norm.bias"),
                                  h->film.as<float>(), fld, h->tcond.as<float>(), fld, h->step_ctr.as<int>(), 0, h->u.as<float>(), st);

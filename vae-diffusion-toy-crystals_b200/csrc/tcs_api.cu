@@ -115,7 +115,7 @@ struct tcs_handle {
 
   // workspace (sized for `chunk` images)
   int chunk = 0;
-  DevBuf raw64, raw32, raw16, partials, gnstats, counters;
+  DevBuf raw64, raw32, raw16, partials, gnstats;
   DevBuf p64_h1, p64_a, p64_b;
   DevBuf p32_96a, p32_96b, p32_192a, p32_192h2, p32_192b;
   DevBuf p16_a, p16_b, p16_c, qkv, atty;
@@ -202,7 +202,6 @@ static int alloc_workspace(tcs_handle* h) {
   TCS_CHECK(h->raw16.ensure(MB * 256 * 192 * 4));
   TCS_CHECK(h->partials.ensure(MB * 128 * 16 * 4));
   TCS_CHECK(h->gnstats.ensure(MB * 8 * 8));
-  TCS_CHECK(h->counters.ensure(MB * 4));
   const size_t P64 = MB * 66 * 66 * 96 * e, P32a = MB * 34 * 34 * 96 * e, P32b = MB * 34 * 34 * 192 * e,
                P16 = MB * 18 * 18 * 192 * e;
   TCS_CHECK(h->p64_h1.ensure(P64)); TCS_CHECK(h->p64_a.ensure(P64)); TCS_CHECK(h->p64_b.ensure(P64));
@@ -272,7 +271,6 @@ static int build_plans(tcs_handle* h) {
     if (w.epi == EPI_GN_FUSED) {
       ea.gamma = h->dw.at(std::string(w.gn) + ".weight");
       ea.beta = h->dw.at(std::string(w.gn) + ".bias");
-      ea.counters = h->counters.as<int>();
     }
     TCS_CHECK(conv_tc_make_plan(&h->plan[id], g, w.s0, w.s1, h->wpack[id].as<__nv_bfloat16>(), w.epi, ea, h->sm_count));
   }
