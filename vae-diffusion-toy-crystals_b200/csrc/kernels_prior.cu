@@ -274,18 +274,18 @@ __global__ void __launch_bounds__(256) ln_film_kernel(const float* __restrict__ 
     const int c = i * 128 + lane * 4;
     g[i] = fr ? load4(fr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     b[i] = fr ? load4(fr + W + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  float4 u[NV];
-  warp_layernorm<NV>(h + static_cast<size_t>(r) * W, lane, ln_w, ln_b, u);
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int c = i * 128 + lane * 4;
     if (fs) {
       const float4 g2 = __ldg(reinterpret_cast<const float4*>(fs + c));
       const float4 b2 = __ldg(reinterpret_cast<const float4*>(fs + W + c));
       g[i].x += g2.x; g[i].y += g2.y; g[i].z += g2.z; g[i].w += g2.w;
       b[i].x += b2.x; b[i].y += b2.y; b[i].z += b2.z; b[i].w += b2.w;
     }
+  }
+  float4 u[NV];
+  warp_layernorm<NV>(h + static_cast<size_t>(r) * W, lane, ln_w, ln_b, u);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = i * 128 + lane * 4;
     const float o0 = u[i].x * (1.0f + g[i].x) + b[i].x, o1 = u[i].y * (1.0f + g[i].y) + b[i].y;
     const float o2 = u[i].z * (1.0f + g[i].z) + b[i].z, o3 = u[i].w * (1.0f + g[i].w) + b[i].w;
     if constexpr (sizeof(TO) == 4) {
