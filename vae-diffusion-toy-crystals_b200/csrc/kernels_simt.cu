@@ -129,7 +129,7 @@ template <> __device__ __forceinline__ void store_pair<__nv_bfloat16>(__nv_bfloa
 // sum_p conv_c(p)^2 = sum_{k,l} w_ck w_cl R(k-l)  with  R(d) = sum_p x_p x_{p+d}  (circular autocorrelation at
 // the 25 lags |dy|,|dx| <= 2), both exact identities; R and the quadratic forms are evaluated in fp64.
 // Each sample is split over FC_SPLIT blocks (row bands); every block recomputes the (cheap) statistics.
-constexpr int FC_SPLIT = 4;
+constexpr int FC_SPLIT = 2;
 template <typename T>
 __global__ void __launch_bounds__(384, 2) first_conv_gn_kernel(const float* __restrict__ x, const float* __restrict__ w9,
                                                            const float* __restrict__ tvec, int tvec_stride,
