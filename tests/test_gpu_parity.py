@@ -389,3 +389,25 @@ def test_training_hook_accepts_a_foreign_module(tmp_path):
     a = shim.predict_eps_cfg(f, x, t, y_cat, y_cont, 1.5)
     b = shim.predict_eps_cfg(P.model("bf16", seed=1), x, t, y_cat, y_cont, 1.5)
     assert torch.equal(a, b)
+
+
+def test_output_conv_variants_agree(monkeypatch):
+    """The 96 -> 1 output conv with the kx taps as GEMM columns (default) against the one-window-per-tap variant
+    (TCS_EPS_KXN=0): same bf16 operands, fp32 accumulation in a different order."""
+    import toycrystals_oracle as orc
+    from toycrystals_b200.models import sde_score_model as shim
+    sd = orc.default_init_state_dict(1)
+    y_cat, y_cont = (t.cuda() for t in orc.condition_grid(5, 4, 4))
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn((5, 1, 64, 64), generator=g).cuda()
+    t = torch.full((5,), 0.3).cuda()
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("TCS_EPS_KXN", flag)
+        m = shim.CondUNetTiny(**orc.DEFAULT_CFG, precision="bf16")
+        m.load_state_dict(sd)
+        m = m.to("cuda").eval()
+        outs.append((shim.predict_eps_cfg(m, x, t, y_cat, y_cont, 1.5), shim.predict_eps_cfg(m, x, t, y_cat, y_cont, 0.0)))
+        del m
+    for a, b in zip(outs[0], outs[1]):
+        assert orc.rel_l2(a, b) < 1e-5

@@ -251,3 +251,25 @@ def test_sample_images_end_to_end():
     assert x.shape == (G["n"], 1, 64, 64) and float(x.min()) >= 0.0 and float(x.max()) <= 1.0
     assert float(((x.cpu() - G["x"]).abs() > 1e-3).float().mean()) < 2e-2
     assert m.launch_count() > 0 and vae().launch_count() > 0
+
+
+def test_ddim_jobs_larger_than_one_chunk():
+    """tcs_prior_ddim_sample runs jobs above 16384 samples in chunks: rows on both sides of the boundary must equal the
+    same rows sampled on their own (conditions, Philox offsets, output and trace offsets per chunk)."""
+    m, _, _ = prior("bf16")
+    s = sched_gpu()
+    n = 16384 + 70
+    y_cat, y_cont = (t.cuda() for t in orc.condition_grid(n, 4, 4))
+    z0, tr = s.ddim_sample(m, y_cat, y_cont, n_steps=3, seed=5, return_trace=True)
+    lo, hi = 16384 - 40, 16384 + 70
+    sub, trs = s.ddim_sample(m, y_cat[lo:hi], y_cont[lo:hi], n_steps=3, seed=5, global_index_offset=lo, return_trace=True)
+    assert torch.equal(sub, z0[lo:hi])
+    assert torch.equal(trs.eps, tr.eps[:, lo:hi]) and torch.equal(trs.z_in, tr.z_in[:, lo:hi])
+    assert bool(torch.isfinite(z0).all())
+    # forward (per-sample timesteps) across the same boundary
+    g = torch.Generator().manual_seed(3)
+    z = torch.randn((n, 32), generator=g).cuda()
+    t = torch.randint(0, 1000, (n,), generator=g).cuda()
+    e = m(z, t, y_cat, y_cont)
+    e_sub = m(z[lo:hi], t[lo:hi], y_cat[lo:hi], y_cont[lo:hi])
+    assert torch.equal(e_sub, e[lo:hi])
