@@ -44,6 +44,9 @@ template <typename T>
 int launch_gn_apply(const void* in, int in_padded, const float* partials, int slots, const float* gamma,
                     const float* beta, int B, int H, int W, int C, int silu, T* out_padded, float2* stats_scratch /*[B][8]*/,
                     cudaStream_t st);
+// GroupNorm (no activation) of padded 16x16x192 images in one kernel: padded T -> padded T (attn.norm)
+template <typename T>
+int launch_gn_image16(const T* in_padded, int B, const float* gamma, const float* beta, T* out_padded, cudaStream_t st);
 // statistics of a padded T tensor -> partials [B][1][8][2]
 template <typename T>
 int launch_gn_stats(const T* in_padded, int B, int H, int W, int C, float* partials, cudaStream_t st);

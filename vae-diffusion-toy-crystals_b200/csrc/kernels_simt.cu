@@ -412,6 +412,97 @@ int launch_gn_apply(const void* in, int in_padded, const float* partials, int sl
 template int launch_gn_apply<float>(const void*, int, const float*, int, const float*, const float*, int, int, int, int, int, float*, float2*, cudaStream_t);
 template int launch_gn_apply<__nv_bfloat16>(const void*, int, const float*, int, const float*, const float*, int, int, int, int, int, __nv_bfloat16*, float2*, cudaStream_t);
 
+// GroupNorm of a whole 16x16x192 padded image in ONE kernel (attn.norm, sde_score_model.py:146-150): block = image,
+// thread = (channel vector of 8, pixel lane); the image (96 KB in bf16) stays in registers between the statistics and
+// the normalisation, so the three launches gn_stats -> gn_finalize -> gn_apply (and two re-reads) become one.
+constexpr int GNI_LANES = 10;                      // pixel lanes: 24 channel vectors x 10 = 240 of 256 threads
+constexpr int GNI_ITERS = (256 + GNI_LANES - 1) / GNI_LANES;
+template <typename T>
+__global__ void __launch_bounds__(256) gn_image16_kernel(const T* __restrict__ in, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, T* __restrict__ out) {
+  constexpr int H = 16, W = 16, C = 192, CV = C / 8, Hp = H + 2, Wp = W + 2, CPG = C / GN_GROUPS;
+  __shared__ float red[8][GN_GROUPS][2];
+  __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
+  const int b = blockIdx.x, t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int vc = t % CV, pl = t / CV;                // channel vector, pixel lane
+  const bool active = pl < GNI_LANES;
+  const int c = vc * 8, g = c / CPG;                 // 8 | 24: a vector never straddles a group
+  const T* ib = in + static_cast<size_t>(b) * Hp * Wp * C + c;
+  Vec8<T> v[GNI_ITERS];
+  float s = 0.f, q = 0.f;
+#pragma unroll
+  for (int k = 0; k < GNI_ITERS; ++k) {
+    const int pix = pl + k * GNI_LANES;
+    if (active && pix < H * W) {
+      const int y = pix / W, x = pix - y * W;
+      v[k].load(ib + (static_cast<size_t>(y + 1) * Wp + x + 1) * C);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < GNI_ITERS; ++k) {
+    const int pix = pl + k * GNI_LANES;
+    if (active && pix < H * W) {
+      float f[8];
+      v[k].get(f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s += f[j]; q += f[j] * f[j]; }
+    }
+  }
+  // block reduction per group: lanes of a warp may belong to different groups -> shared-memory atomics on 16 floats
+  if (t < 8 * GN_GROUPS * 2) reinterpret_cast<float*>(red)[t] = 0.f;
+  __syncthreads();
+  if (active) {
+    atomicAdd(&red[warp][g][0], s);
+    atomicAdd(&red[warp][g][1], q);
+  }
+  __syncthreads();
+  if (t < GN_GROUPS) {
+    double sd = 0.0, qd = 0.0;
+    for (int w = 0; w < 8; ++w) { sd += red[w][t][0]; qd += red[w][t][1]; }
+    const double inv = 1.0 / (static_cast<double>(H) * W * CPG);
+    const double mean = sd * inv;
+    double var = qd * inv - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    s_mean[t] = static_cast<float>(mean);
+    s_rstd[t] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(GN_EPS)));
+  }
+  __syncthreads();
+  (void)lane;
+  if (!active) return;
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+  const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+  const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  const float mean = s_mean[g], rstd = s_rstd[g];
+#pragma unroll
+  for (int k = 0; k < GNI_ITERS; ++k) {
+    const int pix = pl + k * GNI_LANES;
+    if (pix >= H * W) continue;
+    const int y = pix / W, x = pix - y * W;
+    float f[8];
+    v[k].get(f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = (f[j] - mean) * rstd * gm[j] + bt[j];
+    Vec8<T> ov;
+    ov.set(f);
+    const int wy = halo_wrap(y, H), wx = halo_wrap(x, W);
+    const size_t base = (static_cast<size_t>(b) * Hp + y + 1) * Wp + x + 1;
+    ov.store(out + base * C + c);
+    if (wy) ov.store(out + (base + static_cast<long long>(wy) * Wp) * C + c);
+    if (wx) ov.store(out + (base + wx) * C + c);
+    if (wy && wx) ov.store(out + (base + static_cast<long long>(wy) * Wp + wx) * C + c);
+  }
+}
+template <typename T>
+int launch_gn_image16(const T* in, int B, const float* gamma, const float* beta, T* out, cudaStream_t st) {
+  if (B <= 0) return TCS_OK;
+  gn_image16_kernel<T><<<B, 256, 0, st>>>(in, gamma, beta, out);
+  TCS_CUDA(cudaGetLastError());
+  return TCS_OK;
+}
+template int launch_gn_image16<float>(const float*, int, const float*, const float*, float*, cudaStream_t);
+template int launch_gn_image16<__nv_bfloat16>(const __nv_bfloat16*, int, const float*, const float*, __nv_bfloat16*, cudaStream_t);
+
 // statistics of a padded T tensor (one block per image; thread = channel) -> one partial slot
 template <typename T>
 __global__ void __launch_bounds__(192) gn_stats_kernel(const T* __restrict__ in, int H, int W, int C,

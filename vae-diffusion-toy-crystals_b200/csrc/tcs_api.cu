@@ -384,11 +384,8 @@ static int forward_chunk(tcs_handle* h, const PassArgs& a, cudaStream_t st, TapR
   // ---- mid + attention ---------------------------------------------------------------------
   CONV_GN(C_MA, h->raw16.p, 16, 192);
   CONV_GN(C_MB, h->raw16.p, 16, 192);   // -> p16_a = x_in of the attention block
-  ++h->launches;
-  TCS_CHECK(launch_gn_stats<T>(h->p16_a.as<T>(), B, 16, 16, 192, part, st));
-  h->launches += 2;
-  TCS_CHECK(launch_gn_apply<T>(h->p16_a.p, 1, part, 1, gnw("attn.norm"), gnb("attn.norm"), B, 16, 16, 192, 0,
-                               h->p16_b.as<T>(), h->gnstats.as<float2>(), st));
+  ++h->launches;   // attn.norm: statistics + normalisation of the 16x16x192 image in one kernel
+  TCS_CHECK(launch_gn_image16<T>(h->p16_a.as<T>(), B, gnw("attn.norm"), gnb("attn.norm"), h->p16_b.as<T>(), st));
   TCS_CHECK(run_conv<T>(h, C_QKV, B, st));
   TAP(2, h->qkv.p, 16, 16, 576);
   ++h->launches;
