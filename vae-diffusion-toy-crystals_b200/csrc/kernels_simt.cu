@@ -798,12 +798,18 @@ __device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-__global__ void __launch_bounds__(256) attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv,
+// MT = 16-row query tiles per warp.  MT = 1 (a block = one HALF of the queries of an (image, head), grid doubled) keeps the
+// kernel near 100 registers so that two blocks share an SM and hide each other's latencies; MT = 2 was 178 registers, 1 block.
+constexpr int ATT_MT = 1;
+__global__ void __launch_bounds__(256, 2) attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                            __nv_bfloat16* __restrict__ yout) {
   extern __shared__ __align__(16) uint8_t att_raw[];
   __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(att_raw);
   __nv_bfloat16* Vs = Ks + ATT_TOK * ATT_STRIDE;
-  const int b = blockIdx.x >> 2, head = blockIdx.x & 3;
+  constexpr int MT = ATT_MT, QPB = 8 * 16 * MT;          // queries per block
+  constexpr int BPH = ATT_TOK / QPB;                      // blocks per (image, head)
+  const int bh = blockIdx.x / BPH, qpart = blockIdx.x - bh * BPH;
+  const int b = bh >> 2, head = bh & 3;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
   const __nv_bfloat16* base = qkv + static_cast<size_t>(b) * ATT_TOK * (3 * ATT_C) + head * ATT_D;
   for (int e = tid; e < ATT_TOK * 6; e += 256) {
@@ -814,10 +820,10 @@ __global__ void __launch_bounds__(256) attention_mma_kernel(const __nv_bfloat16*
     *reinterpret_cast<uint4*>(Vs + tok * ATT_STRIDE + ch * 8) = vv;
   }
   // Q fragments: 2 m-tiles x 3 k-steps, straight from global memory
-  uint32_t qf[2][3][4];
-  const int row0 = warp * 32;
+  uint32_t qf[MT][3][4];
+  const int row0 = qpart * QPB + warp * 16 * MT;
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
     for (int ks = 0; ks < 3; ++ks) {
       const __nv_bfloat16* q0 = base + static_cast<size_t>(row0 + mt * 16 + g) * (3 * ATT_C) + ks * 16 + 2 * t4;
@@ -831,10 +837,10 @@ __global__ void __launch_bounds__(256) attention_mma_kernel(const __nv_bfloat16*
   const uint32_t ks_addr = static_cast<uint32_t>(__cvta_generic_to_shared(Ks));
   const uint32_t vs_addr = static_cast<uint32_t>(__cvta_generic_to_shared(Vs));
   const float c = 0.14433756729740643f * 1.4426950408889634f;  // (1/sqrt(48)) * log2(e)
-  float o[2][6][4];
-  float mrow[2][2], lrow[2][2];
+  float o[MT][6][4];
+  float mrow[MT][2], lrow[MT][2];
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt) {
+  for (int mt = 0; mt < MT; ++mt) {
     mrow[mt][0] = mrow[mt][1] = -INFINITY;
     lrow[mt][0] = lrow[mt][1] = 0.f;
 #pragma unroll
@@ -843,9 +849,9 @@ __global__ void __launch_bounds__(256) attention_mma_kernel(const __nv_bfloat16*
       for (int k = 0; k < 4; ++k) o[mt][nt][k] = 0.f;
   }
   for (int kc = 0; kc < ATT_TOK; kc += 64) {
-    float sacc[2][8][4];
+    float sacc[MT][8][4];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
@@ -858,14 +864,14 @@ __global__ void __launch_bounds__(256) attention_mma_kernel(const __nv_bfloat16*
       ldsm_x4(rowaddr + (lane >> 3) * 16, kb);             // d chunks 0..3 -> (b0,b1) of k-steps 0,1
       ldsm_x2(rowaddr + (4 + ((lane >> 3) & 1)) * 16, kb + 4);  // d chunks 4,5 -> k-step 2
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
+      for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int ks = 0; ks < 3; ++ks) mma_bf16_16816(sacc[mt][nt], qf[mt][ks], kb[2 * ks], kb[2 * ks + 1]);
     }
     // ---- online softmax (base 2) --------------------------------------------------------------------
-    uint32_t pf[2][4][4];
+    uint32_t pf[MT][4][4];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
+    for (int mt = 0; mt < MT; ++mt) {
       float mx0 = mrow[mt][0], mx1 = mrow[mt][1];
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
@@ -903,7 +909,7 @@ __global__ void __launch_bounds__(256) attention_mma_kernel(const __nv_bfloat16*
         const int key = kc + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
         ldsm_x4_trans(vs_addr + static_cast<uint32_t>(key * ATT_STRIDE * 2 + (np * 2 + (lane >> 4)) * 16), vb);
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
+        for (int mt = 0; mt < MT; ++mt) {
           mma_bf16_16816(o[mt][np * 2], pf[mt][kk], vb[0], vb[1]);
           mma_bf16_16816(o[mt][np * 2 + 1], pf[mt][kk], vb[2], vb[3]);
         }
@@ -911,7 +917,7 @@ __global__ void __launch_bounds__(256) attention_mma_kernel(const __nv_bfloat16*
     }
   }
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt) {
+  for (int mt = 0; mt < MT; ++mt) {
     float l0 = lrow[mt][0], l1 = lrow[mt][1];
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
@@ -934,7 +940,7 @@ int launch_attention_mma(const __nv_bfloat16* qkv, int B, __nv_bfloat16* y, cuda
     TCS_CUDA(cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     done = true;
   }
-  attention_mma_kernel<<<B * N_HEADS, 256, smem, st>>>(qkv, y);
+  attention_mma_kernel<<<B * N_HEADS * (ATT_TOK / (128 * ATT_MT)), 256, smem, st>>>(qkv, y);
   TCS_CUDA(cudaGetLastError());
   return TCS_OK;
 }
