@@ -65,6 +65,15 @@ __device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned 
   return v;
 }
 __device__ __forceinline__ void epi_bar_sync(int grp) { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(32 * GRP_WARPS) : "memory"); }
+// fp16 pair (a in the low half), saturating to the largest finite value
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t v) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&v));
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
@@ -91,9 +100,13 @@ __device__ __forceinline__ void add2(float& d0, float& d1, float a0, float a1, f
       : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
 __device__ __forceinline__ float tanh_fast(float x) {
+#ifdef TCS_NO_TANH
+  return x * 0.25f;   // timing experiment only: no MUFU in the fused epilogue
+#else
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x));
   return t;
+#endif
 }
 __device__ __forceinline__ void st_shared_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -476,32 +489,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int G = p.tiles_per_img;
         const int img = mt / G;
         float rv[2 * NGL];                     // (sum, sum of squares) per local group
+        // Pass 1 reads the accumulator ONCE: statistics in fp32, and the biased values are kept in registers as packed
+        // fp16 pairs (48 registers; fp16 keeps 3 more mantissa bits than the bf16 output, satfinite) so that the TMEM set
+        // goes back to the MMA warps before the cross-CTA exchange instead of after the second pass (the accumulator
+        // hold time was the bound of the K = 864 layers: ~10k cycles against ~6k of MMA work per tile).
+        uint32_t stash[UC / 2];
         {
-          float gs[NGL], gq[NGL], gs1[NGL], gq1[NGL];   // even / odd column partial sums kept packed
+          float gs[NGL], gq[NGL];
 #pragma unroll
-          for (int g = 0; g < NGL; ++g) gs[g] = gq[g] = gs1[g] = gq1[g] = 0.f;
-          float vbuf[2][32];
-          ptx::tmem_ld32(taddr, vbuf[0]);
+          for (int g = 0; g < NGL; ++g) gs[g] = gq[g] = 0.f;
 #pragma unroll
-          for (int k = 0; k < 3; ++k) {
+          for (int k = 0; k < UC / 16; ++k) {
+            float v[16];
+            ptx::tmem_ld16(taddr + k * 16, v);
             ptx::tmem_ld_wait();
-            if (k < 2) ptx::tmem_ld32(taddr + (k + 1) * 32, vbuf[(k + 1) & 1]);
-            const float* v = vbuf[k & 1];
+            if (k == UC / 16 - 1) release_tmem();
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + col0 + k * 32 + i);
+            for (int i = 0; i < 16; i += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + col0 + k * 16 + i);
               float t0, t1, t2, t3;
               add2(t0, t1, v[i], v[i + 1], b4.x, b4.y);
               add2(t2, t3, v[i + 2], v[i + 3], b4.z, b4.w);
-              const int g0 = (k * 32 + i) / CPGN, g1 = (k * 32 + i + 2) / CPGN;   // pairs never straddle a group
-              add2(gs[g0], gs1[g0], gs[g0], gs1[g0], t0, t1);
-              fma2(gq[g0], gq1[g0], t0, t1, t0, t1, gq[g0], gq1[g0]);
-              add2(gs[g1], gs1[g1], gs[g1], gs1[g1], t2, t3);
-              fma2(gq[g1], gq1[g1], t2, t3, t2, t3, gq[g1], gq1[g1]);
+              const int g0 = (k * 16 + i) / CPGN, g1 = (k * 16 + i + 2) / CPGN;   // pairs never straddle a group
+              gs[g0] += t0; gq[g0] = fmaf(t0, t0, gq[g0]);
+              gs[g0] += t1; gq[g0] = fmaf(t1, t1, gq[g0]);
+              gs[g1] += t2; gq[g1] = fmaf(t2, t2, gq[g1]);
+              gs[g1] += t3; gq[g1] = fmaf(t3, t3, gq[g1]);
+              stash[(k * 16 + i) / 2] = pack_f16x2_sat(t0, t1);
+              stash[(k * 16 + i) / 2 + 1] = pack_f16x2_sat(t2, t3);
             }
           }
 #pragma unroll
-          for (int g = 0; g < NGL; ++g) { rv[2 * g] = gs[g] + gs1[g]; rv[2 * g + 1] = gq[g] + gq1[g]; }
+          for (int g = 0; g < NGL; ++g) { rv[2 * g] = gs[g]; rv[2 * g + 1] = gq[g]; }
         }
         // lane reduction: a reduce-scatter over the top lane bits (2*NGL values -> 1 per lane), butterflies for the rest
         constexpr int NV = 2 * NGL;            // 8 or 16
@@ -576,17 +595,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             gsm->mean[lane >> 1] = static_cast<float>(mean);
             gsm->rstd[lane >> 1] = rsqrtf(static_cast<float>(var) + GN_EPS);
           }
+          __syncwarp();
+          for (int c = lane; c < N; c += 32) {      // per-channel affine table, by the same warp (saves a group barrier)
+            const int g = c / CPGN;
+            const float sc = gsm->rstd[g] * fs->gamma[c];
+            gsm->scale[c] = 0.5f * sc;                                                  // h = y / 2 = v * scale + shift
+            gsm->shift[c] = 0.5f * (fs->beta[c] - gsm->mean[g] * sc);                   // the bias is inside the stashed values
+          }
         }
         epi_bar_sync(grp);
         if (prof) { pc1 = clock64(); p_b += pc1 - pc0; pc0 = pc1; }
-        for (int c = threadIdx.x - 64 - grp * (32 * GRP_WARPS); c < N; c += 32 * GRP_WARPS) {
-          const int g = c / CPGN;
-          const float sc = gsm->rstd[g] * fs->gamma[c];
-          gsm->scale[c] = 0.5f * sc;                                                  // h = y / 2 = v * scale + shift
-          gsm->shift[c] = 0.5f * ((bias_s[c] - gsm->mean[g]) * sc + fs->beta[c]);
-        }
-        epi_bar_sync(grp);
-        if (prof) { pc1 = clock64(); r_ss += pc1 - pc0; }
         __nv_bfloat16* obase = static_cast<__nv_bfloat16*>(p.epi.out);
         const int m = (mt * MSUB + sub) * 128 + row;
         const int rem = m - img * HW;
@@ -594,34 +612,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int wy = (y == 0) ? p.H : ((y == p.H - 1) ? -p.H : 0);
         const int wx = (x == 0) ? p.W : ((x == p.W - 1) ? -p.W : 0);
         const size_t pix = (static_cast<size_t>(img) * Hp + (y + 1)) * Wp + (x + 1);
-        {
-          float vbuf[2][32];
-          ptx::tmem_ld32(taddr, vbuf[0]);
 #pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            ptx::tmem_ld_wait();
-            if (k < 2) ptx::tmem_ld32(taddr + (k + 1) * 32, vbuf[(k + 1) & 1]);
-            else release_tmem();   // the accumulator set is free as soon as its last column block is in registers
-            const float* v = vbuf[k & 1];
-            const int cc = col0 + k * 32;
-            uint32_t pk[16];
+        for (int k = 0; k < 3; ++k) {
+          const int cc = col0 + k * 32;
+          uint32_t pk[16];
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 s4 = *reinterpret_cast<const float4*>(gsm->scale + cc + i);
-              const float4 h4 = *reinterpret_cast<const float4*>(gsm->shift + cc + i);
-              float h0, h1, h2, h3, y0, y1, y2, y3;
-              fma2(h0, h1, v[i], v[i + 1], s4.x, s4.y, h4.x, h4.y);          // h = y/2
-              fma2(h2, h3, v[i + 2], v[i + 3], s4.z, s4.w, h4.z, h4.w);
-              fma2(y0, y1, h0, h1, tanh_fast(h0), tanh_fast(h1), h0, h1);    // SiLU(y) = h + h tanh(h)
-              fma2(y2, y3, h2, h3, tanh_fast(h2), tanh_fast(h3), h2, h3);
-              pk[i / 2] = pack_bf16x2(y0, y1);
-              pk[i / 2 + 1] = pack_bf16x2(y2, y3);
-            }
-            if (!(p.debug & 2))
-              store_padded_block(&mapO, use_tma_out, slab, slab_buf, lane, obase, pix, wy, wx, Wp, p.epi.ldo, cc, img, y, x, pk,
-                                 prof ? tacc : nullptr);
-            else if (pk[0] == 0x12345678u && pk[7] == 0x9abcdef0u) obase[0] = __float2bfloat16(0.f);
+          for (int i = 0; i < 32; i += 4) {
+            const float4 s4 = *reinterpret_cast<const float4*>(gsm->scale + cc + i);
+            const float4 h4 = *reinterpret_cast<const float4*>(gsm->shift + cc + i);
+            const float2 va = unpack_f16x2(stash[(k * 32 + i) / 2]), vb = unpack_f16x2(stash[(k * 32 + i) / 2 + 1]);
+            float h0, h1, h2, h3, y0, y1, y2, y3;
+            fma2(h0, h1, va.x, va.y, s4.x, s4.y, h4.x, h4.y);              // h = y/2
+            fma2(h2, h3, vb.x, vb.y, s4.z, s4.w, h4.z, h4.w);
+            fma2(y0, y1, h0, h1, tanh_fast(h0), tanh_fast(h1), h0, h1);    // SiLU(y) = h + h tanh(h)
+            fma2(y2, y3, h2, h3, tanh_fast(h2), tanh_fast(h3), h2, h3);
+            pk[i / 2] = pack_bf16x2(y0, y1);
+            pk[i / 2 + 1] = pack_bf16x2(y2, y3);
           }
+          if (!(p.debug & 2))
+            store_padded_block(&mapO, use_tma_out, slab, slab_buf, lane, obase, pix, wy, wx, Wp, p.epi.ldo, cc, img, y, x, pk,
+                               prof ? tacc : nullptr);
+          else if (pk[0] == 0x12345678u && pk[7] == 0x9abcdef0u) obase[0] = __float2bfloat16(0.f);
         }
         if (prof) r_math += clock64() - pc1;
       } else if constexpr (N >= 96) {
