@@ -111,6 +111,9 @@ __device__ __forceinline__ float tanh_fast(float x) {
 __device__ __forceinline__ void st_shared_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+__device__ __forceinline__ void ld_shared_u4(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
+}
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
@@ -489,34 +492,58 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int G = p.tiles_per_img;
         const int img = mt / G;
         float rv[2 * NGL];                     // (sum, sum of squares) per local group
-        // Pass 1 reads the accumulator ONCE: statistics in fp32, and the biased values are kept in registers as packed
-        // fp16 pairs (48 registers; fp16 keeps 3 more mantissa bits than the bf16 output, satfinite) so that the TMEM set
-        // goes back to the MMA warps before the cross-CTA exchange instead of after the second pass (the accumulator
-        // hold time was the bound of the K = 864 layers: ~10k cycles against ~6k of MMA work per tile).
-        uint32_t stash[UC / 2];
+        // Pass 1 reads the accumulator ONCE (32 columns at a time, next tcgen05.ld in flight): statistics in fp32, and the
+        // biased values are kept as fp16 (3 more mantissa bits than the bf16 output, satfinite): column blocks 0 and 1 in
+        // this warp's two output staging blocks (same [32 px][64 B] swizzled rows as the bf16 output that replaces them in
+        // place in pass 2; a lane only ever touches its own row), block 2 in 16 registers.  The TMEM set therefore goes
+        // back to the MMA warps BEFORE the cross-CTA exchange (the accumulator hold time was the bound of the K = 864
+        // layers: ~10k cycles against ~6k of MMA work per tile).
+        uint32_t stash2[BLK / 2];
+        const uint32_t srow = slab + lane * 64;        // this lane's row inside a staging block
+        const int ssw = (lane >> 1) & 3;
+        const uint32_t sb0 = slab_buf;                 // staging block that pass 2 fills first
+        if (use_tma_out) {                             // the previous tile's TMA stores have left the staging blocks
+          const long long cl0 = prof ? clock64() : 0;
+          if (lane == 0) ptx::bulk_wait_read<0>();
+          __syncwarp();
+          if (prof) p_ld += clock64() - cl0;
+        }
         {
           float gs[NGL], gq[NGL];
 #pragma unroll
           for (int g = 0; g < NGL; ++g) gs[g] = gq[g] = 0.f;
+          float vbuf[2][32];
+          ptx::tmem_ld32(taddr, vbuf[0]);
 #pragma unroll
-          for (int k = 0; k < UC / 16; ++k) {
-            float v[16];
-            ptx::tmem_ld16(taddr + k * 16, v);
+          for (int k = 0; k < 3; ++k) {
             ptx::tmem_ld_wait();
-            if (k == UC / 16 - 1) release_tmem();
+            if (k < 2) ptx::tmem_ld32(taddr + (k + 1) * 32, vbuf[(k + 1) & 1]);
+            else release_tmem();
+            const float* v = vbuf[k & 1];
+            const uint32_t sblk = srow + ((sb0 ^ (k & 1)) * 2048);
 #pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + col0 + k * 16 + i);
-              float t0, t1, t2, t3;
-              add2(t0, t1, v[i], v[i + 1], b4.x, b4.y);
-              add2(t2, t3, v[i + 2], v[i + 3], b4.z, b4.w);
-              const int g0 = (k * 16 + i) / CPGN, g1 = (k * 16 + i + 2) / CPGN;   // pairs never straddle a group
-              gs[g0] += t0; gq[g0] = fmaf(t0, t0, gq[g0]);
-              gs[g0] += t1; gq[g0] = fmaf(t1, t1, gq[g0]);
-              gs[g1] += t2; gq[g1] = fmaf(t2, t2, gq[g1]);
-              gs[g1] += t3; gq[g1] = fmaf(t3, t3, gq[g1]);
-              stash[(k * 16 + i) / 2] = pack_f16x2_sat(t0, t1);
-              stash[(k * 16 + i) / 2 + 1] = pack_f16x2_sat(t2, t3);
+            for (int i = 0; i < 32; i += 8) {
+              uint32_t hw[4];
+#pragma unroll
+              for (int u = 0; u < 8; u += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bias_s + col0 + k * 32 + i + u);
+                float t0, t1, t2, t3;
+                add2(t0, t1, v[i + u], v[i + u + 1], b4.x, b4.y);
+                add2(t2, t3, v[i + u + 2], v[i + u + 3], b4.z, b4.w);
+                const int g0 = (k * 32 + i + u) / CPGN, g1 = (k * 32 + i + u + 2) / CPGN;   // pairs never straddle a group
+                gs[g0] += t0; gq[g0] = fmaf(t0, t0, gq[g0]);
+                gs[g0] += t1; gq[g0] = fmaf(t1, t1, gq[g0]);
+                gs[g1] += t2; gq[g1] = fmaf(t2, t2, gq[g1]);
+                gs[g1] += t3; gq[g1] = fmaf(t3, t3, gq[g1]);
+                hw[u / 2] = pack_f16x2_sat(t0, t1);
+                hw[u / 2 + 1] = pack_f16x2_sat(t2, t3);
+              }
+              if (k < 2) {
+                st_shared_u4(sblk + (((i / 8) ^ ssw) << 4), hw[0], hw[1], hw[2], hw[3]);
+              } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) stash2[i / 2 + u] = hw[u];
+              }
             }
           }
 #pragma unroll
@@ -615,12 +642,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           const int cc = col0 + k * 32;
+          uint32_t hv[16];
+          if (k < 2) {
+            const uint32_t sblk = srow + ((sb0 ^ k) * 2048);   // = the block store_padded_block fills next (in place)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ld_shared_u4(sblk + ((j ^ ssw) << 4), hv[4 * j], hv[4 * j + 1], hv[4 * j + 2], hv[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) hv[j] = stash2[j];
+          }
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             const float4 s4 = *reinterpret_cast<const float4*>(gsm->scale + cc + i);
             const float4 h4 = *reinterpret_cast<const float4*>(gsm->shift + cc + i);
-            const float2 va = unpack_f16x2(stash[(k * 32 + i) / 2]), vb = unpack_f16x2(stash[(k * 32 + i) / 2 + 1]);
+            const float2 va = unpack_f16x2(hv[i / 2]), vb = unpack_f16x2(hv[i / 2 + 1]);
             float h0, h1, h2, h3, y0, y1, y2, y3;
             fma2(h0, h1, va.x, va.y, s4.x, s4.y, h4.x, h4.y);              // h = y/2
             fma2(h2, h3, vb.x, vb.y, s4.z, s4.w, h4.z, h4.w);

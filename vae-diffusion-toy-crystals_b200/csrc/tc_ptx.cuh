@@ -113,11 +113,15 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void mbar_arrive_rank0(uint32_t bar) {   // arrive on CTA 0's copy of this barrier
+// Arrive on CTA 0's copy of this barrier.  RELAXED: the only thing this arrival publishes is "my tcgen05.ld of the
+// accumulator set have completed" (tcgen05.wait::ld + tcgen05.fence::before_thread_sync precede it), no memory.  With
+// .release.cluster the compiler emits MEMBAR.ALL.GPU + ERRBAR here, which waits for every global store the thread has in
+// flight (the halo stores of the previous tile): ~2k cycles per tile in the ncu stall samples (stall_membar).
+__device__ __forceinline__ void mbar_arrive_rank0(uint32_t bar) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar) : "memory");
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
                                                 int c2, int c3) {
