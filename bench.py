@@ -546,7 +546,7 @@ def run_gpu(args):
     return 0
 
 
-def profile_kernels(model, sde, dev):
+def profile_kernels(model, sde, dev, n=128):
     """Per-kernel numbers, measured live: (a) the tcgen05 conv family of one network pass via tcs_score_profiled
     (CUDA events on the library stream around each conv launch), (b) the fused SDE update kernel alone."""
     import ctypes as C
@@ -555,7 +555,6 @@ def profile_kernels(model, sde, dev):
     from toycrystals_b200.models import sde_score_model as shim
     L = _cabi.lib()
     h = model.engine_handle(sde)
-    n = 128
     y_cat, y_cont = shim.condition_grid(model, n, 3.141592653589793 / 3.0, dev)
     x = torch.randn((n, 1, 64, 64), device=dev)
     t = torch.full((n,), 0.37, device=dev)

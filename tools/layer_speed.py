@@ -14,6 +14,7 @@ from toycrystals_b200.models import sde_score_model as shim  # noqa: E402
 
 torch.manual_seed(1)
 m = shim.CondUNetTiny(4, 4, 96, 128, 8, 8, precision="bf16").cuda().eval()
-k = bench.profile_kernels(m, shim.VPSDE(0.1, 30.0), torch.device("cuda", 0))
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 128   # samples per pass (images = 2n); bench.py uses 128
+k = bench.profile_kernels(m, shim.VPSDE(0.1, 30.0), torch.device("cuda", 0), n)
 print(os.environ.get("TCS_DEBUG", "0"), round(k["conv_tflops"], 1), round(k["conv_ms"], 3), round(k["conv_share"], 3),
       json.dumps(k["per_layer"]))
