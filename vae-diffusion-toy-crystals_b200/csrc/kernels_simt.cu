@@ -119,6 +119,13 @@ template <bool FAST> __device__ __forceinline__ float silu_f(float v);
 // statistics, pass 2: normalise + write the padded activation) instead of round-tripping fp32.
 // thread = (output-channel pair, pixel phase): 48 x 8 = 384 threads.
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 pk_fma2v(float2 a, float2 b, float2 c) {   // packed fp32 FMA (FFMA2)
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
 template <typename T> __device__ __forceinline__ void store_pair(T* p, float a, float b);
 template <> __device__ __forceinline__ void store_pair<float>(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
 template <> __device__ __forceinline__ void store_pair<__nv_bfloat16>(__nv_bfloat16* p, float a, float b) {
@@ -139,7 +146,7 @@ __global__ void __launch_bounds__(384, 2) first_conv_gn_kernel(const float* __re
                                                            T* __restrict__ out) {
   constexpr bool FAST = sizeof(T) == 2;
   constexpr int P = IMG + 4;                 // halo of 2 for the autocorrelation lags
-  __shared__ float xs[P][P];
+  __shared__ float2 xs[P][P];                // {x, x}: the packed-FMA main loop wants the input value in both halves
   __shared__ double racc[12][14];            // per-warp partial: 13 lags + sum x
   __shared__ double R[5][5];
   __shared__ double S1;
@@ -150,7 +157,8 @@ __global__ void __launch_bounds__(384, 2) first_conv_gn_kernel(const float* __re
   const int warp = t >> 5, lane = t & 31;
   for (int e = t; e < P * P; e += 384) {
     const int r = e / P, c = e - r * P;
-    xs[r][c] = x[(static_cast<size_t>(i) * IMG + ((r - 2 + IMG) & (IMG - 1))) * IMG + ((c - 2 + IMG) & (IMG - 1))];
+    const float xval = x[(static_cast<size_t>(i) * IMG + ((r - 2 + IMG) & (IMG - 1))) * IMG + ((c - 2 + IMG) & (IMG - 1))];
+    xs[r][c] = make_float2(xval, xval);
   }
   __syncthreads();
   {  // R(dy,dx) for the 13 lags with (dy > 0) or (dy == 0 and dx >= 0); R(-d) = R(d)
@@ -159,12 +167,12 @@ __global__ void __launch_bounds__(384, 2) first_conv_gn_kernel(const float* __re
     for (int k = 0; k < 14; ++k) acc[k] = 0.0;
     for (int p = t; p < IMG_PIX; p += 384) {
       const int yy = (p >> 6) + 2, xx = (p & 63) + 2;
-      const double x0 = xs[yy][xx];
+      const double x0 = xs[yy][xx].x;
       acc[13] += x0;
 #pragma unroll
       for (int k = 0; k < 13; ++k) {
         const int dy = (k + 2) / 5, dx = (k + 2) % 5 - 2;   // k=0..2 -> dy=0,dx=0..2 ; then dy=1,2 with dx=-2..2
-        acc[k] += x0 * static_cast<double>(xs[yy + dy][xx + dx]);
+        acc[k] += x0 * static_cast<double>(xs[yy + dy][xx + dx].x);
       }
     }
 #pragma unroll
@@ -238,6 +246,55 @@ __global__ void __launch_bounds__(384, 2) first_conv_gn_kernel(const float* __re
   const int p_begin = band * (IMG_PIX / FC_SPLIT), p_end = p_begin + IMG_PIX / FC_SPLIT;
   // runs of 4 horizontally adjacent pixels: 18 shared-memory loads feed 72 FMAs (the one-pixel version was LDS-bound)
   (void)p_end;
+  if constexpr (FAST) {
+    // bf16 output: packed fp32 math (FFMA2).  The two channels of a thread are the two halves of every operand: weights
+    // {w0, w1}, input {x, x} (stored duplicated), accumulators {c0, c1}; 0.5 of SiLU(y) = h + h tanh(h), h = y / 2, is
+    // folded into the affine.  (The scalar version was issue-bound: 77 % issue-active for 160 MB of output.)
+    float2 w2[9], sc2[2], sh2[2];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) w2[k] = make_float2(w0[k], w1[k]);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) { sc2[u] = make_float2(0.5f * sc0[u], 0.5f * sc1[u]); sh2[u] = make_float2(0.5f * sh0[u], 0.5f * sh1[u]); }
+    for (int qd = pg; qd < IMG_PIX / FC_SPLIT / 4; qd += 8) {
+      const int p = p_begin + qd * 4;
+      const int yy = p >> 6, xx = p & 63;
+      float2 c[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) c[j] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        float2 xv[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) xv[k] = xs[yy + 1 + ky][xx + 1 + k];
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) c[j] = pk_fma2v(w2[ky * 3 + kx], xv[j + kx], c[j]);
+      }
+      const int wy = halo_wrap(yy, IMG);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int wx = halo_wrap(xx + j, IMG);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (u >= dup) break;
+          const float2 hh = pk_fma2v(c[j], sc2[u], sh2[u]);
+          float t0, t1;
+          asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(hh.x));
+          asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(hh.y));
+          const float2 yv = pk_fma2v(hh, make_float2(t0, t1), hh);
+          const size_t base = ((static_cast<size_t>(i) * dup + u) * PO + yy + 1) * PO + xx + j + 1;
+          store_pair<T>(out + base * 96 + oc, yv.x, yv.y);
+          if (wy | wx) {
+            if (wy) store_pair<T>(out + (base + static_cast<long long>(wy) * PO) * 96 + oc, yv.x, yv.y);
+            if (wx) store_pair<T>(out + (base + wx) * 96 + oc, yv.x, yv.y);
+            if (wy && wx) store_pair<T>(out + (base + static_cast<long long>(wy) * PO + wx) * 96 + oc, yv.x, yv.y);
+          }
+        }
+      }
+    }
+    return;
+  }
   for (int qd = pg; qd < IMG_PIX / FC_SPLIT / 4; qd += 8) {
     const int p = p_begin + qd * 4;
     const int yy = p >> 6, xx = p & 63;
@@ -245,7 +302,7 @@ __global__ void __launch_bounds__(384, 2) first_conv_gn_kernel(const float* __re
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-      for (int k = 0; k < 6; ++k) xv[ky][k] = xs[yy + 1 + ky][xx + 1 + k];
+      for (int k = 0; k < 6; ++k) xv[ky][k] = xs[yy + 1 + ky][xx + 1 + k].x;
     float c[4][2];
 #pragma unroll
     for (int j = 0; j < 4; ++j) c[j][0] = c[j][1] = 0.f;
