@@ -288,6 +288,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                   if (cta_rank == 0) ptx::mbar_expect_tx(full, 2 * (p.a_bytes + p.T * NB * 64));
                   ptx::tma_load_4d_2sm(a_dst, mapA, full, cb * 32, kx + p.kxn + p.base_off[src],
                                        p.stride * y0 + kyg + p.base_off[src], b);
+                  if (p.pair)
+                    ptx::tma_load_4d_2sm(a_dst + p.a_bytes / 2, mapA, full, cb * 32, kx + p.kxn + p.base_off[src],
+                                         p.stride * y0 + kyg + p.base_off[src], b + 1);
                   for (int j = 0; j < p.T; ++j)
                     ptx::tma_load_2d_2sm(b_dst + j * NB * 64, &mapW, full, 0,
                                          (ks * p.T + j) * p.ntot + nt * N + static_cast<int>(cta_rank) * NB);
@@ -871,7 +874,7 @@ int conv_tc_make_pair(ConvTcPlan* pl, const void* src, int B) {
   p.tiles_per_img = p.H / p.Rt;                       // tiles per image PAIR
   p.n_mtiles = (B / 2) * p.tiles_per_img;
   p.a_bytes = 2u * static_cast<uint32_t>(p.WR) * p.W * 64;
-  p.stage_bytes = (p.a_bytes + p.T * pl->N * 64 + 1023u) & ~1023u;
+  p.stage_bytes = (p.a_bytes + p.T * (pl->N / pl->cg) * 64 + 1023u) & ~1023u;
   const size_t budget = 227 * 1024 - 2048 - 1024 - EPI_SLAB_BYTES - EPI_BIAS_BYTES - EPI_FUSED_BYTES;
   p.nstage = static_cast<int>(budget / p.stage_bytes);
   if (p.nstage > MAX_STAGES) p.nstage = MAX_STAGES;
@@ -932,7 +935,7 @@ int conv_tc_launch(const ConvTcPlan& pl, cudaStream_t st) {
   if (!pl.valid) return fail(TCS_ERR_STATE, "conv_tc_launch: plan not built");
 #define TCS_TC_CASE(NN, EE, MM)                                                        \
   if (pl.N == NN && pl.epi == EE && pl.msub == MM) {                                    \
-    if (pl.cg == 2) { if constexpr (NN >= 96) return launch_t<NN, EE, MM, 2>(pl, st); } \
+    if (pl.cg == 2) { if constexpr (NN >= 96 || EE == EPI_EPS) return launch_t<NN, EE, MM, 2>(pl, st); } \
     else return launch_t<NN, EE, MM, 1>(pl, st);                                        \
   }
   TCS_TC_CASE(96, EPI_RAW_STATS, 2)
@@ -967,6 +970,10 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, con
   {
     const char* e = getenv("TCS_CG");   // 1 = single-CTA MMA everywhere (A/B switch)
     pl.cg = (pl.N >= 96 && !(e && atoi(e) == 1)) ? 2 : 1;
+    // the 96 -> 1 output conv is bound by MMA ISSUE (36 tiny N = 16 MMAs per tile at ~100 cycles each): as a CTA pair one
+    // thread's MMA covers both CTAs' tiles, which halves the issue work per tile
+    const char* e2 = getenv("TCS_EPS_CG");
+    if (epi == EPI_EPS && !(e && atoi(e) == 1) && !(e2 && atoi(e2) == 1) && (g.B * (g.H / (2 * (128 / g.W)))) % 2 == 0) pl.cg = 2;
   }
   if (g.H % (pl.msub * (128 / g.W))) return fail(TCS_ERR_UNSUPPORTED, "conv_tc: image height not a multiple of the tile");
   p.debug = getenv("TCS_DEBUG") ? atoi(getenv("TCS_DEBUG")) : 0;
