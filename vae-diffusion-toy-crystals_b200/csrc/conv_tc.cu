@@ -233,7 +233,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     ptx::prefetch_tmap(&mapA0);
     ptx::prefetch_tmap(&mapA1);
     ptx::prefetch_tmap(&mapW);
-    if (EPI != EPI_PLAIN && EPI != EPI_EPS) ptx::prefetch_tmap(&mapO);
+    if (EPI != EPI_EPS) ptx::prefetch_tmap(&mapO);
     for (int s = 0; s < p.nstage; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bars.full[s]), 1);
       ptx::mbar_init(ptx::smem_u32(&bars.empty[s]), p.issuers);     // one tcgen05.commit per issuing thread
@@ -761,21 +761,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             }
             store_padded_block(&mapO, use_tma_out, slab, slab_buf, lane, obase, pix, wy, wx, Wp, p.epi.ldo, n_off + c0, b, y, x, pk);
           }
-        } else {  // EPI_PLAIN
+        } else {  // EPI_PLAIN: unpadded bf16 [pixel][ldo] rows; 32 px x 32 ch blocks staged in the warp's slabs and
+                  // TMA-stored (a lane-per-row 16-byte store touches 32 different lines per instruction)
           __nv_bfloat16* orow = static_cast<__nv_bfloat16*>(p.epi.out) + static_cast<size_t>(m) * p.epi.ldo + n_off;
+          const bool tma_plain = !(p.debug & 4);
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
             ptx::tmem_ld_wait();
             if (k < 2) ptx::tmem_ld32(taddr + (k + 1) * 32, vbuf[(k + 1) & 1]);
             else release_tmem();
             const float* v = vbuf[k & 1];
+            uint32_t pk[16];
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) {
+            for (int i = 0; i < 32; i += 4) {
               const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n_off + k * 32 + i);
-              const float4 b5 = *reinterpret_cast<const float4*>(bias_s + n_off + k * 32 + i + 4);
-              *reinterpret_cast<uint4*>(orow + k * 32 + i) =
-                  make_uint4(pack_bf16x2(v[i] + b4.x, v[i + 1] + b4.y), pack_bf16x2(v[i + 2] + b4.z, v[i + 3] + b4.w),
-                             pack_bf16x2(v[i + 4] + b5.x, v[i + 5] + b5.y), pack_bf16x2(v[i + 6] + b5.z, v[i + 7] + b5.w));
+              pk[i / 2] = pack_bf16x2(v[i] + b4.x, v[i + 1] + b4.y);
+              pk[i / 2 + 1] = pack_bf16x2(v[i + 2] + b4.z, v[i + 3] + b4.w);
+            }
+            if (tma_plain) {
+              if (lane == 0) ptx::bulk_wait_read<SLAB_BUFS - 1>();
+              __syncwarp();
+              const uint32_t base = slab + (SLAB_BUFS == 2 ? slab_buf * 2048 : 0);
+              const uint32_t dst = base + lane * 64;
+              const int sw = (lane >> 1) & 3;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) st_shared_u4(dst + ((j ^ sw) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+              ptx::fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                ptx::tma_store_2d(&mapO, base, n_off + k * 32, m - lane);   // rows m - lane .. m - lane + 31 of the [M, ldo] tensor
+                ptx::bulk_commit();
+              }
+              slab_buf ^= 1;
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                *reinterpret_cast<uint4*>(orow + k * 32 + i * 8) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
             }
           }
         }
@@ -1040,6 +1061,17 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, con
     if (r != CUDA_SUCCESS) return fail(TCS_ERR_CUDA, "cuTensorMapEncodeTiled(W) failed: " + std::to_string(r));
   }
   pl.mapO = pl.mapW;
+  if (epi == EPI_PLAIN) {   // bf16 [M = B*H*W, ldo] output, 32-row x 32-channel boxes
+    const cuuint64_t C = static_cast<cuuint64_t>(ea.ldo);
+    cuuint64_t dims[2] = {C, static_cast<cuuint64_t>(g.B) * g.H * g.W};
+    cuuint64_t strides[1] = {C * 2};
+    cuuint32_t box[2] = {BLK, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&pl.mapO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ea.out, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(TCS_ERR_CUDA, "cuTensorMapEncodeTiled(O plain) failed: " + std::to_string(r));
+  }
   if ((epi == EPI_GN_FUSED || epi == EPI_PADDED) && g.W >= 32) {   // bf16 padded output, 32-pixel x 32-channel boxes
     const cuuint64_t C = static_cast<cuuint64_t>(ea.ldo);
     cuuint64_t dims[4] = {C, static_cast<cuuint64_t>(g.W + 2), static_cast<cuuint64_t>(g.H + 2), static_cast<cuuint64_t>(g.B)};
