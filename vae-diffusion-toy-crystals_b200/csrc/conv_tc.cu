@@ -126,7 +126,7 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
 __device__ __forceinline__ void store_padded_block(const CUtensorMap* mapO, bool use_tma, uint32_t slab, uint32_t& slab_buf,
                                                    int lane, __nv_bfloat16* obase, size_t pix, int wy, int wx, int Wp,
                                                    int ldo, int ch, int img, int y, int x, const uint32_t* pk,
-                                                   long long* tacc = nullptr) {
+                                                   long long* tacc = nullptr, int h16 = 0) {
   if (!use_tma) {
     store_with_halo(obase, pix, wy, wx, Wp, ldo, ch, pk);
     return;
@@ -144,8 +144,15 @@ __device__ __forceinline__ void store_padded_block(const CUtensorMap* mapO, bool
   __syncwarp();
   if (tacc) { const long long c1 = clock64(); tacc[1] += c1 - c0; c0 = c1; }
   if (lane == 0) {   // lane 0 holds the first pixel of the block: (y, x) -> padded (y+1, x+1)
-    tma_store_4d(mapO, base, ch, x + 1, y + 1, img);
-    if (wy) tma_store_4d(mapO, base, ch, x + 1, y + 1 + wy, img);
+    if (h16 == 0) {
+      tma_store_4d(mapO, base, ch, x + 1, y + 1, img);
+      if (wy) tma_store_4d(mapO, base, ch, x + 1, y + 1 + wy, img);
+    } else {         // 16-pixel rows: the block is image rows y (lanes 0-15) and y + 1 (lanes 16-31), one 16-pixel box each
+      tma_store_4d(mapO, base, ch, 1, y + 1, img);
+      tma_store_4d(mapO, base + 1024, ch, 1, y + 2, img);
+      if (y == 0) tma_store_4d(mapO, base, ch, 1, h16 + 1, img);                 // row 0 -> also padded row H + 1
+      if (y + 1 == h16 - 1) tma_store_4d(mapO, base + 1024, ch, 1, 0, img);      // row H - 1 -> also padded row 0
+    }
     ptx::bulk_commit();
   }
   __syncwarp();
@@ -412,7 +419,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     EpiGroupSmem* gsm = &fs->grp[grp];
     (void)gsm;
     const uint32_t slab = slab_base + static_cast<uint32_t>(e) * EPI_WARP_SLAB;      // this warp's 2 x 2 KB staging halves
-    const bool use_tma_out = p.W >= 32 && !(p.debug & 4);
+    const bool use_tma_out = !(p.debug & 4);
+    const int h16 = p.W == 16 ? p.H : 0;       // 16-pixel rows: a 32-lane block spans two image rows
+    (void)h16;
     (void)use_tma_out; (void)slab;
     const int sub = (MSUB == 2) ? h : 0;
     const int col0 = (MSUB == 2) ? 0 : h * UC;   // first channel (inside the N tile) of this warp's columns
@@ -670,7 +679,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           }
           if (!(p.debug & 2))
             store_padded_block(&mapO, use_tma_out, slab, slab_buf, lane, obase, pix, wy, wx, Wp, p.epi.ldo, cc, img, y, x, pk,
-                               prof ? tacc : nullptr);
+                               prof ? tacc : nullptr, h16);
           else if (pk[0] == 0x12345678u && pk[7] == 0x9abcdef0u) obase[0] = __float2bfloat16(0.f);
         }
         if (prof) r_math += clock64() - pc1;
@@ -759,7 +768,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
               pk[i / 2] = pack_bf16x2(v[i] + b4.x, v[i + 1] + b4.y);
               pk[i / 2 + 1] = pack_bf16x2(v[i + 2] + b4.z, v[i + 3] + b4.w);
             }
-            store_padded_block(&mapO, use_tma_out, slab, slab_buf, lane, obase, pix, wy, wx, Wp, p.epi.ldo, n_off + c0, b, y, x, pk);
+            store_padded_block(&mapO, use_tma_out, slab, slab_buf, lane, obase, pix, wy, wx, Wp, p.epi.ldo, n_off + c0, b, y, x, pk, nullptr, h16);
           }
         } else {  // EPI_PLAIN: unpadded bf16 [pixel][ldo] rows; 32 px x 32 ch blocks staged in the warp's slabs and
                   // TMA-stored (a lane-per-row 16-byte store touches 32 different lines per instruction)
@@ -1072,11 +1081,11 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, con
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(TCS_ERR_CUDA, "cuTensorMapEncodeTiled(O plain) failed: " + std::to_string(r));
   }
-  if ((epi == EPI_GN_FUSED || epi == EPI_PADDED) && g.W >= 32) {   // bf16 padded output, 32-pixel x 32-channel boxes
+  if (epi == EPI_GN_FUSED || epi == EPI_PADDED) {   // bf16 padded output, 32-pixel (16 for 16-pixel rows) x 32-channel boxes
     const cuuint64_t C = static_cast<cuuint64_t>(ea.ldo);
     cuuint64_t dims[4] = {C, static_cast<cuuint64_t>(g.W + 2), static_cast<cuuint64_t>(g.H + 2), static_cast<cuuint64_t>(g.B)};
     cuuint64_t strides[3] = {C * 2, C * 2 * (g.W + 2), C * 2 * (g.W + 2) * (g.H + 2)};
-    cuuint32_t box[4] = {BLK, 32, 1, 1};
+    cuuint32_t box[4] = {BLK, static_cast<cuuint32_t>(g.W >= 32 ? 32 : 16), 1, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = encode(&pl.mapO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ea.out, dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, BLK == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
