@@ -271,10 +271,14 @@ __global__ void __launch_bounds__(384, 2) first_conv_gn_kernel(const float* __re
 #pragma unroll
           for (int j = 0; j < 4; ++j) c[j] = pk_fma2v(w2[ky * 3 + kx], xv[j + kx], c[j]);
       }
-      const int wy = halo_wrap(yy, IMG);
+      // addresses: one 64-bit base per run, then constant strides (the scalar version spent a third of its issue slots
+      // on predicated 64-bit address arithmetic for the halo copies)
+      T* const o_run = out + ((static_cast<size_t>(i) * dup * PO + yy + 1) * PO + xx + 1) * 96 + oc;
+      constexpr long long IMG_STRIDE = static_cast<long long>(PO) * PO * 96, COL_WRAP = static_cast<long long>(IMG) * 96;
+      const long long wyo = static_cast<long long>(halo_wrap(yy, IMG)) * PO * 96;   // 0 = not a border row
+      const bool left = xx == 0, right = xx == IMG - 4;                           // runs are 4-aligned
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int wx = halo_wrap(xx + j, IMG);
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           if (u >= dup) break;
@@ -283,12 +287,16 @@ __global__ void __launch_bounds__(384, 2) first_conv_gn_kernel(const float* __re
           asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(hh.x));
           asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(hh.y));
           const float2 yv = pk_fma2v(hh, make_float2(t0, t1), hh);
-          const size_t base = ((static_cast<size_t>(i) * dup + u) * PO + yy + 1) * PO + xx + j + 1;
-          store_pair<T>(out + base * 96 + oc, yv.x, yv.y);
-          if (wy | wx) {
-            if (wy) store_pair<T>(out + (base + static_cast<long long>(wy) * PO) * 96 + oc, yv.x, yv.y);
-            if (wx) store_pair<T>(out + (base + wx) * 96 + oc, yv.x, yv.y);
-            if (wy && wx) store_pair<T>(out + (base + static_cast<long long>(wy) * PO + wx) * 96 + oc, yv.x, yv.y);
+          T* const o = o_run + j * 96 + u * IMG_STRIDE;
+          store_pair<T>(o, yv.x, yv.y);
+          if (wyo) store_pair<T>(o + wyo, yv.x, yv.y);
+          if (j == 0 && left) {
+            store_pair<T>(o + COL_WRAP, yv.x, yv.y);
+            if (wyo) store_pair<T>(o + wyo + COL_WRAP, yv.x, yv.y);
+          }
+          if (j == 3 && right) {
+            store_pair<T>(o - COL_WRAP, yv.x, yv.y);
+            if (wyo) store_pair<T>(o + wyo - COL_WRAP, yv.x, yv.y);
           }
         }
       }
