@@ -925,12 +925,21 @@ __global__ void __launch_bounds__(256, 2) attention_mma_kernel(const __nv_bfloat
   const int b = bh >> 2, head = bh & 3;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
   const __nv_bfloat16* base = qkv + static_cast<size_t>(b) * ATT_TOK * (3 * ATT_C) + head * ATT_D;
-  for (int e = tid; e < ATT_TOK * 6; e += 256) {
-    const int tok = e / 6, ch = e - tok * 6;
-    const uint4 kv = *reinterpret_cast<const uint4*>(base + static_cast<size_t>(tok) * (3 * ATT_C) + ATT_C + ch * 8);
-    const uint4 vv = *reinterpret_cast<const uint4*>(base + static_cast<size_t>(tok) * (3 * ATT_C) + 2 * ATT_C + ch * 8);
-    *reinterpret_cast<uint4*>(Ks + tok * ATT_STRIDE + ch * 8) = kv;
-    *reinterpret_cast<uint4*>(Vs + tok * ATT_STRIDE + ch * 8) = vv;
+  // K and V of the four 64-key chunks arrive as four cp.async groups, so the first chunk's MMAs start while the
+  // other three are still in flight (the plain load + barrier kept the block idle for a whole L2/HBM round trip)
+  {
+    const uint32_t ks_sh = static_cast<uint32_t>(__cvta_generic_to_shared(Ks)), vs_sh = static_cast<uint32_t>(__cvta_generic_to_shared(Vs));
+#pragma unroll
+    for (int cch = 0; cch < ATT_TOK / 64; ++cch) {
+      for (int e = tid; e < 64 * 6; e += 256) {
+        const int tok = cch * 64 + e / 6, ch = e % 6;
+        const __nv_bfloat16* src = base + static_cast<size_t>(tok) * (3 * ATT_C) + ATT_C + ch * 8;
+        const uint32_t off = static_cast<uint32_t>((tok * ATT_STRIDE + ch * 8) * 2);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ks_sh + off), "l"(src) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(vs_sh + off), "l"(src + ATT_C) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
   }
   // Q fragments: 2 m-tiles x 3 k-steps, straight from global memory
   uint32_t qf[MT][3][4];
@@ -946,7 +955,6 @@ __global__ void __launch_bounds__(256, 2) attention_mma_kernel(const __nv_bfloat
       qf[mt][ks][2] = *reinterpret_cast<const uint32_t*>(q0 + 8);
       qf[mt][ks][3] = *reinterpret_cast<const uint32_t*>(q1 + 8);
     }
-  __syncthreads();
   const uint32_t ks_addr = static_cast<uint32_t>(__cvta_generic_to_shared(Ks));
   const uint32_t vs_addr = static_cast<uint32_t>(__cvta_generic_to_shared(Vs));
   const float c = 0.14433756729740643f * 1.4426950408889634f;  // (1/sqrt(48)) * log2(e)
@@ -962,6 +970,11 @@ __global__ void __launch_bounds__(256, 2) attention_mma_kernel(const __nv_bfloat
       for (int k = 0; k < 4; ++k) o[mt][nt][k] = 0.f;
   }
   for (int kc = 0; kc < ATT_TOK; kc += 64) {
+    if (kc == 0) asm volatile("cp.async.wait_group 3;" ::: "memory");
+    else if (kc == 64) asm volatile("cp.async.wait_group 2;" ::: "memory");
+    else if (kc == 128) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();        // every thread's copies of this chunk are in shared memory
     float sacc[MT][8][4];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
