@@ -411,3 +411,31 @@ def test_output_conv_variants_agree(monkeypatch):
         del m
     for a, b in zip(outs[0], outs[1]):
         assert orc.rel_l2(a, b) < 1e-5
+
+
+@pytest.mark.gpu
+def test_tma_store_epilogues_match_per_lane_stores(monkeypatch):
+    """Every epilogue that stages 32x32 blocks and hands them to TMA (padded outputs at 64/32/16-pixel rows, the
+    unpadded qkv rows, the fused GroupNorm layers) against the per-lane store path (TCS_DEBUG=4) and against single-CTA
+    MMAs (TCS_CG=1): the arithmetic is the same, only the way the bytes reach memory changes, so a whole CFG evaluation
+    must be bit-identical; n = 5 gives a ragged number of image groups and CTA pairs."""
+    import toycrystals_oracle as orc
+    from toycrystals_b200.models import sde_score_model as shim
+    sd = orc.default_init_state_dict(1)
+    y_cat, y_cont = (t.cuda() for t in orc.condition_grid(5, 4, 4))
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn((5, 1, 64, 64), generator=g).cuda()
+    t = torch.full((5,), 0.6).cuda()
+    outs = []
+    for env in ({}, {"TCS_DEBUG": "4"}, {"TCS_CG": "1"}):
+        for k in ("TCS_DEBUG", "TCS_CG"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        m = shim.CondUNetTiny(**orc.DEFAULT_CFG, precision="bf16")
+        m.load_state_dict(sd)
+        m = m.to("cuda").eval()
+        outs.append(shim.predict_eps_cfg(m, x, t, y_cat, y_cont, 1.5).clone())
+        del m
+    assert torch.equal(outs[0], outs[1]), "TMA-store epilogues differ from per-lane stores"
+    assert torch.equal(outs[0], outs[2]), "CTA-pair MMAs differ from single-CTA MMAs"
