@@ -228,7 +228,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const int n_tiles = p.n_mtiles * p.n_ntiles;
-  // after the operand ring: 4 epilogue warps x 2 x 4 KB output slabs (TMA-store staging), then the bias
+  // after the operand ring: 16 epilogue warps x 2 x 2 KB staging blocks (fp16 stash of the fused epilogue, TMA-store
+  // source of every bf16 output), then the bias
   const uint32_t slab_base = smem_base + p.nstage * p.stage_bytes;
   float* bias_s = reinterpret_cast<float*>(smem_raw + (slab_base - ptx::smem_u32(smem_raw)) + EPI_SLAB_BYTES);
   for (int i = threadIdx.x; i < p.ntot; i += TC_THREADS) bias_s[i] = p.epi.bias[i];
@@ -427,8 +428,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const int col0 = (MSUB == 2) ? 0 : h * UC;   // first channel (inside the N tile) of this warp's columns
     uint32_t it = 0;
     const bool prof = TCS_KERNEL_PROFILE && (p.debug & 128) && blockIdx.x == 0 && e == 0;
-    long long pw_full = 0, p_ld = 0, p_a = 0, p_b = 0, p_c = 0, pc0 = 0, pc1 = 0, q_post = 0, q_poll = 0, q_npoll = 0, r_ss = 0, r_math = 0, r_store = 0;
-    (void)p_ld; (void)r_store;
+    long long pw_full = 0, p_ld = 0, p_a = 0, p_b = 0, p_c = 0, pc0 = 0, pc1 = 0, q_post = 0, q_poll = 0, q_npoll = 0, r_math = 0;
+    (void)p_ld;
     long long tacc[3] = {0, 0, 0};
     auto release_tmem = [&]() {
       ptx::tc_fence_before();
@@ -812,8 +813,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       }
     }
     if (prof && lane == 0 && it > 1)
-      printf("[epi N=%d EPI=%d] per tile: wait tmem_full %lld  tmem ld %lld  stats+barA %lld  exchange+barB %lld (post %lld, poll %lld, polls %lld)  rest(pass2+stores) %lld (scale/shift+barC %lld, pass2 %lld: wait_read %lld, sts+fence %lld, tma issue %lld)\n",
-             N, EPI, pw_full / it, p_ld / it, p_a / it, p_b / it, q_post / it, q_poll / it, q_npoll / it, p_c / (it - 1), r_ss / it, r_math / it, tacc[0] / it, tacc[1] / it, tacc[2] / it);
+      printf("[epi N=%d EPI=%d] per tile: wait tmem_full %lld  staging-block wait %lld  pass1+barA %lld  exchange+table+barB %lld (post %lld, poll %lld, polls %lld)  pass2+stores+loop %lld (pass2 %lld: wait_read %lld, sts+fence %lld, tma issue %lld)\n",
+             N, EPI, pw_full / it, p_ld / it, p_a / it, p_b / it, q_post / it, q_poll / it, q_npoll / it, p_c / (it - 1), r_math / it, tacc[0] / it, tacc[1] / it, tacc[2] / it);
     if (lane == 0) ptx::bulk_wait_all();   // staged TMA stores have left shared memory
   }
 
