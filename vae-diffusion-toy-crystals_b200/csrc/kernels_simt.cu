@@ -710,7 +710,7 @@ __device__ __forceinline__ void up_emit(T* __restrict__ dst, const float* o, int
   }
 }
 template <typename T>
-__global__ void __launch_bounds__(UP_THREADS, 3) upsample2x_tiled_kernel(const T* __restrict__ in, int h, int w, int C,
+__global__ void __launch_bounds__(UP_THREADS, 4) upsample2x_tiled_kernel(const T* __restrict__ in, int h, int w, int C,
                                                                          T* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char up_smem[];
   T* tile = reinterpret_cast<T*>(up_smem);            // [UP_BR + 2][w][C / 2]: this block's channel half
