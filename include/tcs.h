@@ -62,6 +62,8 @@ typedef struct tcs_config {
   int32_t device;      /* CUDA ordinal */
   int32_t chunk;       /* images per network pass (0 = library default); sizing knob only */
   int32_t use_graph;   /* 1 = replay the per-step launch sequence from a CUDA graph      */
+  int32_t fuse_gn;     /* 1 (default) = GroupNorm+SiLU fused into the tcgen05 conv epilogue (pre-norm values are staged as
+                          fp16: |v| <= 65504); 0 = conv -> fp32 -> GroupNorm kernel, any magnitude */
 } tcs_config;
 
 /* Fill *cfg with the reference defaults (n_types 4, y_cont_dim 4, 96/128/8/8, beta 0.1..30). */
@@ -102,6 +104,8 @@ typedef struct tcs_sample_args {
   float* trace_eps;             /* NULL or [nfe,n,1,64,64]: CFG-combined eps of every evaluation */
   float* trace_x;               /* NULL or [nfe,n,1,64,64]: the x_t every evaluation saw */
   float* x0_hat;                /* NULL or [n,1,64,64]: projection before the [0,1] map/clamp */
+  double beta_min;              /* VPSDE(beta_min, beta_max) of THIS call; beta_max <= 0 -> the tcs_config values. */
+  double beta_max;              /* (The schedule is per call, as in the reference where `sde` is a sampler argument.) */
 } tcs_sample_args;
 
 int tcs_sample(tcs_handle* h, const tcs_sample_args* args, void* stream);
@@ -119,9 +123,25 @@ int tcs_condition_grid(tcs_handle* h, int32_t n, int64_t offset, int64_t n_total
 int tcs_sde_update(tcs_handle* h, float* x, const float* eps, const float* noise, int32_t n, float t, float t_next,
                    uint64_t seed, uint64_t global_index_offset, int32_t step, void* stream);
 
+/* The probability-flow (Heun) update kernels on their own (sde_score_model.py:426-449, :490-493, :496-504), for the
+ * bit-exactness tests.  mode 1 = predictor: d0 <- drift(x, eps, t), x_pred <- x + d0 * (t_next - t);
+ * mode 2 = corrector: x <- x + 0.5 * (d0 + drift(x_pred, eps, t_next)) * (t_next - t);
+ * mode 3 = final projection at t: x0_hat <- (x - sigma eps) / max(alpha, 1e-6) into d0, image into x_pred. */
+int tcs_ode_update(tcs_handle* h, int32_t mode, float* x, float* x_pred, float* d0, const float* eps, int32_t n,
+                   float t, float t_next, void* stream);
+
 /* Host-side schedule, exactly as the kernels use it (for tests): ts has steps+1 entries. */
 int tcs_time_grid_host(int32_t steps, double t_end, float* ts_host);
 int tcs_schedule_host(double beta_min, double beta_max, float t, float* beta, float* alpha, float* sigma);
+
+/* Waits for the handle's enqueued work and returns its sticky status bits (then clears them):
+ *   bit 0: a fused GroupNorm layer saw a pre-norm activation that may exceed the fp16 staging range; the eps / images of
+ *          the calls since the last check are INVALID - re-run with tcs_config.fuse_gn = 0 (the Python shim does).
+ * Negative = tcs_status (e.g. a kernel fault). */
+int32_t tcs_check(tcs_handle* h);
+/* bit 0: GroupNorm fused into the conv epilogue; bit 1: fused layers launch as CTA pairs with the cooperative attribute;
+ * bits 8..: CTAs of the fused kernel the device holds at once (cudaOccupancyMaxActiveClusters * 2). */
+int32_t tcs_launch_mode(const tcs_handle* h);
 
 /* Counters: kernels launched by this handle since creation / library build info. */
 int64_t tcs_launch_count(const tcs_handle* h);

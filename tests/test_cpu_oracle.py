@@ -239,3 +239,40 @@ def test_adopt_accepts_any_module_with_the_reference_state_dict():
     assert float(again.state_dict()["out.bias"]) == pytest.approx(float(sd["out.bias"]) + 1.0, rel=1e-6)
     with pytest.raises(TypeError, match="does not carry"):
         shim.adopt(torch.nn.Linear(2, 2))
+
+
+# ---- round 2: build freshness and the staged reference ------------------------------------------------
+def test_library_carries_the_hash_of_the_sources_in_the_tree():
+    """A prebuilt libtcs.so that does not match csrc/ + include/ must never be used silently (round-1 review #11)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("tcs_build", os.path.join(ROOT, "vae-diffusion-toy-crystals_b200", "build.py"))
+    bm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bm)
+    info = _cabi.lib().tcs_build_info().decode()
+    assert f"TCS_SRC_HASH={bm.source_hash()}" in info, f"stale libtcs.so: {info}; run python __graft_entry__.py build"
+    assert bm.lib_hash() == bm.source_hash()
+
+
+def test_staged_reference_is_the_unmodified_module_and_runs():
+    """bench.py's reference arm drives the reference's own module from oracle/_ref (oracle/stage_ref.py)."""
+    import hashlib
+    import bench
+    staged = bench._reference_module()
+    if staged is None:
+        pytest.skip("oracle/_ref not staged (run python oracle/stage_ref.py in the build container)")
+    ref, man = staged
+    src = "/root/reference/src/toycrystals/models/sde_score_model.py"
+    if os.path.exists(src):
+        assert hashlib.sha256(open(src, "rb").read()).hexdigest() == man["files"]["toycrystals/models/sde_score_model.py"]
+    img = bench._reference_job(ref, torch.device("cpu"), 2, 1)()
+    assert img.shape == (2, 1, 64, 64) and float(img.min()) >= 0.0 and float(img.max()) <= 1.0
+    # the same run through the oracle port with the same random draws: bit-identical (the pin of the oracle).
+    # _reference_job seeds torch with 1, builds the model, and the sampler then draws x_T and one z per step.
+    torch.manual_seed(1)
+    sd = {k: v.clone() for k, v in ref.CondUNetTiny(4, 4, 96, 128, 8, 8).state_dict().items()}
+    x0 = torch.randn((2, 1, 64, 64))
+    z = torch.randn((2, 1, 64, 64))
+    y_cat, y_cont = orc.condition_grid(2, 4, 4)
+    with torch.no_grad():
+        tr = orc.sample(sd, orc.DEFAULT_CFG, orc.Schedule(0.1, 30.0), y_cat, y_cont, x0, "sde", 1, 1.5, 0.005, [z])
+    assert torch.equal(img, tr.image)

@@ -126,8 +126,8 @@ def test_sampler_teacher_forced_and_free_running(precision, engine):
             # stated per-pixel tolerance for final samples: pre-clamp rel-L2 <= 1e-3 and
             # |delta| > 1/255 on <= 0.5% of the (nearly binary) clamped pixels
             assert x0_err < 1e-3 and mism < 5e-3, (key, x0_err, mism)
-        else:
-            assert x0_err < 1e-1, (key, x0_err)
+        else:   # measured on B200: 1e-3 .. 3e-3 (2-sample, few-step runs of an expanding random-weight trajectory)
+            assert x0_err < 1e-2, (key, x0_err)
 
 
 # ---- the fused update kernel and its RNG ---------------------------------------------------------------
@@ -439,3 +439,248 @@ def test_tma_store_epilogues_match_per_lane_stores(monkeypatch):
         del m
     assert torch.equal(outs[0], outs[1]), "TMA-store epilogues differ from per-lane stores"
     assert torch.equal(outs[0], outs[2]), "CTA-pair MMAs differ from single-CTA MMAs"
+
+
+# ---- round 2: gaps named by the round-1 review ----------------------------------------------------------
+def _oracle_on_cuda():
+    """The oracle evaluated by PyTorch on the GPU in IEEE fp32 (TF32 off): seconds instead of minutes at n = 1024."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.set_float32_matmul_precision("highest")
+
+
+@pytest.mark.parametrize("precision,engine", [("fp32", "simt"), ("fp32", "tcgen05"), ("bf16", "tcgen05")])
+def test_full_size_pass_teacher_forced_against_the_oracle(precision, engine):
+    """BASELINE configs[1] shape: n = 1024 with CFG 1.5 = ONE 2048-image pass (the production shape: 144/148-CTA grids,
+    G-CTA lock step, CTA pairs), eps against the oracle (IEEE fp32 on the GPU) at t = 1, 0.37, 0.005."""
+    pu = _pu()
+    import toycrystals_oracle as orc
+    from toycrystals_b200.models import sde_score_model as shim
+    _oracle_on_cuda()
+    n = 1024
+    m = pu.model(precision, engine, seed=1)
+    sd = {k: v.cuda() for k, v in orc.default_init_state_dict(1).items()}
+    yc, yk = shim.condition_grid(m, n, math.pi / 3, "cuda")
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn((n, 1, 64, 64), generator=g).cuda()
+    for scale, tval in ((1.0, 1.0), (37.0, 0.37), (900.0, 0.005)):
+        t = torch.full((n,), tval, device="cuda")
+        got = shim.predict_eps_cfg(m, x * scale, t, yc, yk, 1.5)
+        with torch.no_grad():
+            want = torch.cat([orc.eps_cfg(sd, pu.CFG, x[i:i + 256] * scale, t[i:i + 256], yc[i:i + 256], yk[i:i + 256], 1.5)
+                              for i in range(0, n, 256)])
+        err = pu.rel_l2(got, want)
+        per_sample = ((got - want).flatten(1).norm(dim=1) / want.flatten(1).norm(dim=1)).max().item()
+        print(f"{precision}/{engine} n={n} t={tval}: eps rel-L2 {err:.3e}, worst sample {per_sample:.3e}")
+        assert err < TOL_EPS[precision], (tval, err)
+        assert per_sample < 2.5 * TOL_EPS[precision], (tval, per_sample)
+
+
+def test_ode_update_kernels_are_bit_exact_vs_torch_expressions():
+    """_probflow_drift (:426-449), the Heun predictor / corrector (:490-493) and the final projection (:496-504) in the
+    reference's fp32 operation order."""
+    pu = _pu()
+    from toycrystals_b200 import _cabi
+    from toycrystals_b200.models.sde_score_model import VPSDE
+    m = pu.model("fp32", "simt")
+    h = m.engine_handle(VPSDE(0.1, 30.0))
+    L = _cabi.lib()
+    sde = VPSDE(0.1, 30.0)
+    g = torch.Generator().manual_seed(6)
+    n = 5
+    x = (torch.randn((n, 1, 64, 64), generator=g) * 30).cuda()
+    e0, e1 = torch.randn((n, 1, 64, 64), generator=g).cuda(), torch.randn((n, 1, 64, 64), generator=g).cuda()
+    t, t_next = torch.tensor(0.3712, device="cuda"), torch.tensor(0.3651, device="cuda")
+    dt = t_next - t
+
+    def drift(xx, ee, tt):
+        beta_t, sigma_t = sde.beta(tt), sde.sigma(tt)
+        score = -ee / sigma_t
+        return -0.5 * beta_t * xx - 0.5 * beta_t * score
+
+    d_want = drift(x, e0, t)
+    xe_want = x + d_want * dt
+    x_want = x + 0.5 * (d_want + drift(xe_want, e1, t_next)) * dt
+    xs, xp, d0 = x.clone(), torch.empty_like(x), torch.empty_like(x)
+    _cabi.check(L.tcs_ode_update(h, 1, xs.data_ptr(), xp.data_ptr(), d0.data_ptr(), e0.data_ptr(), n, float(t), float(t_next), None))
+    torch.cuda.synchronize()
+    assert torch.equal(d0, d_want) and torch.equal(xp, xe_want) and torch.equal(xs, x)
+    _cabi.check(L.tcs_ode_update(h, 2, xs.data_ptr(), xp.data_ptr(), d0.data_ptr(), e1.data_ptr(), n, float(t), float(t_next), None))
+    torch.cuda.synchronize()
+    assert torch.equal(xs, x_want)
+    # final projection at t_end
+    te = torch.tensor(0.005, device="cuda")
+    a, sg = sde.alpha(te), sde.sigma(te)
+    x0_want = (x - sg * e0) / torch.clamp(a, min=1e-6)
+    img_want = ((x0_want + 1.0) * 0.5).clamp(0.0, 1.0)
+    xs = x.clone()
+    _cabi.check(L.tcs_ode_update(h, 3, xs.data_ptr(), xp.data_ptr(), d0.data_ptr(), e0.data_ptr(), n, float(te), float(te), None))
+    torch.cuda.synchronize()
+    assert torch.equal(d0, x0_want) and torch.equal(xp, img_want)
+
+
+def test_graph_cache_follows_workspace_reallocation():
+    """the captured step graph holds the device pointers of per-call buffers that grow with `steps` and
+    with tcs_score / tcs_debug_layer calls in between; a re-allocation must force a re-capture."""
+    pu = _pu()
+    import toycrystals_oracle as orc
+    from toycrystals_b200.models import sde_score_model as shim
+    sde = shim.VPSDE(0.1, 30.0)
+    y_cat, y_cont = orc.condition_grid(4, 4, 4)
+    yc, yk = y_cat.cuda(), y_cont.cuda()
+    x0 = torch.randn((4, 1, 64, 64), generator=torch.Generator().manual_seed(3)).cuda()
+
+    def run(m, steps):
+        return shim.sample_reverse_sde_euler_maruyama(m, sde, yc, yk, (4, 1, 64, 64), n_steps=steps, guidance_scale=1.5,
+                                                      t_end=0.005, x_init=x0, seed=0).clone()
+    fresh = lambda: pu.model("bf16", "tcgen05", seed=1, chunk=8 + run.calls)   # a new handle per reference run
+    run.calls = 0
+    m = pu.model("bf16", "tcgen05", seed=1, chunk=64)
+    a50 = run(m, 50)
+    a300 = run(m, 300)           # tvec / tvals / coef grow -> the old graph would replay freed pointers
+    run.calls += 1
+    assert torch.equal(a300, run(fresh(), 300))
+    # a large tcs_score between two identical sampling calls grows cvec / tvec / eps
+    yc2, yk2 = shim.condition_grid(m, 600, math.pi / 3, "cuda")
+    shim.predict_eps_cfg(m, torch.randn((600, 1, 64, 64), device="cuda"), torch.full((600,), 0.5, device="cuda"), yc2, yk2, 1.5)
+    assert torch.equal(run(m, 50), a50)
+
+
+def test_seed_alone_reproduces_and_shards():
+    """with `seed=` and no x_init the initial state comes from Philox keyed (seed, global index), so a
+    2-shard run equals the 1-shard run and does not depend on torch's generator."""
+    pu = _pu()
+    import toycrystals_oracle as orc
+    from toycrystals_b200.models import sde_score_model as shim
+    m = pu.model("bf16", "tcgen05", seed=1)
+    sde = shim.VPSDE(0.1, 30.0)
+    n = 6
+    yc, yk = shim.condition_grid(m, n, math.pi / 3, "cuda")
+
+    def run(lo, hi, torch_seed):
+        torch.manual_seed(torch_seed)
+        c, k = shim.condition_grid(m, hi - lo, math.pi / 3, "cuda", offset=lo, n_total=n)
+        return shim.sample_reverse_sde_euler_maruyama(m, sde, c, k, (hi - lo, 1, 64, 64), n_steps=3, guidance_scale=1.5,
+                                                      t_end=0.005, seed=42, global_index_offset=lo)
+    full = run(0, n, 1)
+    assert torch.equal(full, run(0, n, 2)), "seed= alone must fix the run"
+    assert torch.equal(torch.cat([run(0, 4, 3), run(4, 6, 4)]), full), "sharded run differs"
+    ode = shim.sample_probability_flow_ode(m, sde, yc, yk, (n, 1, 64, 64), n_steps=2, guidance_scale=1.5, t_end=0.005, seed=42)
+    ode2 = shim.sample_probability_flow_ode(m, sde, yc, yk, (n, 1, 64, 64), n_steps=2, guidance_scale=1.5, t_end=0.005, seed=42)
+    assert torch.equal(ode, ode2)
+
+
+def test_weight_updates_through_data_are_seen():
+    """the reference's EMA update writes p_ema.data in place (scripts/train_sde_score_model.py:239-240), which
+    does not bump tensor._version; the samplers and the training hook must still pick the new weights up."""
+    import toycrystals_oracle as orc
+    from toycrystals_b200.models import sde_score_model as shim
+    sd = orc.default_init_state_dict(1)
+    sde = shim.VPSDE(0.1, 30.0)
+    y_cat, y_cont = (t.cuda() for t in orc.condition_grid(3, 4, 4))
+    x0 = torch.randn((3, 1, 64, 64), generator=torch.Generator().manual_seed(4)).cuda()
+
+    def build():
+        m = shim.CondUNetTiny(**orc.DEFAULT_CFG, precision="bf16")
+        m.load_state_dict(sd)
+        return m.cuda().eval()
+
+    def run(model):
+        return shim.sample_reverse_sde_euler_maruyama(model, sde, y_cat, y_cont, (3, 1, 64, 64), n_steps=2, guidance_scale=1.5,
+                                                      t_end=0.005, x_init=x0, seed=1).clone()
+    m = build()
+    before = run(m)
+    vers = [p._version for p in m.parameters()]
+    with torch.no_grad():
+        for p in m.parameters():
+            p.data.mul_(0.999).add_(0.01 * torch.ones_like(p), alpha=0.001)
+    assert [p._version for p in m.parameters()] == vers, "the premise of this test: .data updates are invisible to _version"
+    after = run(m)
+    assert not torch.equal(before, after), "stale weights: the .data update was not seen"
+    ref = build()
+    ref.load_state_dict(m.state_dict())
+    assert torch.equal(after, run(ref))
+
+    class Foreign(torch.nn.Module):       # the training script's own module: only its state dict is known
+        def __init__(self, inner):
+            super().__init__()
+            self.inner = inner
+            self.n_types, self.y_cont_dim = 4, 4
+
+        def state_dict(self, *a, **k):
+            return self.inner.state_dict(*a, **k)
+    f = Foreign(build())
+    t = torch.full((3,), 0.4, device="cuda")
+    e0 = shim.predict_eps_cfg(f, x0, t, y_cat, y_cont, 1.5).clone()
+    with torch.no_grad():
+        for p in f.inner.parameters():
+            p.data.mul_(0.99)
+    e1 = shim.predict_eps_cfg(f, x0, t, y_cat, y_cont, 1.5)
+    assert not torch.equal(e0, e1)
+
+
+def test_unsupported_architectures_fail_at_construction():
+    from toycrystals_b200.models.sde_score_model import CondUNetTiny
+    with pytest.raises(NotImplementedError, match="base_ch=96"):
+        CondUNetTiny(4, 4)            # the reference's own default base_ch=32
+    with pytest.raises(ValueError):
+        CondUNetTiny(4, 2, base_ch=96)
+
+
+def test_fused_groupnorm_stash_range_is_guarded():
+    """The fused conv+GroupNorm epilogue stages pre-norm values as fp16 (|v| <= 65504).  GroupNorm is scale invariant, so
+    a conv whose weights are scaled by 3e5 must give the same eps: the kernel flags the launch and the shim re-runs the
+    evaluation on the unfused path instead of returning clipped activations."""
+    pu = _pu()
+    import toycrystals_oracle as orc
+    from toycrystals_b200.models import sde_score_model as shim
+    sd = orc.default_init_state_dict(1)
+    big = {k: v.clone() for k, v in sd.items()}
+    for k in ("down1.net.3", "up1.net.0"):
+        big[k + ".weight"] *= 3e5
+        big[k + ".bias"] *= 3e5
+    y_cat, y_cont = (t.cuda() for t in orc.condition_grid(5, 4, 4))
+    x = torch.randn((5, 1, 64, 64), generator=torch.Generator().manual_seed(12)).cuda()
+    t = torch.full((5,), 0.37).cuda()
+    m = shim.CondUNetTiny(**orc.DEFAULT_CFG, precision="bf16")
+    m.load_state_dict(big)
+    m = m.cuda().eval()
+    with pytest.warns(UserWarning, match="fp16 staging range"):
+        got = shim.predict_eps_cfg(m, x, t, y_cat, y_cont, 1.5)
+    with torch.no_grad():
+        want = orc.eps_cfg(big, pu.CFG, x.cpu(), t.cpu(), y_cat.cpu(), y_cont.cpu(), 1.5)
+    assert pu.rel_l2(got, want) < TOL_EPS["bf16"]
+    assert m._fuse_gn is False
+    # and the ordinary model never trips the guard
+    m2 = pu.model("bf16", "tcgen05", seed=1)
+    import warnings as W
+    with W.catch_warnings():
+        W.simplefilter("error")
+        shim.predict_eps_cfg(m2, x * 900.0, torch.full((5,), 0.005).cuda(), y_cat, y_cont, 1.5)
+    assert m2._fuse_gn is True
+
+
+def test_pass_survives_a_busy_neighbour_stream():
+    """The fused-GroupNorm CTAs poll each other's partial sums: the launch must stay correct (and must not hang) while a
+    kernel of ANOTHER stream holds part of the SMs."""
+    pu = _pu()
+    import toycrystals_oracle as orc
+    from toycrystals_b200 import _cabi
+    from toycrystals_b200.models import sde_score_model as shim
+    m = pu.model("bf16", "tcgen05", seed=1)
+    n = 64
+    yc, yk = shim.condition_grid(m, n, math.pi / 3, "cuda")
+    x = torch.randn((n, 1, 64, 64), generator=torch.Generator().manual_seed(13)).cuda()
+    t = torch.full((n,), 0.5).cuda()
+    quiet = shim.predict_eps_cfg(m, x, t, yc, yk, 1.5).clone()
+    mode = int(_cabi.lib().tcs_launch_mode(m.engine_handle()))
+    print(f"launch mode: fused={mode & 1} cooperative+cluster={(mode >> 1) & 1} max resident CTAs={mode >> 8}")
+    side = torch.cuda.Stream()
+    a = torch.randn((8192, 8192), device="cuda", dtype=torch.bfloat16)
+    for _ in range(3):
+        with torch.cuda.stream(side):
+            for _ in range(20):
+                a @ a                      # keeps every SM busy from another stream
+        got = shim.predict_eps_cfg(m, x, t, yc, yk, 1.5)
+        torch.cuda.synchronize()
+        assert torch.equal(got, quiet)

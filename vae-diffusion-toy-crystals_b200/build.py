@@ -6,6 +6,7 @@ is a plain C-ABI shared object that the Python shim loads with ctypes.
 """
 from __future__ import annotations
 
+import hashlib
 import os
 import subprocess
 import sys
@@ -23,6 +24,28 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 
 
+def source_hash() -> str:
+    """SHA-256 over every source and header that goes into libtcs.so (and this recipe); compiled into the library
+    (tcs_build_info() ends in TCS_SRC_HASH=<hex>) so that a stale prebuilt .so is detected, whatever its mtime."""
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
+    files += [os.path.join(HERE, "..", "include", "tcs.h"), os.path.join(HERE, "..", "include", "tcs_prior.h"),
+              os.path.abspath(__file__)]
+    h = hashlib.sha256()
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
+def lib_hash(path: str = LIB):
+    """The TCS_SRC_HASH compiled into an existing libtcs.so (read from the file, no dlopen), or None."""
+    if not os.path.exists(path):
+        return None
+    blob = open(path, "rb").read()
+    k = blob.find(b"TCS_SRC_HASH=")
+    return blob[k + 13:k + 29].decode(errors="replace") if k >= 0 else None
+
+
 def _newer(target: str, deps) -> bool:
     if not os.path.exists(target):
         return False
@@ -36,14 +59,17 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     headers.append(os.path.join(HERE, "..", "include", "tcs.h"))
     headers.append(os.path.join(HERE, "..", "include", "tcs_prior.h"))
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    if not force and _newer(LIB, srcs + headers + [os.path.abspath(__file__)]):
+    want = source_hash()
+    if not force and lib_hash() == want:
         return LIB
 
     def compile_one(src):
         obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
-        if not force and _newer(obj, [src] + headers):
+        is_api = os.path.basename(src) == "tcs_api.cu"       # carries the hash: rebuilt whenever anything changed
+        if not force and not is_api and _newer(obj, [src] + headers):
             return obj, ""
-        r = subprocess.run([NVCC, *FLAGS, "-c", src, "-o", obj], capture_output=True, text=True)
+        extra = [f'-DTCS_SRC_HASH="{want}"'] if is_api else []
+        r = subprocess.run([NVCC, *FLAGS, *extra, "-c", src, "-o", obj], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
         return obj, r.stderr
@@ -60,6 +86,8 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
                        capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    if lib_hash() != want:
+        raise RuntimeError("libtcs.so does not carry the source hash it was just built with")
     return LIB
 
 

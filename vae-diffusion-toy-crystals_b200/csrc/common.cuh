@@ -70,12 +70,14 @@ struct EpiArgs {
   int slots;              // partial slots per image
   const float* gamma;     // EPI_GN_FUSED: GroupNorm affine [ntot]
   const float* beta;
+  int* overflow;          // EPI_GN_FUSED: device flag, set when a pre-norm value may not fit the fp16 stash (|v| > 65504)
 };
 
 // device buffer that only ever grows (cudaMalloc / cudaFree outside the hot loop)
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
+  uint64_t* gen = nullptr;   // optional generation counter of the owner, bumped whenever the buffer moves
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
@@ -86,6 +88,7 @@ struct DevBuf {
     p = nullptr; bytes = 0;
     TCS_CUDA(cudaMalloc(&p, b));
     bytes = b;
+    if (gen) ++*gen;
     return TCS_OK;
   }
   template <typename U> U* as() const { return static_cast<U*>(p); }

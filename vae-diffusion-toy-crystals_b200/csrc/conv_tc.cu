@@ -55,6 +55,10 @@ struct EpiFusedSmem {          // EPI_GN_FUSED scratch (lives right after the bi
   EpiGroupSmem grp[2];
 };
 constexpr uint32_t EPI_FUSED_BYTES = sizeof(EpiFusedSmem);
+// The G CTAs of an image wait for each other's GroupNorm partial sums (one L2 round trip when they run in lock step).
+// Co-residency of the whole grid is guaranteed by the launch (cooperative attribute, grid clamped to
+// cudaOccupancyMaxActiveClusters), so this bound only turns a protocol bug into a launch failure instead of a hang.
+constexpr long long EXCHANGE_TIMEOUT_CYCLES = 1000000000LL;   // ~0.5 s
 
 __device__ __forceinline__ void st_relaxed_gpu_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -559,8 +563,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
               }
             }
           }
+          // fp16 stash range guard, for free: a row whose sum of squares over a group stays below 65504^2 cannot hold a
+          // value that saturated in cvt.rn.satfinite.  Otherwise flag the launch: the host re-runs the evaluation on the
+          // unfused path (conv -> fp32 -> GroupNorm kernel) instead of returning a clipped activation.
+          bool ovf = false;
 #pragma unroll
-          for (int g = 0; g < NGL; ++g) { rv[2 * g] = gs[g]; rv[2 * g + 1] = gq[g]; }
+          for (int g = 0; g < NGL; ++g) { rv[2 * g] = gs[g]; rv[2 * g + 1] = gq[g]; ovf |= !(gq[g] < 4.2907e9f); }
+          if (__any_sync(0xffffffffu, ovf) && lane == 0 && p.epi.overflow) atomicOr(p.epi.overflow, 1);
         }
         // lane reduction: a reduce-scatter over the top lane bits (2*NGL values -> 1 per lane), butterflies for the rest
         constexpr int NV = 2 * NGL;            // 8 or 16
@@ -617,7 +626,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
               if (p.debug & 1) ready = true;
               if (!ready) {
                 ++polls;
-                if (clock64() - t0 > 4000000000LL) __trap();
+                if (clock64() - t0 > EXCHANGE_TIMEOUT_CYCLES) __trap();   // -> launch failure, reported as TCS_ERR_CUDA
               }
             } while (!ready);
 #pragma unroll
@@ -927,26 +936,85 @@ int conv_tc_make_pair(ConvTcPlan* pl, const void* src, int B) {
 int conv_tc_grid(const ConvTcPlan& pl, int B, int sm_count) {
   const int tiles = (pl.p.pair ? B / 2 : B) * pl.p.tiles_per_img * pl.p.n_ntiles;
   int grid = tiles < sm_count ? tiles : sm_count;
+  if (pl.max_ctas > 0 && grid > pl.max_ctas) grid = pl.max_ctas;   // what the device can hold at once (occupancy query)
   if (pl.epi == EPI_GN_FUSED) grid = grid / pl.p.tiles_per_img * pl.p.tiles_per_img;  // whole image groups only
   if (pl.cg == 2) grid &= ~1;                                                         // whole CTA pairs
   return grid;
 }
 
+// Can one launch carry BOTH the cooperative and the cluster attribute?  Probed once with an empty kernel, outside any
+// stream capture (a failed launch would invalidate a capture).
+__global__ void coop_cluster_probe_kernel() {}
+static bool coop_cluster_supported() {
+  static int state = -1;
+  if (state < 0) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2); cfg.blockDim = dim3(32); cfg.dynamicSmemBytes = 0; cfg.stream = nullptr;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+    at[1].id = cudaLaunchAttributeClusterDimension;
+    at[1].val.clusterDim.x = 2; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 2;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(nullptr, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return false; }
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, coop_cluster_probe_kernel);
+    cudaGetLastError();
+    state = (e == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess) ? 1 : 0;
+    if (getenv("TCS_NO_COOP_CLUSTER")) state = 0;
+  }
+  return state == 1;
+}
+
+template <int N, int EPI, int MSUB, int CG>
+static int set_smem_attr() {
+  static bool attr_done = false;
+  if (!attr_done) {
+    TCS_CUDA(cudaFuncSetAttribute(conv_tc_kernel<N, EPI, MSUB, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
+    attr_done = true;
+  }
+  return TCS_OK;
+}
+
+// CTAs of this kernel instance the device can hold at the same time (1 CTA per SM by shared memory; with CTA pairs,
+// whole clusters only: on a partitioned or partly occupied device fewer pairs fit than SMs / 2)
+template <int N, int EPI, int MSUB, int CG>
+static int max_ctas_t(const ConvTcPlan& pl, int* out) {
+  TCS_CHECK((set_smem_attr<N, EPI, MSUB, CG>()));
+  auto kern = conv_tc_kernel<N, EPI, MSUB, CG>;
+  if (CG == 2) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = pl.smem; cfg.stream = nullptr;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int nclusters = 0;
+    TCS_CUDA(cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg));
+    *out = 2 * nclusters;
+  } else {
+    int per_sm = 0, dev = 0, sms = 0;
+    TCS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TC_THREADS, pl.smem));
+    TCS_CUDA(cudaGetDevice(&dev));
+    TCS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    *out = per_sm * sms;
+  }
+  return TCS_OK;
+}
+
 template <int N, int EPI, int MSUB, int CG>
 static int launch_t(const ConvTcPlan& pl, cudaStream_t st) {
   auto kern = conv_tc_kernel<N, EPI, MSUB, CG>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    TCS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
-    attr_done = true;
-  }
+  TCS_CHECK((set_smem_attr<N, EPI, MSUB, CG>()));
   if (EPI == EPI_GN_FUSED)   // the CTAs of an image group exchange (value, flag) words: flag 0 = not written yet
     TCS_CUDA(cudaMemsetAsync(pl.p.epi.partials, 0, sizeof(unsigned long long) * 16 * pl.p.n_mtiles, st));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(pl.grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = pl.smem; cfg.stream = st;
   cudaLaunchAttribute at[2];
   int na = 0;
-  if (EPI == EPI_GN_FUSED && CG == 1) {   // co-resident launch (with CTA pairs the grid <= #SMs, 1 CTA/SM guarantees it)
+  // the CTAs of an image group poll each other's partial sums: the whole grid must be co-resident.  The cooperative
+  // attribute makes the runtime guarantee it (gang scheduling, also against kernels of other streams); where it cannot
+  // be combined with clusters the grid is still <= cudaOccupancyMaxActiveClusters (conv_tc_grid).
+  if (EPI == EPI_GN_FUSED && (CG == 1 || pl.coop_cluster)) {
     at[na].id = cudaLaunchAttributeCooperative;
     at[na].val.cooperative = 1;
     ++na;
@@ -960,6 +1028,25 @@ static int launch_t(const ConvTcPlan& pl, cudaStream_t st) {
   TCS_CUDA(cudaLaunchKernelEx(&cfg, kern, pl.mapA[0], pl.mapA[1], pl.mapW, pl.mapO, pl.p));
   TCS_CUDA(cudaGetLastError());
   return TCS_OK;
+}
+
+static int conv_tc_max_ctas(const ConvTcPlan& pl, int* out) {
+#define TCS_TC_CASE(NN, EE, MM)                                                        \
+  if (pl.N == NN && pl.epi == EE && pl.msub == MM) {                                    \
+    if (pl.cg == 2) { if constexpr (NN >= 96 || EE == EPI_EPS) return max_ctas_t<NN, EE, MM, 2>(pl, out); } \
+    else return max_ctas_t<NN, EE, MM, 1>(pl, out);                                     \
+  }
+  TCS_TC_CASE(96, EPI_RAW_STATS, 2)
+  TCS_TC_CASE(96, EPI_PADDED, 2)
+  TCS_TC_CASE(96, EPI_PLAIN, 2)
+  TCS_TC_CASE(96, EPI_GN_FUSED, 2)
+  TCS_TC_CASE(192, EPI_RAW_STATS, 1)
+  TCS_TC_CASE(192, EPI_PADDED, 1)
+  TCS_TC_CASE(192, EPI_PLAIN, 1)
+  TCS_TC_CASE(192, EPI_GN_FUSED, 1)
+  TCS_TC_CASE(16, EPI_EPS, 2)
+#undef TCS_TC_CASE
+  return fail(TCS_ERR_UNSUPPORTED, "conv_tc: no kernel instance for this (N, epilogue, msub)");
 }
 
 int conv_tc_launch(const ConvTcPlan& pl, cudaStream_t st) {
@@ -1034,11 +1121,14 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, con
   if (p.nstage < 2) return fail(TCS_ERR_UNSUPPORTED, "conv_tc: stage does not fit shared memory twice");
   pl.smem = static_cast<size_t>(p.nstage) * p.stage_bytes + 1024 + EPI_SLAB_BYTES + EPI_BIAS_BYTES + EPI_FUSED_BYTES;
   p.epi = ea;
-  const int tiles = p.n_mtiles * p.n_ntiles;
+  TCS_CHECK(conv_tc_max_ctas(pl, &pl.max_ctas));
+  if (getenv("TCS_MAX_CTAS")) pl.max_ctas = atoi(getenv("TCS_MAX_CTAS"));   // test hook: pretend part of the device is taken
+  pl.coop_cluster = pl.cg == 2 && epi == EPI_GN_FUSED && coop_cluster_supported();
   pl.grid = conv_tc_grid(pl, g.B, sm_count);
   if (epi == EPI_GN_FUSED && (p.n_ntiles != 1 || pl.grid < p.tiles_per_img))
-    return fail(TCS_ERR_UNSUPPORTED, "conv_tc: fused GroupNorm needs one N tile and a whole image group on the GPU");
-  (void)tiles;
+    return fail(TCS_ERR_UNSUPPORTED,
+                "conv_tc: fused GroupNorm needs one N tile and a whole image group (" + std::to_string(p.tiles_per_img) +
+                    " CTAs) resident at once; the device can hold " + std::to_string(pl.max_ctas));
 
   const void* srcs[2] = {src0, src1};
   for (int s = 0; s < 2; ++s) {

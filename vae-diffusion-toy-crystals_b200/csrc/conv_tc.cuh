@@ -37,6 +37,8 @@ struct ConvTcPlan {
   int msub;    // 128-row sub-tiles per CTA tile
   int cg;      // 1 = one CTA per MMA, 2 = CTA pairs (tcgen05 cta_group::2, weights split across the pair)
   int grid;
+  int max_ctas = 0;          // CTAs of this kernel the device holds at once (cudaOccupancyMaxActiveClusters x 2 for pairs)
+  bool coop_cluster = false; // launch the fused-GroupNorm CTA pairs with the cooperative attribute as well
   size_t smem;
   bool valid = false;
 };

@@ -127,13 +127,21 @@ struct tcs_handle {
 
   // per-call state
   DevBuf cvec, tvec, tvals, coef, x, xpred, d0, eps, step_ctr, ycat_tmp, ycont_tmp;
+  DevBuf status;                          // device status word (bit 0: fp16 stash range exceeded in a fused GroupNorm layer)
   void* pinned = nullptr; size_t pinned_bytes = 0;
   cudaEvent_t ev_pinned = nullptr;
 
-  // graph cache
+  // graph cache.  The captured kernels hold the device pointers of the per-call buffers below, so the key carries the
+  // workspace generation: DevBuf::ensure bumps ws_gen whenever one of them is re-allocated (by tcs_sample with more
+  // steps / samples, or by tcs_score / tcs_debug_layer in between), which forces a re-capture.
   cudaGraphExec_t gexec = nullptr;
-  struct GKey { int n = -1, dup, sampler; const void *noise, *teps, *tx; float guidance; uint64_t seed, gidx; int nfe_rows; } gkey;
+  uint64_t ws_gen = 0;
+  struct GKey { int n = -1, dup, sampler; const void *noise, *teps, *tx; float guidance; uint64_t seed, gidx, gen; } gkey;
   int64_t graph_kernels = 0;
+
+  tcs_handle() {
+    for (DevBuf* b : {&cvec, &tvec, &tvals, &coef, &x, &xpred, &d0, &eps, &step_ctr}) b->gen = &ws_gen;
+  }
 
   ~tcs_handle() {
     if (gexec) cudaGraphExecDestroy(gexec);
@@ -268,11 +276,31 @@ static int build_plans(tcs_handle* h) {
     ea.bias = h->dw.at(std::string(kConv[id].key) + ".bias");
     ea.out = w.out; ea.partials = h->partials.as<float>(); ea.residual = w.residual; ea.ldo = w.ldo;
     ea.slots = slots_of(h, id);
+    ea.overflow = h->status.as<int>();
     if (w.epi == EPI_GN_FUSED) {
       ea.gamma = h->dw.at(std::string(w.gn) + ".weight");
       ea.beta = h->dw.at(std::string(w.gn) + ".bias");
     }
     TCS_CHECK(conv_tc_make_plan(&h->plan[id], g, w.s0, w.s1, h->wpack[id].as<__nv_bfloat16>(), w.epi, ea, h->sm_count));
+  }
+  // The fused-GroupNorm kernels are launched as CTA pairs WITH the cooperative attribute where the runtime accepts the
+  // combination.  Try it once here, outside any stream capture (a refused launch inside a capture would invalidate the
+  // captured graph): a full-width grid over a few images of the (uninitialised) workspace.
+  for (int id = 0; id < C_COUNT; ++id) {
+    if (!h->plan[id].coop_cluster) continue;
+    ConvTcPlan pl = h->plan[id];
+    const int B = h->chunk < 16 ? h->chunk : 16;
+    pl.p.n_mtiles = B * pl.p.tiles_per_img;
+    pl.grid = conv_tc_grid(pl, B, h->sm_count);
+    const int rc = conv_tc_launch(pl, h->stream);
+    const cudaError_t se = cudaStreamSynchronize(h->stream);
+    if (rc != TCS_OK || se != cudaSuccess) {
+      cudaGetLastError();
+      if (se != cudaSuccess && se != cudaErrorCooperativeLaunchTooLarge && se != cudaErrorInvalidValue)
+        return fail(TCS_ERR_CUDA, std::string("trial launch of a fused conv failed: ") + cudaGetErrorString(se));
+      for (int j = 0; j < C_COUNT; ++j) h->plan[j].coop_cluster = false;
+      break;
+    }
   }
   return TCS_OK;
 }
@@ -495,10 +523,30 @@ __global__ void cond_grid_kernel(int n, long long offset, long long n_total, flo
 extern "C" {
 
 const char* tcs_last_error(void) { return g_err.c_str(); }
+#ifndef TCS_SRC_HASH
+#define TCS_SRC_HASH "unknown"
+#endif
+// build.py passes the SHA-256 of every source and header of the library; __graft_entry__.build() and the tests compare
+// it with the tree, so that a prebuilt libtcs.so that does not match the sources is rebuilt / reported, never used silently
 const char* tcs_build_info(void) {
-  return "libtcs sm_100a: tcgen05 implicit-GEMM conv (bf16) + FFMA conv (fp32), built " __DATE__ " " __TIME__;
+  return "libtcs sm_100a: tcgen05 implicit-GEMM conv (bf16, bf16x3) + FFMA conv (fp32), built " __DATE__ " " __TIME__
+         " TCS_SRC_HASH=" TCS_SRC_HASH;
 }
 int64_t tcs_launch_count(const tcs_handle* h) { return h ? h->launches : 0; }
+int32_t tcs_check(tcs_handle* h) {
+  if (!h) return fail(TCS_ERR_BAD_ARGUMENT, "tcs_check: null handle");
+  TCS_CUDA(cudaSetDevice(h->cfg.device));
+  int bits = 0;
+  TCS_CUDA(cudaMemcpyAsync(&bits, h->status.p, 4, cudaMemcpyDeviceToHost, h->stream));
+  TCS_CUDA(cudaStreamSynchronize(h->stream));
+  if (bits) TCS_CUDA(cudaMemsetAsync(h->status.p, 0, 4, h->stream));
+  return bits & 0x7fffffff;
+}
+int32_t tcs_launch_mode(const tcs_handle* h) {
+  if (!h || !h->finalized || !h->use_tc) return 0;
+  const ConvTcPlan& pl = h->plan[C_D1B];
+  return (h->fuse_gn ? 1 : 0) | (pl.coop_cluster ? 2 : 0) | (pl.max_ctas << 8);
+}
 int32_t tcs_nfe(int32_t sampler, int32_t steps) { return sampler == TCS_SAMPLER_ODE ? 2 * steps + 1 : steps + 1; }
 
 void tcs_default_config(tcs_config* c) {
@@ -506,7 +554,7 @@ void tcs_default_config(tcs_config* c) {
   memset(c, 0, sizeof(*c));
   c->n_types = 4; c->y_cont_dim = 4; c->base_ch = 96; c->emb_dim = 128; c->cond_ch = 8; c->time_ch = 8;
   c->beta_min = 0.1; c->beta_max = 30.0;
-  c->precision = TCS_BF16; c->engine = TCS_ENGINE_AUTO; c->device = 0; c->chunk = 0; c->use_graph = 1;
+  c->precision = TCS_BF16; c->engine = TCS_ENGINE_AUTO; c->device = 0; c->chunk = 0; c->use_graph = 1; c->fuse_gn = 1;
 }
 
 int tcs_time_grid_host(int32_t steps, double t_end, float* ts) {
@@ -554,7 +602,7 @@ int tcs_create(tcs_handle** out, const tcs_config* cfg) {
   h->use_tc = eng == TCS_ENGINE_TCGEN05;
   {
     const char* e = getenv("TCS_FUSE_GN");   // 0 = keep conv -> raw fp32 -> gn_apply (A/B switch)
-    h->fuse_gn = h->use_tc && !(e && atoi(e) == 0);
+    h->fuse_gn = h->use_tc && cfg->fuse_gn != 0 && !(e && atoi(e) == 0);
     h->fuse_first = !(e && atoi(e) == 0);
   }
   h->chunk = cfg->chunk > 0 ? cfg->chunk : 2048;
@@ -564,6 +612,8 @@ int tcs_create(tcs_handle** out, const tcs_config* cfg) {
   TCS_CUDA(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
   TCS_CUDA(cudaEventCreateWithFlags(&h->ev_pinned, cudaEventDisableTiming));
   TCS_CHECK(h->step_ctr.ensure(16));
+  TCS_CHECK(h->status.ensure(16));
+  TCS_CUDA(cudaMemset(h->status.p, 0, 16));
   *out = h.release();
   return TCS_OK;
 }
@@ -816,6 +866,38 @@ int tcs_sde_update(tcs_handle* h, float* x, const float* eps, const float* noise
   return leave(h, user);
 }
 
+int tcs_ode_update(tcs_handle* h, int32_t mode, float* x, float* x_pred, float* d0, const float* eps, int32_t n, float t,
+                   float t_next, void* stream) {
+  if (!h || !x || !x_pred || !d0 || !eps || n < 0 || mode < STEP_ODE_PREDICT || mode > STEP_FINAL)
+    return fail(TCS_ERR_BAD_ARGUMENT, "tcs_ode_update: bad argument");
+  if (n == 0) return TCS_OK;
+  TCS_CUDA(cudaSetDevice(h->cfg.device));
+  cudaStream_t user = static_cast<cudaStream_t>(stream);
+  TCS_CHECK(enter(h, user));
+  const Sched s{h->cfg.beta_min, h->cfg.beta_max};
+  TCS_CHECK(h->coef.ensure(sizeof(StepCoef) * 8));
+  TCS_CHECK(ensure_pinned(h, sizeof(StepCoef) * 8 + 64));
+  StepCoef* c = static_cast<StepCoef*>(h->pinned);
+  memset(c, 0, sizeof(StepCoef) * 2);
+  const float tt[2] = {t, t_next};
+  for (int i = 0; i < 2; ++i) {   // row 0: schedule at t and dt of the step; row 1: schedule at t_next (the corrector's)
+    c[i].t = tt[i]; c[i].beta = s.beta(tt[i]); c[i].sigma = s.sigma(tt[i]); c[i].alpha = s.alpha(tt[i]);
+    c[i].dt = i == 0 ? t_next - t : 0.f;
+    c[i].g_sqrt_dt = sqrtf(c[i].beta) * sqrtf(fabsf(c[i].dt));
+  }
+  TCS_CUDA(cudaMemcpyAsync(h->coef.p, c, sizeof(StepCoef) * 2, cudaMemcpyHostToDevice, h->stream));
+  TCS_CUDA(cudaEventRecord(h->ev_pinned, h->stream));
+  StepArgs a{};
+  a.coef = h->coef.as<StepCoef>();
+  a.step_ptr = nullptr;
+  a.row_off = mode == STEP_ODE_CORRECT ? 1 : 0;
+  a.mode = mode; a.x = x; a.x_pred = x_pred; a.d0 = d0; a.eps = eps; a.n = n;
+  if (mode == STEP_FINAL) { a.out_img = x_pred; a.out_x0 = d0; }
+  ++h->launches;
+  TCS_CHECK(launch_step(a, h->stream));
+  return leave(h, user);
+}
+
 int tcs_sample(tcs_handle* h, const tcs_sample_args* args, void* stream) {
   TCS_CHECK(check_ready(h, "tcs_sample"));
   if (!args) return fail(TCS_ERR_BAD_ARGUMENT, "tcs_sample: null args");
@@ -848,7 +930,7 @@ int tcs_sample(tcs_handle* h, const tcs_sample_args* args, void* stream) {
   float* hts = reinterpret_cast<float*>(hc + steps + 2);
   if (steps >= 1) time_grid_host(steps, A.t_end, hts);
   else hts[0] = static_cast<float>(A.t_end) + static_cast<float>(1.0 - A.t_end);  // linspace(0,1,1) = [0]
-  const Sched sc{h->cfg.beta_min, h->cfg.beta_max};
+  const Sched sc = A.beta_max > 0.0 ? Sched{A.beta_min, A.beta_max} : Sched{h->cfg.beta_min, h->cfg.beta_max};
   for (int i = 0; i <= steps; ++i) {
     StepCoef c{};
     c.t = hts[i]; c.beta = sc.beta(c.t); c.sigma = sc.sigma(c.t); c.alpha = sc.alpha(c.t);
@@ -911,10 +993,11 @@ int tcs_sample(tcs_handle* h, const tcs_sample_args* args, void* stream) {
     if (h->cfg.use_graph) {
       tcs_handle::GKey k;
       k.n = n; k.dup = dup; k.sampler = A.sampler; k.noise = A.noise; k.teps = A.trace_eps; k.tx = A.trace_x;
-      k.guidance = A.guidance; k.seed = A.seed; k.gidx = A.global_index_offset; k.nfe_rows = 0;
+      k.guidance = A.guidance; k.seed = A.seed; k.gidx = A.global_index_offset; k.gen = h->ws_gen;
       const bool same = h->gexec && h->gkey.n == k.n && h->gkey.dup == k.dup && h->gkey.sampler == k.sampler &&
                         h->gkey.noise == k.noise && h->gkey.teps == k.teps && h->gkey.tx == k.tx &&
-                        h->gkey.guidance == k.guidance && h->gkey.seed == k.seed && h->gkey.gidx == k.gidx;
+                        h->gkey.guidance == k.guidance && h->gkey.seed == k.seed && h->gkey.gidx == k.gidx &&
+                        h->gkey.gen == k.gen;
       if (!same) {
         if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
         const int64_t before = h->launches;

@@ -19,14 +19,15 @@ class TcsConfig(C.Structure):
     _fields_ = [("n_types", C.c_int32), ("y_cont_dim", C.c_int32), ("base_ch", C.c_int32), ("emb_dim", C.c_int32),
                 ("cond_ch", C.c_int32), ("time_ch", C.c_int32), ("beta_min", C.c_double), ("beta_max", C.c_double),
                 ("precision", C.c_int32), ("engine", C.c_int32), ("device", C.c_int32), ("chunk", C.c_int32),
-                ("use_graph", C.c_int32)]
+                ("use_graph", C.c_int32), ("fuse_gn", C.c_int32)]
 
 
 class TcsSampleArgs(C.Structure):
     _fields_ = [("sampler", C.c_int32), ("n", C.c_int32), ("steps", C.c_int32), ("guidance", C.c_float),
                 ("t_end", C.c_double), ("y_cat", C.c_void_p), ("y_cont", C.c_void_p), ("x_init", C.c_void_p),
                 ("noise", C.c_void_p), ("seed", C.c_uint64), ("global_index_offset", C.c_uint64),
-                ("x_out", C.c_void_p), ("trace_eps", C.c_void_p), ("trace_x", C.c_void_p), ("x0_hat", C.c_void_p)]
+                ("x_out", C.c_void_p), ("trace_eps", C.c_void_p), ("trace_x", C.c_void_p), ("x0_hat", C.c_void_p),
+                ("beta_min", C.c_double), ("beta_max", C.c_double)]
 
 
 class TcsPriorConfig(C.Structure):
@@ -62,10 +63,14 @@ SIGNATURES = {
                                      C.c_void_p]),
     "tcs_sde_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float,
                                  C.c_uint64, C.c_uint64, C.c_int32, C.c_void_p]),
+    "tcs_ode_update": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                 C.c_float, C.c_float, C.c_void_p]),
     "tcs_time_grid_host": (C.c_int, [C.c_int32, C.c_double, C.POINTER(C.c_float)]),
     "tcs_schedule_host": (C.c_int, [C.c_double, C.c_double, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                     C.POINTER(C.c_float)]),
     "tcs_launch_count": (C.c_int64, [C.c_void_p]),
+    "tcs_check": (C.c_int32, [C.c_void_p]),
+    "tcs_launch_mode": (C.c_int32, [C.c_void_p]),
     "tcs_build_info": (C.c_char_p, []),
     "tcs_last_error": (C.c_char_p, []),
     "tcs_debug_layer": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,

@@ -17,6 +17,7 @@ from __future__ import annotations
 import ctypes as C
 import math
 import os
+import warnings
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
@@ -44,6 +45,17 @@ def _as_f32(t: torch.Tensor, device) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 # parameter container with the reference's state-dict layout
 # ------------------------------------------------------------------------------------------------
+def _gn_groups(ch: int, max_groups: int = 8) -> int:
+    """Largest group count <= max_groups that divides ch (reference :89-94)."""
+    g = min(max_groups, ch)
+    while g > 1 and ch % g:
+        g -= 1
+    return g
+
+
+_SUPPORTED_ARCH = dict(base_ch=96, emb_dim=128, cond_ch=8, time_ch=8)
+
+
 def _parameter_plan(n_types, y_cont_dim, base_ch, emb_dim, cond_ch, time_ch) -> List[Tuple[str, nn.Module]]:
     """(dotted state-dict prefix, torch layer) in the order the reference constructor creates them,
     so that default initialisation under a given torch seed is identical."""
@@ -64,16 +76,16 @@ def _parameter_plan(n_types, y_cont_dim, base_ch, emb_dim, cond_ch, time_ch) -> 
 
     def block(name, i, o):
         conv(f"{name}.net.0", i, o, 3)
-        plan.append((f"{name}.net.1", lambda: nn.GroupNorm(8, o)))
+        plan.append((f"{name}.net.1", lambda: nn.GroupNorm(_gn_groups(o), o)))
         conv(f"{name}.net.3", o, o, 3)
-        plan.append((f"{name}.net.4", lambda: nn.GroupNorm(8, o)))
+        plan.append((f"{name}.net.4", lambda: nn.GroupNorm(_gn_groups(o), o)))
 
     block("down1", 1 + cond_ch + time_ch, b)
     conv("ds1", b, b, 4)
     block("down2", b, 2 * b)
     conv("ds2", 2 * b, 2 * b, 4)
     block("mid", 2 * b, 2 * b)
-    plan.append(("attn.norm", lambda: nn.GroupNorm(8, 2 * b)))
+    plan.append(("attn.norm", lambda: nn.GroupNorm(_gn_groups(2 * b), 2 * b)))
     conv("attn.qkv", 2 * b, 6 * b, 1)
     conv("attn.proj", 2 * b, 2 * b, 1)
     conv("us2_conv", 2 * b, 2 * b, 3)
@@ -105,6 +117,11 @@ class CondUNetTiny(nn.Module):
             raise ValueError(f"ch ({2 * int(base_ch)}) must be divisible by num_heads (4)")
         self._arch = dict(n_types=self.n_types, y_cont_dim=self.y_cont_dim, base_ch=int(base_ch), emb_dim=int(emb_dim),
                           cond_ch=int(cond_ch), time_ch=int(time_ch))
+        bad = {k: self._arch[k] for k, v in _SUPPORTED_ARCH.items() if self._arch[k] != v}
+        if bad:   # fail at construction, not at the first forward (the reference's own default base_ch=32 is one of these)
+            raise NotImplementedError(
+                f"libtcs is built for the CLI/README architecture base_ch=96, emb_dim=128, cond_ch=8, time_ch=8 only; "
+                f"got {bad}. Pass base_ch=96 explicitly (the reference constructor defaults to 32).")
         for path, make in _parameter_plan(**self._arch):
             parent: nn.Module = self
             parts = path.split(".")
@@ -123,13 +140,39 @@ class CondUNetTiny(nn.Module):
             raise ValueError(f"engine must be one of {sorted(_ENGINES)}, got {self.engine!r}")
         self._handle: Optional[C.c_void_p] = None
         self._handle_key = None
+        self._checksum = None
+        self._key_by_checksum = False
+        self._fuse_gn = True   # cleared (sticky) when a fused GroupNorm layer reports values beyond its fp16 staging range
+        # VPSDE constants baked into the handle: used by the tcs_sde_update / tcs_ode_update test hooks only; the
+        # samplers pass their `sde` per call (tcs_sample_args.beta_min/beta_max), so a different VPSDE does not
+        # rebuild the handle
         self._sde_key: Tuple[float, float] = (0.1, 30.0)
 
     # -- engine management --------------------------------------------------------------------
     def _weights_key(self):
         ps = list(self.parameters())
-        return (ps[0].device, self.precision, self.engine, self.chunk, self.use_graph, self._sde_key,
-                tuple((p.data_ptr(), p._version) for p in ps))
+        # adopted (foreign) modules are re-copied on every call, which bumps _version without changing a bit: for them
+        # the checksum alone decides
+        ver = None if self._key_by_checksum else tuple((p.data_ptr(), p._version) for p in ps)
+        return (ps[0].device, self.precision, self.engine, self.chunk, self.use_graph, self._sde_key, ver, self._checksum,
+                self._fuse_gn)
+
+    def weights_checksum(self) -> Tuple[int, float]:
+        """Device-side checksum of all parameters (bit pattern sum + sum of squares): catches in-place updates made through
+        ``.data`` (the training loop's EMA update, scripts/train_sde_score_model.py:239-240), which do not bump
+        ``_version``.  One small reduction and a host read."""
+        flat = torch.cat([p.detach().reshape(-1) for p in self.parameters()])
+        a = flat.view(torch.int32).sum(dtype=torch.int64)
+        b = (flat.double() ** 2).sum()
+        return int(a.item()), float(b.item())
+
+    def refresh(self) -> "CondUNetTiny":
+        """Re-read the parameters on the next call if they changed behind autograd's back (``p.data.mul_(...)``).
+        The samplers call this themselves (a sampling job costs far more than the check); ``forward`` /
+        ``predict_eps_cfg`` do not (they may sit in a per-step loop), so call it after editing ``.data`` by hand."""
+        if next(self.parameters()).device.type == "cuda":
+            self._checksum = self.weights_checksum()
+        return self
 
     def _release(self):
         if self._handle is not None:
@@ -170,6 +213,7 @@ class CondUNetTiny(nn.Module):
         cfg.device = dev.index if dev.index is not None else torch.cuda.current_device()
         cfg.chunk = self.chunk
         cfg.use_graph = 1 if self.use_graph else 0
+        cfg.fuse_gn = 1 if self._fuse_gn else 0
         h = C.c_void_p()
         _cabi.check(L.tcs_create(C.byref(h), C.byref(cfg)))
         try:
@@ -200,7 +244,8 @@ def adopt(model: nn.Module, precision: Optional[str] = None) -> CondUNetTiny:
     """Accept ANY module that carries the reference ``CondUNetTiny`` state dict (e.g. the training script's ``model`` /
     ``ema_model``, scripts/train_sde_score_model.py:263-279) and return the libtcs-backed equivalent, so the training-time
     sampling hook ``save_sde_samples(model=sample_model, ...)`` runs on the fast path unchanged.  The architecture is read
-    off the tensor shapes; the weights are re-read whenever the source module's parameters changed (EMA updates)."""
+    off the tensor shapes; the weights are copied on every call and re-packed whenever their checksum changed (the EMA
+    update writes through ``.data``, which autograd's version counter does not record)."""
     if isinstance(model, CondUNetTiny):
         return model
     sd = model.state_dict()
@@ -211,21 +256,44 @@ def adopt(model: nn.Module, precision: Optional[str] = None) -> CondUNetTiny:
                     cond_ch=int(sd["to_cond_map.weight"].shape[0]), time_ch=int(sd["to_time_map.weight"].shape[0]))
     except KeyError as e:
         raise TypeError(f"model does not carry the CondUNetTiny state dict (missing {e})") from None
-    ver = tuple((k, v.data_ptr(), v._version) for k, v in sd.items())
+    # A foreign module's parameters may be updated through `.data` (the reference's EMA loop), which `_version` does not
+    # see: always copy the state dict (device-to-device, 13 MB) and let the checksum decide whether libtcs re-packs.
     hit = _adopted.get(id(model))
-    if hit is not None and hit[0] == ver:
-        return hit[1]
-    fast = hit[1] if hit is not None else CondUNetTiny(**arch, precision=precision)
-    fast.load_state_dict(sd)
+    fast = hit[1] if hit is not None and hit[0] == tuple(sorted(arch.items())) else CondUNetTiny(**arch, precision=precision)
+    with torch.no_grad():
+        fast.load_state_dict(sd)
     fast = fast.to(next(iter(sd.values())).device).eval()
-    _adopted[id(model)] = (ver, fast)
+    fast._key_by_checksum = True
+    fast.refresh()
+    _adopted[id(model)] = (tuple(sorted(arch.items())), fast)
     return fast
+
+
+def _run_checked(model: CondUNetTiny, enqueue) -> None:
+    """enqueue(handle) once; if libtcs then reports that a fused GroupNorm layer saw pre-norm activations beyond the fp16
+    staging range (|v| > 65504: possible with untrained / exploding weights, never seen with the README model), switch
+    this model to the unfused GroupNorm path for good and run the call again, so that a clipped result is never returned."""
+    L = _cabi.lib()
+    for attempt in (0, 1):
+        h = model.engine_handle()
+        enqueue(h)
+        bits = int(L.tcs_check(h))
+        if bits < 0:
+            _cabi.check(bits)
+        if not (bits & 1):
+            return
+        if attempt == 1 or not model._fuse_gn:
+            raise _cabi.TcsError("libtcs: activation range error persists on the unfused GroupNorm path")
+        warnings.warn("toycrystals_b200: a pre-GroupNorm activation exceeded the fp16 staging range of the fused conv "
+                      "epilogue; re-running on the unfused GroupNorm path (kept for this model from now on)")
+        model._fuse_gn = False
 
 
 def _score(model: CondUNetTiny, x_t, t, y_cat, y_cont, guidance: float) -> torch.Tensor:
     model = adopt(model)
-    h = model.engine_handle()
     dev = next(model.parameters()).device
+    if dev.type != "cuda":
+        model.engine_handle()   # raises: no CPU fallback
     B, Cc, H, W = x_t.shape
     if Cc != 1 or H != 64 or W != 64:
         raise NotImplementedError(f"libtcs evaluates [B,1,64,64] images only (got {tuple(x_t.shape)})")
@@ -237,8 +305,9 @@ def _score(model: CondUNetTiny, x_t, t, y_cat, y_cont, guidance: float) -> torch
     yk = _as_f32(y_cont, dev)
     out = torch.empty((B, 1, 64, 64), device=dev, dtype=torch.float32)
     with torch.cuda.device(dev):
-        _cabi.check(_cabi.lib().tcs_score(h, x.data_ptr(), tt.data_ptr(), yc.data_ptr(), yk.data_ptr(), B,
-                                          float(guidance), out.data_ptr(), _stream_ptr(dev)))
+        _run_checked(model, lambda h: _cabi.check(_cabi.lib().tcs_score(
+            h, x.data_ptr(), tt.data_ptr(), yc.data_ptr(), yk.data_ptr(), B, float(guidance), out.data_ptr(),
+            _stream_ptr(dev))))
     return out
 
 
@@ -290,20 +359,23 @@ def _sample(model: CondUNetTiny, sde: VPSDE, y_cat, y_cont, img_shape, n_steps, 
                            "GPU (no CPU fallback)")
     if H != 64 or W != 64:
         raise NotImplementedError(f"libtcs samples 64x64 images only (got {H}x{W})")
-    h = model.engine_handle(sde)
+    model.refresh()
     L = _cabi.lib()
     n_steps = int(n_steps)
     yc = y_cat.to(torch.int64).contiguous()
     yk = _as_f32(y_cont, device)
-    if x_init is None:
+    if x_init is None and seed is None:
         # same draw as the reference: one torch.randn from the device's global generator
         x_init = torch.randn((B, Cc, H, W), device=device)
-    x_init = _as_f32(x_init, device)
+    # x_init None with a seed: the kernel draws x_T from Philox keyed (seed, global_index_offset + i), so `seed=` alone
+    # reproduces a run and a sharded job equals the unsharded one
+    x_init = None if x_init is None else _as_f32(x_init, device)
     noise_t = None
     if sampler == _cabi.SAMPLER_SDE:
         if isinstance(noise, str) and noise == "torch":
             # reference-identical consumption of the global generator: one randn_like per step
-            noise_t = torch.stack([torch.randn_like(x_init) for _ in range(n_steps)]) if n_steps else None
+            noise_t = (torch.stack([torch.randn((B, 1, 64, 64), device=device) for _ in range(n_steps)])
+                       if n_steps else None)
         elif torch.is_tensor(noise):
             noise_t = _as_f32(noise, device)
             if noise_t.shape[0] != n_steps or noise_t[0].numel() != B * 4096:
@@ -321,11 +393,12 @@ def _sample(model: CondUNetTiny, sde: VPSDE, y_cat, y_cont, img_shape, n_steps, 
     a.sampler, a.n, a.steps = sampler, B, n_steps
     a.guidance, a.t_end = float(guidance_scale), t_end
     a.y_cat, a.y_cont = yc.data_ptr(), yk.data_ptr()
-    a.x_init, a.noise = x_init.data_ptr(), _ptr(noise_t)
+    a.x_init, a.noise = _ptr(x_init), _ptr(noise_t)
+    a.beta_min, a.beta_max = float(sde.beta_min), float(sde.beta_max)
     a.seed, a.global_index_offset = int(seed) & (2 ** 64 - 1), int(global_index_offset)
     a.x_out, a.trace_eps, a.trace_x, a.x0_hat = out.data_ptr(), _ptr(tr_eps), _ptr(tr_x), _ptr(x0h)
     with torch.cuda.device(device):
-        _cabi.check(L.tcs_sample(h, C.byref(a), _stream_ptr(device)))
+        _run_checked(model, lambda h: _cabi.check(L.tcs_sample(h, C.byref(a), _stream_ptr(device))))
     if noise_t is not None:
         noise_t.record_stream(torch.cuda.current_stream(device))
     if return_trace:

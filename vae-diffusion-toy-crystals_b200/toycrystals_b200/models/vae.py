@@ -107,6 +107,8 @@ class CondVAE(nn.Module):
         if self.training and self.cond_drop > 0.0:
             raise NotImplementedError("condition dropout is a training-time feature: call .eval() (training is out of "
                                       "scope of toycrystals_b200)")
+        if (z_mean is None) != (z_std is None):
+            raise ValueError("decode: give both z_mean and z_std or neither")
         h = self.engine_handle()
         dev = self.dec_fc.weight.device
         B = int(z.shape[0])
