@@ -20,12 +20,26 @@ def rel_l2(a, b):
     return orc.rel_l2(a, b)
 
 
+TEST_CHUNK = 128   # images per network pass in the tests; the library default (2048) needs 15-35 GB of workspace per model
+MAX_MODELS = 4
+
+
 def model(precision: str, engine: str = "auto", seed: int = 0, chunk: int = 0, use_graph: bool = True) -> CondUNetTiny:
+    """Cached libtcs-backed model.  chunk = 0 -> TEST_CHUNK (pass chunk=2048 for the production pass size); the cache
+    keeps the MAX_MODELS most recently used models and frees the others' device workspaces."""
+    chunk = chunk or TEST_CHUNK
     key = (precision, engine, seed, chunk, use_graph)
-    if key not in _models:
-        m = CondUNetTiny(**CFG, precision=precision, engine=engine, chunk=chunk, use_graph=use_graph)
-        m.load_state_dict(orc.default_init_state_dict(seed))
-        _models[key] = m.to("cuda").eval()
+    if key in _models:
+        _models[key] = _models.pop(key)          # most recently used last
+        return _models[key]
+    while len(_models) >= MAX_MODELS:
+        old = _models.pop(next(iter(_models)))
+        old._release()
+        del old
+        torch.cuda.empty_cache()
+    m = CondUNetTiny(**CFG, precision=precision, engine=engine, chunk=chunk, use_graph=use_graph)
+    m.load_state_dict(orc.default_init_state_dict(seed))
+    _models[key] = m.to("cuda").eval()
     return _models[key]
 
 

@@ -10,7 +10,8 @@ import torch
 pytestmark = pytest.mark.gpu
 
 TOL_EPS = {"fp32": 1e-4, "bf16": 2e-2}
-MODES = [("fp32", "simt"), ("bf16", "simt"), ("bf16", "tcgen05")]
+# fp32/tcgen05 = the fp32 mode on the tensor pipe: operands as bf16 (hi, lo) pairs, three MMAs per product (bf16x3)
+MODES = [("fp32", "simt"), ("bf16", "simt"), ("bf16", "tcgen05"), ("fp32", "tcgen05")]
 
 
 def _pu():
@@ -74,7 +75,7 @@ def test_layers_against_oracle(precision, engine):
         want = taps[name].permute(0, 2, 3, 1)
         err = pu.rel_l2(got, want)
         worst = max(worst, err)
-        assert err < (2e-5 if precision == "fp32" else 1.5e-2), (name, err)
+        assert err < ((2e-5 if engine == "simt" else 5e-5) if precision == "fp32" else 1.5e-2), (name, err)
     print(f"{precision}/{engine}: worst layer rel-L2 {worst:.3e}")
 
 
@@ -262,7 +263,7 @@ def _zero_out_model(precision):
     from toycrystals_b200.models.sde_score_model import CondUNetTiny
     sd = orc.default_init_state_dict(1)
     sd["out.weight"].zero_(); sd["out.bias"].zero_()
-    m = CondUNetTiny(**pu.CFG, precision=precision)
+    m = CondUNetTiny(**pu.CFG, precision=precision, chunk=2048)
     m.load_state_dict(sd)
     return m.cuda().eval()
 
@@ -300,7 +301,7 @@ def test_full_size_determinism_and_condition_grid():
     import toycrystals_oracle as orc
     from toycrystals_b200.models import sde_score_model as shim
     n = 1024
-    m = pu.model("bf16", "tcgen05", seed=1)
+    m = pu.model("bf16", "tcgen05", seed=1, chunk=2048)
     sde = shim.VPSDE(0.1, 30.0)
     yc, yk = shim.condition_grid(m, n, math.pi / 3, "cuda")
     oc, ok = orc.condition_grid(n, 4, 4)
@@ -341,7 +342,7 @@ def test_c1_full_config_against_the_reference(golden_dir):
     y_cat, y_cont = orc.condition_grid(g["n"], 4, 4)
     x_init = torch.randn((g["n"], 1, 64, 64), generator=torch.Generator().manual_seed(g["seed_x"]))
     sde = shim.VPSDE(0.1, 30.0)
-    for precision, engine in (("fp32", "simt"), ("bf16", "tcgen05")):
+    for precision, engine in (("fp32", "simt"), ("fp32", "tcgen05"), ("bf16", "tcgen05")):
         m = pu.model(precision, engine, seed=1)
         img, tr = shim.sample_probability_flow_ode(m, sde, y_cat.cuda(), y_cont.cuda(), (g["n"], 1, 64, 64),
                                                    n_steps=g["steps"], guidance_scale=g["cfg"], t_end=g["t_end"],
@@ -356,8 +357,10 @@ def test_c1_full_config_against_the_reference(golden_dir):
         print(f"C1 {precision}/{engine}: x0_hat rel-L2 {x0_err:.3e}, mismatched pixels {mism:.4%}, final eps (teacher-forced) {e_err:.3e}")
         assert e_err < TOL_EPS[precision]
         # stated per-pixel tolerance for final PF-ODE samples (measured on B200: fp32 3.8e-7 / 0 pixels, bf16 1.3e-3 / 0.08 %)
-        if precision == "fp32":
+        if precision == "fp32" and engine == "simt":
             assert x0_err < 1e-5 and mism < 1e-4, (x0_err, mism)
+        elif precision == "fp32":      # bf16x3 on the tensor pipe: the stated final-sample tolerance
+            assert x0_err < 1e-3 and mism < 5e-3, (x0_err, mism)
         else:
             assert x0_err < 1e-2 and mism < 1e-2, (x0_err, mism)
 
@@ -404,7 +407,7 @@ def test_output_conv_variants_agree(monkeypatch):
     outs = []
     for flag in ("1", "0"):
         monkeypatch.setenv("TCS_EPS_KXN", flag)
-        m = shim.CondUNetTiny(**orc.DEFAULT_CFG, precision="bf16")
+        m = shim.CondUNetTiny(**orc.DEFAULT_CFG, precision="bf16", chunk=64)
         m.load_state_dict(sd)
         m = m.to("cuda").eval()
         outs.append((shim.predict_eps_cfg(m, x, t, y_cat, y_cont, 1.5), shim.predict_eps_cfg(m, x, t, y_cat, y_cont, 0.0)))
@@ -432,7 +435,7 @@ def test_tma_store_epilogues_match_per_lane_stores(monkeypatch):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
-        m = shim.CondUNetTiny(**orc.DEFAULT_CFG, precision="bf16")
+        m = shim.CondUNetTiny(**orc.DEFAULT_CFG, precision="bf16", chunk=64)
         m.load_state_dict(sd)
         m = m.to("cuda").eval()
         outs.append(shim.predict_eps_cfg(m, x, t, y_cat, y_cont, 1.5).clone())
@@ -458,7 +461,7 @@ def test_full_size_pass_teacher_forced_against_the_oracle(precision, engine):
     from toycrystals_b200.models import sde_score_model as shim
     _oracle_on_cuda()
     n = 1024
-    m = pu.model(precision, engine, seed=1)
+    m = pu.model(precision, engine, seed=1, chunk=2048)
     sd = {k: v.cuda() for k, v in orc.default_init_state_dict(1).items()}
     yc, yk = shim.condition_grid(m, n, math.pi / 3, "cuda")
     g = torch.Generator().manual_seed(21)
@@ -488,9 +491,11 @@ def test_ode_update_kernels_are_bit_exact_vs_torch_expressions():
     sde = VPSDE(0.1, 30.0)
     g = torch.Generator().manual_seed(6)
     n = 5
-    x = (torch.randn((n, 1, 64, 64), generator=g) * 30).cuda()
-    e0, e1 = torch.randn((n, 1, 64, 64), generator=g).cuda(), torch.randn((n, 1, 64, 64), generator=g).cuda()
-    t, t_next = torch.tensor(0.3712, device="cuda"), torch.tensor(0.3651, device="cuda")
+    # expectations in torch CPU fp32: libtcs evaluates the schedule (exp, sqrt) on the host; torch's CUDA exp may differ
+    # from the CPU one by an ulp, and sigma(t_end) = sqrt(1 - alpha^2) amplifies an ulp of alpha 1000-fold
+    x = torch.randn((n, 1, 64, 64), generator=g) * 30
+    e0, e1 = torch.randn((n, 1, 64, 64), generator=g), torch.randn((n, 1, 64, 64), generator=g)
+    t, t_next = torch.tensor(0.3712), torch.tensor(0.3651)
     dt = t_next - t
 
     def drift(xx, ee, tt):
@@ -501,22 +506,55 @@ def test_ode_update_kernels_are_bit_exact_vs_torch_expressions():
     d_want = drift(x, e0, t)
     xe_want = x + d_want * dt
     x_want = x + 0.5 * (d_want + drift(xe_want, e1, t_next)) * dt
-    xs, xp, d0 = x.clone(), torch.empty_like(x), torch.empty_like(x)
-    _cabi.check(L.tcs_ode_update(h, 1, xs.data_ptr(), xp.data_ptr(), d0.data_ptr(), e0.data_ptr(), n, float(t), float(t_next), None))
+    xs, xp, d0 = x.cuda(), torch.empty_like(x).cuda(), torch.empty_like(x).cuda()
+    e0c, e1c = e0.cuda(), e1.cuda()
+    _cabi.check(L.tcs_ode_update(h, 1, xs.data_ptr(), xp.data_ptr(), d0.data_ptr(), e0c.data_ptr(), n, float(t), float(t_next), None))
     torch.cuda.synchronize()
-    assert torch.equal(d0, d_want) and torch.equal(xp, xe_want) and torch.equal(xs, x)
-    _cabi.check(L.tcs_ode_update(h, 2, xs.data_ptr(), xp.data_ptr(), d0.data_ptr(), e1.data_ptr(), n, float(t), float(t_next), None))
+    assert torch.equal(d0.cpu(), d_want) and torch.equal(xp.cpu(), xe_want) and torch.equal(xs.cpu(), x)
+    _cabi.check(L.tcs_ode_update(h, 2, xs.data_ptr(), xp.data_ptr(), d0.data_ptr(), e1c.data_ptr(), n, float(t), float(t_next), None))
     torch.cuda.synchronize()
-    assert torch.equal(xs, x_want)
+    assert torch.equal(xs.cpu(), x_want)
     # final projection at t_end
-    te = torch.tensor(0.005, device="cuda")
+    te = torch.tensor(0.005)
     a, sg = sde.alpha(te), sde.sigma(te)
     x0_want = (x - sg * e0) / torch.clamp(a, min=1e-6)
     img_want = ((x0_want + 1.0) * 0.5).clamp(0.0, 1.0)
-    xs = x.clone()
-    _cabi.check(L.tcs_ode_update(h, 3, xs.data_ptr(), xp.data_ptr(), d0.data_ptr(), e0.data_ptr(), n, float(te), float(te), None))
+    xs = x.cuda()
+    _cabi.check(L.tcs_ode_update(h, 3, xs.data_ptr(), xp.data_ptr(), d0.data_ptr(), e0c.data_ptr(), n, float(te), float(te), None))
     torch.cuda.synchronize()
-    assert torch.equal(d0, x0_want) and torch.equal(xp, img_want)
+    assert torch.equal(d0.cpu(), x0_want) and torch.equal(xp.cpu(), img_want)
+
+
+def test_update_kernels_are_bit_identical_at_scale():
+    """The update kernels divide by a launch-uniform sigma / alpha through a hoisted reciprocal (three FFMA per quotient,
+    the fast path of IEEE division).  260k values per case, |x| up to 1e4 and eps up to 1e4 as on the random-weight
+    trajectory, several times of the grid: every bit must equal torch's fp32 expression (CPU, true division)."""
+    pu = _pu()
+    from toycrystals_b200 import _cabi
+    from toycrystals_b200.models.sde_score_model import VPSDE
+    m = pu.model("fp32", "simt")
+    h = m.engine_handle(VPSDE(0.1, 30.0))
+    L = _cabi.lib()
+    sde = VPSDE(0.1, 30.0)
+    g = torch.Generator().manual_seed(16)
+    n = 64
+    for tv, tn, scale in ((1.0, 0.9934, 1.0), (0.3712, 0.3651, 300.0), (0.0051, 0.005, 1e4)):
+        x = torch.randn((n, 1, 64, 64), generator=g) * scale
+        eps = torch.randn((n, 1, 64, 64), generator=g) * (1.0 + scale)
+        z = torch.randn((n, 1, 64, 64), generator=g)
+        t, t_next = torch.tensor(tv), torch.tensor(tn)
+        beta, sigma, dt = sde.beta(t), sde.sigma(t), t_next - t
+        want = x + ((-0.5 * beta * x) - (beta * (-eps / sigma))) * dt + torch.sqrt(beta) * torch.sqrt(torch.abs(dt)) * z
+        got, ec, zc = x.cuda(), eps.cuda(), z.cuda()
+        _cabi.check(L.tcs_sde_update(h, got.data_ptr(), ec.data_ptr(), zc.data_ptr(), n, float(t), float(t_next), 0, 0, 0, None))
+        torch.cuda.synchronize()
+        assert torch.equal(got.cpu(), want), (tv, float((got.cpu() - want).abs().max()))
+        a, sg = sde.alpha(t), sde.sigma(t)
+        x0_want = (x - sg * eps) / torch.clamp(a, min=1e-6)
+        xs, xp, d0 = x.cuda(), torch.empty_like(x).cuda(), torch.empty_like(x).cuda()
+        _cabi.check(L.tcs_ode_update(h, 3, xs.data_ptr(), xp.data_ptr(), d0.data_ptr(), ec.data_ptr(), n, float(t), float(t), None))
+        torch.cuda.synchronize()
+        assert torch.equal(d0.cpu(), x0_want), tv
 
 
 def test_graph_cache_follows_workspace_reallocation():
@@ -533,13 +571,12 @@ def test_graph_cache_follows_workspace_reallocation():
     def run(m, steps):
         return shim.sample_reverse_sde_euler_maruyama(m, sde, yc, yk, (4, 1, 64, 64), n_steps=steps, guidance_scale=1.5,
                                                       t_end=0.005, x_init=x0, seed=0).clone()
-    fresh = lambda: pu.model("bf16", "tcgen05", seed=1, chunk=8 + run.calls)   # a new handle per reference run
-    run.calls = 0
+    plain = pu.model("bf16", "tcgen05", seed=1, chunk=64, use_graph=False)   # no graph: the ground truth
     m = pu.model("bf16", "tcgen05", seed=1, chunk=64)
     a50 = run(m, 50)
     a300 = run(m, 300)           # tvec / tvals / coef grow -> the old graph would replay freed pointers
-    run.calls += 1
-    assert torch.equal(a300, run(fresh(), 300))
+    assert torch.equal(a300, run(plain, 300))
+    assert torch.equal(a50, run(plain, 50))
     # a large tcs_score between two identical sampling calls grows cvec / tvec / eps
     yc2, yk2 = shim.condition_grid(m, 600, math.pi / 3, "cuda")
     shim.predict_eps_cfg(m, torch.randn((600, 1, 64, 64), device="cuda"), torch.full((600,), 0.5, device="cuda"), yc2, yk2, 1.5)
@@ -581,7 +618,7 @@ def test_weight_updates_through_data_are_seen():
     x0 = torch.randn((3, 1, 64, 64), generator=torch.Generator().manual_seed(4)).cuda()
 
     def build():
-        m = shim.CondUNetTiny(**orc.DEFAULT_CFG, precision="bf16")
+        m = shim.CondUNetTiny(**orc.DEFAULT_CFG, precision="bf16", chunk=64)
         m.load_state_dict(sd)
         return m.cuda().eval()
 
@@ -642,7 +679,7 @@ def test_fused_groupnorm_stash_range_is_guarded():
     y_cat, y_cont = (t.cuda() for t in orc.condition_grid(5, 4, 4))
     x = torch.randn((5, 1, 64, 64), generator=torch.Generator().manual_seed(12)).cuda()
     t = torch.full((5,), 0.37).cuda()
-    m = shim.CondUNetTiny(**orc.DEFAULT_CFG, precision="bf16")
+    m = shim.CondUNetTiny(**orc.DEFAULT_CFG, precision="bf16", chunk=64)
     m.load_state_dict(big)
     m = m.cuda().eval()
     with pytest.warns(UserWarning, match="fp16 staging range"):

@@ -273,3 +273,39 @@ def test_ddim_jobs_larger_than_one_chunk():
     e = m(z, t, y_cat, y_cont)
     e_sub = m(z[lo:hi], t[lo:hi], y_cat[lo:hi], y_cont[lo:hi])
     assert torch.equal(e_sub, e[lo:hi])
+
+
+# ---- round 2: BASELINE configs[3] at full size against the oracle ---------------------------------------------------
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_full_size_forward_and_decode_against_the_oracle(precision):
+    """n = 4096 (configs[3]): eps at three timesteps and the decode against the oracle evaluated by PyTorch on the GPU in
+    IEEE fp32 (TF32 off) - the golden vectors hold a tiny n only."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.set_float32_matmul_precision("highest")
+    m, sd, cfg = prior(precision)
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    n = 4096
+    g = torch.Generator().manual_seed(17)
+    z = (torch.randn((n, 32), generator=g) * 2.0).cuda()
+    y_cat, y_cont = (t.cuda() for t in orc.condition_grid(n, 4, 4))
+    for tv in (999, 500, 0):
+        t = torch.full((n,), tv, dtype=torch.int64, device="cuda")
+        with torch.no_grad():
+            want = po.film_prior(sdc, cfg, z, t, y_cat, y_cont)
+        got = m(z, t, y_cat, y_cont)
+        err = orc.rel_l2(got, want)
+        rows = ((got - want).norm(dim=1) / want.norm(dim=1)).max().item()
+        print(f"prior {precision} n={n} t={tv}: eps rel-L2 {err:.3e}, worst row {rows:.3e}")
+        assert err < TOL[precision], (tv, err)
+        assert rows < 3 * TOL[precision], (tv, rows)
+    v = vae(precision)
+    vsd = {k: t.cuda() for k, t in po.vae_default_init(2).items()}
+    zn = torch.randn((n, 32), generator=g).cuda()
+    with torch.no_grad():
+        want = po.vae_decode(vsd, po.VAE_CFG, zn, y_cat, y_cont)
+    got = v.decode(zn, y_cat, y_cont)
+    tol = 2e-5 if precision == "fp32" else 1e-2
+    assert float((got - want).abs().max()) < tol, float((got - want).abs().max())
+    with pytest.raises(ValueError, match="both z_mean and z_std"):
+        v.decode(zn, y_cat, y_cont, z_std=torch.ones(32, device="cuda"))

@@ -12,8 +12,10 @@ from toycrystals_b200.models import sde_score_model as shim  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 chunk = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+precision = sys.argv[4] if len(sys.argv) > 4 else "bf16"
+engine = sys.argv[5] if len(sys.argv) > 5 else "auto"
 torch.manual_seed(1)
-m = shim.CondUNetTiny(4, 4, 96, 128, 8, 8, precision="bf16", use_graph=False, chunk=chunk).cuda().eval()
+m = shim.CondUNetTiny(4, 4, 96, 128, 8, 8, precision=precision, engine=engine, use_graph=False, chunk=chunk).cuda().eval()
 sde = shim.VPSDE(0.1, 30.0)
 yc, yk = shim.condition_grid(m, n, 3.141592653589793 / 3, "cuda")
 for _ in range(2):

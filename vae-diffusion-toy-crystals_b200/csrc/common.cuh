@@ -57,6 +57,8 @@ struct ConvGeom {
   int csrc[2];    // channels per source (multiples of 32)
   int in_pad[2];  // 1 = source is a padded tensor, 0 = plain
   int ntot;       // total output channels
+  int split3 = 0;  // fp32 mode on the tensor pipe: operands as bf16 (hi, lo) pairs, a*w ~= a_hi*w_hi + a_hi*w_lo + a_lo*w_hi
+                   // accumulated in fp32 (the dropped a_lo*w_lo term and the representation error are ~2^-17 relative)
   int kx_in_n = 0; // 96 -> 1 output conv only: the three kx taps are three GEMM columns sharing ONE (unshifted) window per
                    // channel block; the epilogue sums column kx of pixel x + kx - 1 (circular in x)
 };

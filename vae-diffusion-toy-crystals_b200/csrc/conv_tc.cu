@@ -58,6 +58,7 @@ constexpr uint32_t EPI_FUSED_BYTES = sizeof(EpiFusedSmem);
 // The G CTAs of an image wait for each other's GroupNorm partial sums (one L2 round trip when they run in lock step).
 // Co-residency of the whole grid is guaranteed by the launch (cooperative attribute, grid clamped to
 // cudaOccupancyMaxActiveClusters), so this bound only turns a protocol bug into a launch failure instead of a hang.
+// (TCS_EXCHANGE_TIMEOUT=<cycles> overrides it: instrumented ncu passes run the kernel orders of magnitude slower.)
 constexpr long long EXCHANGE_TIMEOUT_CYCLES = 1000000000LL;   // ~0.5 s
 
 __device__ __forceinline__ void st_relaxed_gpu_u64(unsigned long long* p, unsigned long long v) {
@@ -220,6 +221,7 @@ struct __align__(8) TcBarriers {
 template <int N, int EPI, int MSUB, int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+               const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
                const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapO,
                const ConvTcParams p) {
   constexpr int ACC_STRIDE = (N * MSUB <= 128) ? 128 : 256;  // TMEM columns per accumulator stage
@@ -244,6 +246,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&mapA0);
     ptx::prefetch_tmap(&mapA1);
+    if (p.nsrc > 2) { ptx::prefetch_tmap(&mapA2); ptx::prefetch_tmap(&mapA3); }
     ptx::prefetch_tmap(&mapW);
     if (EPI != EPI_EPS) ptx::prefetch_tmap(&mapO);
     for (int s = 0; s < p.nstage; ++s) {
@@ -280,7 +283,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       const int y0 = (mt % p.tiles_per_img) * rows_per_tile;
       int ks = 0;
       for (int src = 0; src < p.nsrc; ++src) {
-        const CUtensorMap* mapA = src == 0 ? &mapA0 : &mapA1;
+        const int ms = p.msel[src];
+        const CUtensorMap* mapA = ms == 0 ? &mapA0 : (ms == 1 ? &mapA1 : (ms == 2 ? &mapA2 : &mapA3));
         for (int cb = 0; cb < p.cblk[src]; ++cb)
           for (int kyg = 0; kyg < p.KYG; ++kyg)
             for (int kx = 0; kx < p.KW; ++kx, ++ks) {
@@ -303,9 +307,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                   if (p.pair)
                     ptx::tma_load_4d_2sm(a_dst + p.a_bytes / 2, mapA, full, cb * 32, kx + p.kxn + p.base_off[src],
                                          p.stride * y0 + kyg + p.base_off[src], b + 1);
-                  for (int j = 0; j < p.T; ++j)
-                    ptx::tma_load_2d_2sm(b_dst + j * NB * 64, &mapW, full, 0,
-                                         (ks * p.T + j) * p.ntot + nt * N + static_cast<int>(cta_rank) * NB);
+                  // weights: ONE box of 512-byte rows (the T taps of this CTA's N/2 rows, stored in global memory as the
+                  // exact SWIZZLE_64B shared-memory image): 4x fewer TMA/L2 requests than 64-byte rows
+                  ptx::tma_load_2d_2sm(b_dst, &mapW, full, 0,
+                                       ((ks * p.n_ntiles + nt) * 2 + static_cast<int>(cta_rank)) * p.b_rows);
                 } else {
                   ptx::mbar_expect_tx(full, p.a_bytes + p.T * N * 64);
                   ptx::tma_load_4d(a_dst, mapA, full, cb * 32, kx + p.kxn + p.base_off[src],
@@ -313,8 +318,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                   if (p.pair)
                     ptx::tma_load_4d(a_dst + p.a_bytes / 2, mapA, full, cb * 32, kx + p.kxn + p.base_off[src],
                                      p.stride * y0 + kyg + p.base_off[src], b + 1);
-                  for (int j = 0; j < p.T; ++j)
-                    ptx::tma_load_2d(b_dst + j * N * 64, &mapW, full, 0, (ks * p.T + j) * p.ntot + nt * N);
+                  ptx::tma_load_2d(b_dst, &mapW, full, 0, (ks * p.n_ntiles + nt) * p.b_rows);
                 }
               }
               __syncwarp();
@@ -626,7 +630,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
               if (p.debug & 1) ready = true;
               if (!ready) {
                 ++polls;
-                if (clock64() - t0 > EXCHANGE_TIMEOUT_CYCLES) __trap();   // -> launch failure, reported as TCS_ERR_CUDA
+                if (clock64() - t0 > p.exch_timeout) __trap();   // -> launch failure, reported as TCS_ERR_CUDA
               }
             } while (!ready);
 #pragma unroll
@@ -852,7 +856,7 @@ int conv_tc_kstages(const ConvGeom& g) {
   stage_shape(g, &T, &KYG, &KW);
   int cb = 0;
   for (int s = 0; s < g.nsrc; ++s) cb += g.csrc[s] / 32;
-  return cb * KYG * KW;
+  return cb * KYG * KW * (g.split3 ? 3 : 1);
 }
 
 size_t conv_tc_packed_elems(const ConvGeom& g) {
@@ -861,29 +865,51 @@ size_t conv_tc_packed_elems(const ConvGeom& g) {
   return static_cast<size_t>(conv_tc_kstages(g)) * T * g.ntot * 32;
 }
 
-void conv_tc_pack_weights(const ConvGeom& g, const float* w, __nv_bfloat16* out) {
-  int T, KYG, KW;
+// N tile and CTA-pair choice of a layer (shared by the weight packer and the plan)
+void conv_tc_tile_shape(const ConvGeom& g, int epi, int* N, int* cg) {
+  *N = (epi == EPI_EPS) ? 16 : ((g.ntot % 192 == 0) ? 192 : 96);
+  const char* e = getenv("TCS_CG");   // 1 = single-CTA MMA everywhere (A/B switch)
+  *cg = (*N >= 96 && !(e && atoi(e) == 1)) ? 2 : 1;
+  // the 96 -> 1 output conv is bound by MMA ISSUE (36 tiny N = 16 MMAs per tile at ~100 cycles each): as a CTA pair one
+  // thread's MMA covers both CTAs' tiles, which halves the issue work per tile
+  const char* e2 = getenv("TCS_EPS_CG");
+  if (epi == EPI_EPS && !(e && atoi(e) == 1) && !(e2 && atoi(e2) == 1)) *cg = 2;
+}
+
+// Packed layout: [K stage][N tile][CTA of the pair][tap][N/cg rows][32 channels], every 64-byte row with its 16-byte
+// chunks permuted as SWIZZLE_64B would place them (chunk ^ ((row >> 1) & 3)), i.e. the shared-memory image itself, so
+// that TMA can move a stage's weights as one box of 512-byte rows without swizzling.
+void conv_tc_pack_weights(const ConvGeom& g, int epi, const float* w, __nv_bfloat16* out) {
+  int T, KYG, KW, N, cg;
   stage_shape(g, &T, &KYG, &KW);
+  conv_tc_tile_shape(g, epi, &N, &cg);
+  const int NB = N / cg, n_ntiles = g.ntot / N;
   const int k = g.ksize;
   int cin_tot = 0;
   for (int s = 0; s < g.nsrc; ++s) cin_tot += g.csrc[s];
   size_t ks = 0;
   int coff = 0;
+  const int nseg = g.split3 ? 3 : 1;          // K segments per logical source: [w_hi, w_lo, w_hi] against [a_hi, a_hi, a_lo]
   for (int s = 0; s < g.nsrc; ++s) {
-    for (int cb = 0; cb < g.csrc[s] / 32; ++cb)
-      for (int kyg = 0; kyg < KYG; ++kyg)
-        for (int kx = 0; kx < KW; ++kx, ++ks)
-          for (int j = 0; j < T; ++j) {
-            const int ky = (g.ksize == 4) ? kyg + 2 * j : j;
-            for (int n = 0; n < g.ntot; ++n)
-              for (int c = 0; c < 32; ++c) {
-                const int ci = coff + cb * 32 + c;
-                float v;
-                if (g.kx_in_n) v = n < k ? w[((static_cast<size_t>(0) * cin_tot + ci) * k + ky) * k + n] : 0.f;   // column n = tap kx
-                else v = w[((static_cast<size_t>(n) * cin_tot + ci) * k + ky) * k + kx];
-                out[((ks * T + j) * g.ntot + n) * 32 + c] = __float2bfloat16(v);
-              }
-          }
+    for (int seg = 0; seg < nseg; ++seg)
+      for (int cb = 0; cb < g.csrc[s] / 32; ++cb)
+        for (int kyg = 0; kyg < KYG; ++kyg)
+          for (int kx = 0; kx < KW; ++kx, ++ks)
+            for (int j = 0; j < T; ++j) {
+              const int ky = (g.ksize == 4) ? kyg + 2 * j : j;
+              for (int n = 0; n < g.ntot; ++n)
+                for (int c = 0; c < 32; ++c) {
+                  const int ci = coff + cb * 32 + c;
+                  float v;
+                  if (g.kx_in_n) v = n < k ? w[((static_cast<size_t>(0) * cin_tot + ci) * k + ky) * k + n] : 0.f;   // column n = tap kx
+                  else v = w[((static_cast<size_t>(n) * cin_tot + ci) * k + ky) * k + kx];
+                  __nv_bfloat16 hi = __float2bfloat16(v);
+                  if (seg == 1) hi = __float2bfloat16(v - __bfloat162float(hi));   // w_lo
+                  const int nt = n / N, nn = n % N, half = nn / NB, r = nn % NB;
+                  const int pc = (c / 8) ^ ((r >> 1) & 3);
+                  out[((((ks * n_ntiles + nt) * cg + half) * T + j) * NB + r) * 32 + pc * 8 + (c % 8)] = hi;
+                }
+            }
     coff += g.csrc[s];
   }
 }
@@ -929,7 +955,7 @@ int conv_tc_make_pair(ConvTcPlan* pl, const void* src, int B) {
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(TCS_ERR_CUDA, "cuTensorMapEncodeTiled(A pair) failed: " + std::to_string(r));
-  pl->mapA[1] = pl->mapA[0];
+  for (int i = 1; i < 4; ++i) pl->mapA[i] = pl->mapA[0];
   return TCS_OK;
 }
 
@@ -1025,7 +1051,7 @@ static int launch_t(const ConvTcPlan& pl, cudaStream_t st) {
     ++na;
   }
   cfg.attrs = at; cfg.numAttrs = na;
-  TCS_CUDA(cudaLaunchKernelEx(&cfg, kern, pl.mapA[0], pl.mapA[1], pl.mapW, pl.mapO, pl.p));
+  TCS_CUDA(cudaLaunchKernelEx(&cfg, kern, pl.mapA[0], pl.mapA[1], pl.mapA[2], pl.mapA[3], pl.mapW, pl.mapO, pl.p));
   TCS_CUDA(cudaGetLastError());
   return TCS_OK;
 }
@@ -1070,7 +1096,8 @@ int conv_tc_launch(const ConvTcPlan& pl, cudaStream_t st) {
 }
 
 int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, const void* src1,
-                      const __nv_bfloat16* wpacked, int epi, const EpiArgs& ea, int sm_count) {
+                      const __nv_bfloat16* wpacked, int epi, const EpiArgs& ea, int sm_count, const void* lo0,
+                      const void* lo1) {
   PFN_encodeTiled encode = get_encode();
   if (!encode) return fail(TCS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   if (g.W != 64 && g.W != 32 && g.W != 16) return fail(TCS_ERR_UNSUPPORTED, "conv_tc: output width must be 64/32/16");
@@ -1078,24 +1105,19 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, con
   ConvTcPlan& pl = *plan;
   pl = ConvTcPlan();
   ConvTcParams& p = pl.p;
-  pl.N = (epi == EPI_EPS) ? 16 : ((g.ntot % 192 == 0) ? 192 : 96);
+  conv_tc_tile_shape(g, epi, &pl.N, &pl.cg);
   if (g.ntot % pl.N) return fail(TCS_ERR_UNSUPPORTED, "conv_tc: C_out must be a multiple of 96");
   pl.epi = epi;
   // N = 96: two 128-pixel sub-tiles per CTA tile share every weight (B) stage (half the B traffic per
   // MAC) and give each of the 8 epilogue warps a 32-row x 96-column unit; N = 192: one sub-tile, the
   // epilogue warps split its columns in halves.  Either way two accumulator sets double-buffer in TMEM.
   pl.msub = pl.N == 192 ? 1 : 2;
-  {
-    const char* e = getenv("TCS_CG");   // 1 = single-CTA MMA everywhere (A/B switch)
-    pl.cg = (pl.N >= 96 && !(e && atoi(e) == 1)) ? 2 : 1;
-    // the 96 -> 1 output conv is bound by MMA ISSUE (36 tiny N = 16 MMAs per tile at ~100 cycles each): as a CTA pair one
-    // thread's MMA covers both CTAs' tiles, which halves the issue work per tile
-    const char* e2 = getenv("TCS_EPS_CG");
-    if (epi == EPI_EPS && !(e && atoi(e) == 1) && !(e2 && atoi(e2) == 1) && (g.B * (g.H / (2 * (128 / g.W)))) % 2 == 0) pl.cg = 2;
-  }
+  if (epi == EPI_EPS && pl.cg == 2 && (g.B * (g.H / (2 * (128 / g.W)))) % 2)
+    return fail(TCS_ERR_UNSUPPORTED, "conv_tc: the output conv runs as CTA pairs and needs an even number of tiles");
   if (g.H % (pl.msub * (128 / g.W))) return fail(TCS_ERR_UNSUPPORTED, "conv_tc: image height not a multiple of the tile");
   p.debug = getenv("TCS_DEBUG") ? atoi(getenv("TCS_DEBUG")) : 0;
   p.gn_inv_cnt = 1.0 / (static_cast<double>(g.H) * g.W * (pl.N / 8));
+  p.exch_timeout = getenv("TCS_EXCHANGE_TIMEOUT") ? atoll(getenv("TCS_EXCHANGE_TIMEOUT")) : EXCHANGE_TIMEOUT_CYCLES;
   {
     const char* e = getenv("TCS_ISSUERS");   // 1 = a single MMA-issuing thread everywhere (A/B switch)
     p.issuers = (pl.msub == 2 && !(e && atoi(e) == 1)) ? 2 : 1;
@@ -1107,7 +1129,9 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, con
   p.kxn = g.kx_in_n ? 1 : 0;
   p.guidance = 0.f;
   p.WR = p.Rt * pl.msub + p.T - 1;
-  p.nsrc = g.nsrc;
+  p.nsrc = g.nsrc * (g.split3 ? 3 : 1);
+  if (g.split3 && (!lo0 || (g.nsrc == 2 && !lo1))) return fail(TCS_ERR_BAD_ARGUMENT, "conv_tc: bf16x3 mode needs the lo parts of its sources");
+  if (g.split3 && epi != EPI_RAW_STATS) return fail(TCS_ERR_UNSUPPORTED, "conv_tc: bf16x3 mode writes fp32 (EPI_RAW_STATS) only");
   p.ntot = g.ntot;
   p.tiles_per_img = g.H / (p.Rt * pl.msub);
   p.n_mtiles = g.B * p.tiles_per_img;
@@ -1130,33 +1154,48 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, con
                 "conv_tc: fused GroupNorm needs one N tile and a whole image group (" + std::to_string(p.tiles_per_img) +
                     " CTAs) resident at once; the device can hold " + std::to_string(pl.max_ctas));
 
-  const void* srcs[2] = {src0, src1};
-  for (int s = 0; s < 2; ++s) {
-    const int si = s < g.nsrc ? s : 0;  // unused second map mirrors the first
+  // tensor maps: [src0, src1] or, in bf16x3 mode, [hi0, lo0, hi1, lo1]; physical K segments select among them
+  const void* srcs[4] = {src0, src1, src0, src1};
+  int lsrc[4] = {0, 1, 0, 1};            // logical source of each map
+  if (g.split3) {
+    srcs[0] = src0; srcs[1] = lo0; srcs[2] = src1; srcs[3] = lo1;
+    lsrc[0] = lsrc[1] = 0; lsrc[2] = lsrc[3] = 1;
+  }
+  for (int ps = 0; ps < 6; ++ps) {
+    const int ls = g.split3 ? ps / 3 : ps;                 // logical source of this K segment
+    const int li = ls < g.nsrc ? ls : 0;
+    const int conv_pad = (g.ksize == 1) ? 0 : 1;           // halo 1, conv pad: 3x3 -> 1, 4x4/s2 -> 1, 1x1 -> 0
+    p.base_off[ps] = g.in_pad[li] - conv_pad;
+    if (p.base_off[ps] < 0) return fail(TCS_ERR_BAD_ARGUMENT, "conv_tc: a 3x3/4x4 conv needs a padded source");
+    p.cblk[ps] = g.csrc[li] / 32;
+    p.msel[ps] = g.split3 ? 2 * li + (ps % 3 == 2 ? 1 : 0) : li;   // [a_hi, a_hi, a_lo]
+  }
+  for (int s = 0; s < 4; ++s) {
+    int si = lsrc[s] < g.nsrc ? lsrc[s] : 0;  // unused maps mirror the first source
+    if (!srcs[s] || lsrc[s] >= g.nsrc) { srcs[s] = srcs[0]; si = 0; }
     const int pad = g.in_pad[si];
     const int Hin = g.H * g.stride + 2 * pad, Win = g.W * g.stride + 2 * pad;
-    // halo 1, conv pad: 3x3 -> 1, 4x4/s2 -> 1, 1x1 -> 0
-    const int conv_pad = (g.ksize == 1) ? 0 : 1;
-    p.base_off[s] = pad - conv_pad;
-    if (p.base_off[s] < 0) return fail(TCS_ERR_BAD_ARGUMENT, "conv_tc: a 3x3/4x4 conv needs a padded source");
-    p.cblk[s] = g.csrc[si] / 32;
     const cuuint64_t C = g.csrc[si];
     cuuint64_t dims[4] = {C, static_cast<cuuint64_t>(Win), static_cast<cuuint64_t>(Hin), static_cast<cuuint64_t>(g.B)};
     cuuint64_t strides[3] = {C * 2, C * 2 * Win, C * 2 * Win * Hin};
     cuuint32_t box[4] = {32, static_cast<cuuint32_t>(g.W * g.stride), static_cast<cuuint32_t>(p.WR * g.stride), 1};
     cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(g.stride), static_cast<cuuint32_t>(g.stride), 1};
-    CUresult r = encode(&pl.mapA[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(srcs[si]), dims, strides,
+    CUresult r = encode(&pl.mapA[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(srcs[s]), dims, strides,
                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(TCS_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed: " + std::to_string(r));
   }
   {
-    cuuint64_t dims[2] = {32, static_cast<cuuint64_t>(p.kstages) * p.T * g.ntot};
-    cuuint64_t strides[1] = {64};
-    cuuint32_t box[2] = {32, static_cast<cuuint32_t>(pl.N / pl.cg)};
+    // the packed weights ARE the swizzled shared-memory image: plain (unswizzled) 512-byte rows
+    const uint32_t stage_b = static_cast<uint32_t>(p.T) * (pl.N / pl.cg) * 64;     // bytes per stage and CTA
+    if (stage_b % 512) return fail(TCS_ERR_UNSUPPORTED, "conv_tc: weight stage is not a multiple of 512 bytes");
+    p.b_rows = static_cast<int>(stage_b / 512);
+    cuuint64_t dims[2] = {256, static_cast<cuuint64_t>(p.kstages) * p.n_ntiles * pl.cg * p.b_rows};
+    cuuint64_t strides[1] = {512};
+    cuuint32_t box[2] = {256, static_cast<cuuint32_t>(p.b_rows)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(&pl.mapW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(wpacked), dims,
-                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(TCS_ERR_CUDA, "cuTensorMapEncodeTiled(W) failed: " + std::to_string(r));
   }

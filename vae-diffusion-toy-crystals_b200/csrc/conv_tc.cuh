@@ -13,22 +13,25 @@ struct ConvTcParams {
   int Rt;                   // image rows per 128-pixel sub-tile (= 128 / W)
   int T, KYG, KW;           // taps per stage, ky groups, kx count
   int stride, WR;           // conv stride; window rows per stage
-  int nsrc, cblk[2], base_off[2];
+  int nsrc, cblk[6], base_off[6];   // PHYSICAL sources (K segments): 1-2 normally, 3 per logical source in bf16x3 mode
+  int msel[6];              // tensor map (0..3) each physical source reads
   int ntot;                 // total output channels
   int kstages;              // pipeline stages (K iterations) per tile
+  int b_rows;               // 512-byte rows of packed weights per stage and CTA
   int nstage;               // smem ring depth
   uint32_t a_bytes, stage_bytes;
   int pair;                 // EPI_EPS: 1 = the two sub-tiles are the same pixels of images 2i (cond) and 2i+1 (uncond)
   int kxn;                  // EPI_EPS: 1 = kx taps live in accumulator columns 0..2 (ConvGeom::kx_in_n)
   float guidance;           // EPI_EPS with pair: eps = e_u + guidance (e_c - e_u)
   double gn_inv_cnt;        // EPI_GN_FUSED: 1 / (H * W * channels per group)
+  long long exch_timeout;   // EPI_GN_FUSED: cycles a CTA waits for its image group's partial sums before it traps
   int issuers;              // MMA-issuing warps: 2 = one per 128-row sub-tile (MSUB == 2), 1 otherwise
   int debug;                // TCS_DEBUG bits (timing experiments only): 1 = no inter-CTA wait, 2 = no pass-2 stores
   EpiArgs epi;
 };
 
 struct ConvTcPlan {
-  CUtensorMap mapA[2];
+  CUtensorMap mapA[4];   // [source] or, in bf16x3 mode, [hi0, lo0, hi1, lo1]
   CUtensorMap mapW;
   CUtensorMap mapO;   // EPI_PADDED / EPI_GN_FUSED: padded bf16 output, TMA-stored in 32-pixel x 32-channel boxes
   ConvTcParams p;
@@ -47,11 +50,16 @@ struct ConvTcPlan {
 int conv_tc_kstages(const ConvGeom& g);
 size_t conv_tc_packed_elems(const ConvGeom& g);
 // weight [ntot][cin_total][k][k] fp32 (PyTorch layout) -> bf16 [kstage][T][ntot][32]
-void conv_tc_pack_weights(const ConvGeom& g, const float* w, __nv_bfloat16* out_host);
+// (bf16x3 mode: per logical source the K segments [w_hi, w_lo, w_hi], matching the A segments [a_hi, a_hi, a_lo])
+void conv_tc_pack_weights(const ConvGeom& g, int epi, const float* w, __nv_bfloat16* out_host);
+void conv_tc_tile_shape(const ConvGeom& g, int epi, int* N, int* cg);
 
 // src0/src1: bf16 NHWC device tensors (padded or plain as g.in_pad says); wpacked: device bf16
+// bf16x3 mode (g.split3): every fp32 source arrives as two bf16 tensors hi = bf16(a), lo = bf16(a - hi); src0/src1 are
+// the hi parts, lo0/lo1 the lo parts.
 int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, const void* src1,
-                      const __nv_bfloat16* wpacked, int epi, const EpiArgs& ea, int sm_count);
+                      const __nv_bfloat16* wpacked, int epi, const EpiArgs& ea, int sm_count,
+                      const void* lo0 = nullptr, const void* lo1 = nullptr);
 int conv_tc_launch(const ConvTcPlan& plan, cudaStream_t stream);
 int conv_tc_make_pair(ConvTcPlan* plan, const void* src, int B);
 // grid for B images (persistent: <= one CTA per SM; whole image groups for EPI_GN_FUSED)

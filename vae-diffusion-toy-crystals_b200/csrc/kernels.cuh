@@ -78,6 +78,18 @@ int launch_pad_from_plain(const float* in, int B, int H, int W, int C, int pad, 
 template <typename T>
 int launch_unpad_to_f32(const T* in, int B, int H, int W, int C, int pad, float* out, cudaStream_t st);
 
+// ---- fp32 mode on the tensor pipe: bf16 (hi, lo) split tensors (kernels_split.cu) ------------------------------------
+// split tensor = hi plane, then the lo plane lo_off elements later; a ~= hi + lo to ~2^-17 relative
+int launch_split(const float* in, size_t elems, __nv_bfloat16* out, size_t lo_off, cudaStream_t st);
+// raw fp32 conv output [B,H,W,C] -> padded tensor with halo.  mode 0: GroupNorm(stats) + SiLU -> split tensor;
+// mode 1: copy -> split tensor; mode 2: + residual (padded fp32) -> padded fp32
+int launch_raw_to_padded(int mode, const float* raw, const float2* stats, const float* gamma, const float* beta,
+                         const float* residual, int B, int H, int W, int C, void* out, size_t lo_off, cudaStream_t st);
+int launch_unsplit_to_f32(const __nv_bfloat16* in, size_t lo_off, int B, int H, int W, int C, int pad, float* out,
+                          cudaStream_t st);
+// stats[b][g] = (mean, rstd) from the convs' partial sums (fp64 combine, fixed order)
+int launch_gn_finalize(const float* partials, int slots, int B, int H, int W, int C, float2* stats, cudaStream_t st);
+
 // ---- sampler update (kernels_step.cu) ------------------------------------------------------------
 struct StepCoef {   // one row per time-grid index i (host-computed in fp32, see tcs_api.cu)
   float t, beta, sigma, alpha, dt, g_sqrt_dt, pad0, pad1;   // dt = ts[i+1]-ts[i]; g_sqrt_dt = sqrt(beta)*sqrt(|dt|)

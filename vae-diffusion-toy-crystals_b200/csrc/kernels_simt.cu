@@ -456,6 +456,13 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ 
   }
 }
 
+int launch_gn_finalize(const float* partials, int slots, int B, int H, int W, int C, float2* stats, cudaStream_t st) {
+  if (B <= 0) return TCS_OK;
+  gn_finalize_kernel<<<B, 256, 0, st>>>(partials, slots, static_cast<double>(H) * W * (C / GN_GROUPS), stats);
+  TCS_CUDA(cudaGetLastError());
+  return TCS_OK;
+}
+
 template <typename T>
 int launch_gn_apply(const void* in, int in_padded, const float* partials, int slots, const float* gamma,
                     const float* beta, int B, int H, int W, int C, int silu, T* out, float2* stats, cudaStream_t st) {

@@ -26,19 +26,25 @@ __host__ __device__ inline Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
 
 __device__ __forceinline__ float u01(uint32_t r) { return (static_cast<float>(r >> 8) + 0.5f) * (1.0f / 16777216.0f); }
 
+// single-instruction SFU forms (the arguments are never denormal: u01 >= 2^-25)
+__device__ __forceinline__ float sfu_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sfu_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sfu_sin(float x) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sfu_cos(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 // four N(0,1) draws for pixels 4*group .. 4*group+3 of sample gidx, stream word `word`
 __device__ __forceinline__ float4 philox_normal4(unsigned long long seed, unsigned long long gidx, uint32_t word,
                                                  uint32_t group) {
   const Philox4 r = philox4x32_10(group, word, static_cast<uint32_t>(gidx), static_cast<uint32_t>(gidx >> 32),
                                   static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
-  // Box-Muller on the SFU: lg2.approx / sin.approx / cos.approx (abs. error ~1e-6 on N(0,1) draws), so that the
-  // update kernel stays HBM-bound instead of being bound by libm's logf / sincospif
-  const float r0 = sqrtf(-1.3862943611198906f * __log2f(u01(r.x)));   // sqrt(-2 ln u) = sqrt(-2 ln2 log2 u)
-  const float r1 = sqrtf(-1.3862943611198906f * __log2f(u01(r.z)));
-  float s0, c0, s1, c1;
-  __sincosf(6.283185307179586f * u01(r.y) - 3.141592653589793f, &s0, &c0);   // angle in (-pi, pi): best SFU accuracy
-  __sincosf(6.283185307179586f * u01(r.w) - 3.141592653589793f, &s1, &c1);
-  return make_float4(-r0 * c0, -r0 * s0, -r1 * c1, -r1 * s1);              // cos(a - pi) = -cos a, sin(a - pi) = -sin a
+  // Box-Muller on the SFU: lg2 / sqrt / sin / cos .approx, one MUFU each (abs. error ~1e-6 on N(0,1) draws).  The update
+  // kernel is bound by instruction issue, not by HBM, as long as this costs more than a few dozen instructions
+  // (ncu, round 2: 272 instructions per warp with libm-style sqrtf / __sincosf and IEEE divisions, 75 % issue-active).
+  const float r0 = sfu_sqrt(-1.3862943611198906f * sfu_lg2(u01(r.x)));   // sqrt(-2 ln u) = sqrt(-2 ln2 log2 u)
+  const float r1 = sfu_sqrt(-1.3862943611198906f * sfu_lg2(u01(r.z)));
+  const float a0 = 6.283185307179586f * u01(r.y) - 3.141592653589793f;     // angle in (-pi, pi): best SFU accuracy
+  const float a1 = 6.283185307179586f * u01(r.w) - 3.141592653589793f;
+  return make_float4(-r0 * sfu_cos(a0), -r0 * sfu_sin(a0), -r1 * sfu_cos(a1), -r1 * sfu_sin(a1));   // cos(a - pi) = -cos a
 }
 
 }  // namespace tcs

@@ -97,6 +97,7 @@ struct tcs_handle {
   tcs_config cfg;
   int sm_count = 148;
   bool bf16 = false, use_tc = false, fuse_gn = false, fuse_first = true;
+  bool split3 = false;   // precision fp32 on the tcgen05 engine: conv operands as bf16 (hi, lo) pairs (kernels_split.cu)
   size_t esz = 4;
   cudaStream_t stream = nullptr;   // internal stream all work runs on
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
@@ -119,6 +120,7 @@ struct tcs_handle {
   DevBuf p64_h1, p64_a, p64_b;
   DevBuf p32_96a, p32_96b, p32_192a, p32_192h2, p32_192b;
   DevBuf p16_a, p16_b, p16_c, qkv, atty;
+  DevBuf split_s;                         // bf16x3 mode: split copy of the fp32 tensor the next conv reads
   ConvTcPlan plan[C_COUNT];
   ConvTcPlan plan_eps, plan_eps_pair;     // 96 -> 1 output conv on the tensor pipe (N padded to 16)
   DevBuf wpack_out;
@@ -218,6 +220,7 @@ static int alloc_workspace(tcs_handle* h) {
   TCS_CHECK(h->p16_a.ensure(P16)); TCS_CHECK(h->p16_b.ensure(P16)); TCS_CHECK(h->p16_c.ensure(P16));
   TCS_CHECK(h->qkv.ensure(MB * 256 * 576 * e));
   TCS_CHECK(h->atty.ensure(MB * 256 * 192 * e));
+  if (h->split3) TCS_CHECK(h->split_s.ensure(P64));
   return TCS_OK;
 }
 
@@ -255,8 +258,53 @@ static int slots_of(tcs_handle* h, int id) {
   return h->use_tc ? tc_slots(r, r) : simt_slots(r, r);
 }
 
+// ---- bf16x3 mode: (split source tensors, raw fp32 destination) of every conv ---------------------------------------
+// A split tensor lives in a buffer sized for the fp32 tensor it replaces: hi plane first, lo plane `lo` elements later
+// (= the element count of the full-chunk tensor, so the planes never move with the size of a pass).
+struct SplitSrc { const void* p; size_t lo; };
+struct SplitWiring { SplitSrc s0, s1; float* raw; int ldo; int in_pad; };
+static size_t padded_elems(const tcs_handle* h, int res, int C) { return static_cast<size_t>(h->chunk) * (res + 2) * (res + 2) * C; }
+static SplitWiring split_wiring(tcs_handle* h, int id) {
+  const SplitSrc S64{h->split_s.p, padded_elems(h, 64, 96)}, S32{h->split_s.p, padded_elems(h, 32, 192)},
+      S16{h->split_s.p, padded_elems(h, 16, 192)}, SY{h->split_s.p, static_cast<size_t>(h->chunk) * 256 * 192};
+  const SplitSrc h1{h->p64_h1.p, padded_elems(h, 64, 96)}, h2{h->p32_192h2.p, padded_elems(h, 32, 192)};
+  const SplitSrc none{nullptr, 0};
+  float *r64 = h->raw64.as<float>(), *r32 = h->raw32.as<float>(), *r16 = h->raw16.as<float>();
+  switch (id) {
+    case C_D1B: return {S64, none, r64, 96, 1};
+    case C_DS1: return {h1, none, r32, 96, 1};
+    case C_D2A: return {{h->p32_96a.p, padded_elems(h, 32, 96)}, none, r32, 192, 1};
+    case C_D2B: return {{h->p32_192a.p, padded_elems(h, 32, 192)}, none, r32, 192, 1};
+    case C_DS2: return {h2, none, r16, 192, 1};
+    case C_MA: return {{h->p16_c.p, padded_elems(h, 16, 192)}, none, r16, 192, 1};
+    case C_MB: return {{h->p16_b.p, padded_elems(h, 16, 192)}, none, r16, 192, 1};
+    case C_QKV: return {S16, none, h->qkv.as<float>(), 576, 1};
+    case C_PROJ: return {SY, none, r16, 192, 0};
+    case C_US2: return {S32, none, r32, 192, 1};
+    case C_U2A: return {{h->p32_192b.p, padded_elems(h, 32, 192)}, h2, r32, 96, 1};
+    case C_U2B: return {{h->p32_96a.p, padded_elems(h, 32, 96)}, none, r32, 96, 1};
+    case C_US1: return {S64, none, r64, 96, 1};
+    case C_U1A: return {{h->p64_b.p, padded_elems(h, 64, 96)}, h1, r64, 96, 1};
+    default: return {{h->p64_a.p, padded_elems(h, 64, 96)}, none, r64, 96, 1};   // C_U1B
+  }
+}
+
 static int build_plans(tcs_handle* h) {
   if (!h->use_tc) return TCS_OK;
+  if (h->split3) {
+    for (int id = 0; id < C_COUNT; ++id) {
+      const SplitWiring w = split_wiring(h, id);
+      ConvGeom g = geom_of(id, h->chunk, w.in_pad);
+      g.split3 = 1;
+      EpiArgs ea{};
+      ea.bias = h->dw.at(std::string(kConv[id].key) + ".bias");
+      ea.out = w.raw; ea.partials = h->partials.as<float>(); ea.ldo = w.ldo; ea.slots = slots_of(h, id);
+      auto lo = [](const SplitSrc& s) { return s.p ? static_cast<const void*>(static_cast<const __nv_bfloat16*>(s.p) + s.lo) : nullptr; };
+      TCS_CHECK(conv_tc_make_plan(&h->plan[id], g, w.s0.p, w.s1.p, h->wpack[id].as<__nv_bfloat16>(), EPI_RAW_STATS, ea,
+                                  h->sm_count, lo(w.s0), lo(w.s1)));
+    }
+    return TCS_OK;
+  }
   {
     const char* e = getenv("TCS_TC_OUT");   // 0 = keep the CUDA-core out conv (A/B switch)
     h->tc_out = !(e && atoi(e) == 0);
@@ -302,6 +350,7 @@ static int build_plans(tcs_handle* h) {
       break;
     }
   }
+  TCS_CUDA(cudaMemsetAsync(h->status.p, 0, 4, h->stream));   // the trial launches ran on uninitialised data
   return TCS_OK;
 }
 
@@ -461,6 +510,167 @@ static int forward_chunk(tcs_handle* h, const PassArgs& a, cudaStream_t st, TapR
   return TCS_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// the same pass in bf16x3 mode: every conv = tcgen05 over split operands -> raw fp32, everything else fp32 FFMA kernels
+// ------------------------------------------------------------------------------------------
+static int forward_chunk_split3(tcs_handle* h, const PassArgs& a, cudaStream_t st, TapRequest* tap) {
+  const int B = a.ns * a.dup;
+  float* part = h->partials.as<float>();
+  float2* stats = h->gnstats.as<float2>();
+  auto gnw = [&](const char* k) { return h->dw.at(std::string(k) + ".weight"); };
+  auto gnb = [&](const char* k) { return h->dw.at(std::string(k) + ".bias"); };
+  auto bf = [](void* p) { return static_cast<__nv_bfloat16*>(p); };
+  int tap_idx = 0;
+  // kind 0 = raw fp32 plain, 1 = padded fp32, 2 = plain fp32, 3 = split padded, -1 = not materialised in this mode
+  auto tapout = [&](int kind, const void* p, size_t lo, int res, int C) -> int {
+    const int my = tap_idx++;
+    if (!tap || tap->id != my) return 0;
+    if (kind < 0) return fail(TCS_ERR_UNSUPPORTED, "this activation is not materialised in bf16x3 mode");
+    const int64_t cnt = static_cast<int64_t>(B) * res * res * C;
+    if (cnt > tap->capacity) return fail(TCS_ERR_BAD_ARGUMENT, "tcs_debug_layer: output buffer too small");
+    if (kind == 0 || kind == 2) { TCS_CUDA(cudaMemcpyAsync(tap->out, p, cnt * 4, cudaMemcpyDeviceToDevice, st)); }
+    else if (kind == 1) TCS_CHECK(launch_unpad_to_f32<float>(static_cast<const float*>(p), B, res, res, C, 1, tap->out, st));
+    else TCS_CHECK(launch_unsplit_to_f32(static_cast<const __nv_bfloat16*>(p), lo, B, res, res, C, 1, tap->out, st));
+    tap->written = cnt;
+    return 1;
+  };
+#define TAP(kind, p, lo, res, C) { int _r = tapout(kind, p, lo, res, C); if (_r != 0) return _r < 0 ? _r : TCS_OK; }
+  auto conv = [&](int id) -> int {
+    ++h->launches;
+    ConvTcPlan pl = h->plan[id];
+    pl.p.n_mtiles = B * pl.p.tiles_per_img;
+    pl.grid = conv_tc_grid(pl, B, h->sm_count);
+    if (h->profiling) TCS_CUDA(cudaEventRecord(h->prof_ev[2 * id], st));
+    TCS_CHECK(conv_tc_launch(pl, st));
+    if (h->profiling) TCS_CUDA(cudaEventRecord(h->prof_ev[2 * id + 1], st));
+    return TCS_OK;
+  };
+  // fp32 tensor -> split scratch (the conv that follows reads it)
+  auto split_in = [&](const float* src, size_t elems_per_img, size_t lo) -> int {
+    ++h->launches;
+    return launch_split(src, static_cast<size_t>(B) * elems_per_img, bf(h->split_s.p), lo, st);
+  };
+  // raw conv output -> GroupNorm + SiLU -> split padded tensor (next consumer is a conv) or fp32 padded (FFMA consumer)
+  auto gn_split = [&](const char* key, int id, const float* raw, int res, int C, void* out) -> int {
+    h->launches += 2;
+    TCS_CHECK(launch_gn_finalize(part, slots_of(h, id), B, res, res, C, stats, st));
+    return launch_raw_to_padded(0, raw, stats, gnw(key), gnb(key), nullptr, B, res, res, C, out, padded_elems(h, res, C), st);
+  };
+  auto gn_f32 = [&](const char* key, int id, const float* raw, int res, int C, float* out) -> int {
+    h->launches += 2;
+    return launch_gn_apply<float>(raw, 0, part, slots_of(h, id), gnw(key), gnb(key), B, res, res, C, 1, out, stats, st);
+  };
+  auto pad_split = [&](const float* raw, int res, int C, void* out) -> int {
+    ++h->launches;
+    return launch_raw_to_padded(1, raw, nullptr, nullptr, nullptr, nullptr, B, res, res, C, out, padded_elems(h, res, C), st);
+  };
+  float *r64 = h->raw64.as<float>(), *r32 = h->raw32.as<float>(), *r16 = h->raw16.as<float>();
+  const size_t E64 = padded_elems(h, 64, 96), E32a = padded_elems(h, 32, 96), E32b = padded_elems(h, 32, 192),
+               E16 = padded_elems(h, 16, 192);
+  // ---- down1 ---------------------------------------------------------------------------------
+  if (!(tap && tap->id == 0)) {
+    ++h->launches;
+    TCS_CHECK(launch_first_conv_gn<float>(a.x, h->d_w9, a.tvec, a.tvec_stride, a.step_ptr, a.trow_off, a.cvec, a.ns, a.dup,
+                                          gnw("down1.net.1"), gnb("down1.net.1"), h->p64_a.as<float>(), st));
+    ++tap_idx;
+  } else {
+    ++h->launches;
+    TCS_CHECK(launch_first_conv(a.x, h->d_w9, a.tvec, a.tvec_stride, a.step_ptr, a.trow_off, a.cvec, a.ns, a.dup, r64, part, st));
+    TAP(0, r64, 0, 64, 96);
+  }
+  TAP(1, h->p64_a.p, 0, 64, 96);
+  TCS_CHECK(split_in(h->p64_a.as<float>(), 66 * 66 * 96, E64));
+  TCS_CHECK(conv(C_D1B));
+  TAP(0, r64, 0, 64, 96);
+  TCS_CHECK(gn_split("down1.net.4", C_D1B, r64, 64, 96, h->p64_h1.p));
+  TAP(3, h->p64_h1.p, E64, 64, 96);
+  TCS_CHECK(conv(C_DS1));
+  TCS_CHECK(pad_split(r32, 32, 96, h->p32_96a.p));
+  TAP(3, h->p32_96a.p, E32a, 32, 96);
+  // ---- down2 ---------------------------------------------------------------------------------
+  TCS_CHECK(conv(C_D2A));
+  TAP(0, r32, 0, 32, 192);
+  TCS_CHECK(gn_split("down2.net.1", C_D2A, r32, 32, 192, h->p32_192a.p));
+  TAP(3, h->p32_192a.p, E32b, 32, 192);
+  TCS_CHECK(conv(C_D2B));
+  TAP(0, r32, 0, 32, 192);
+  TCS_CHECK(gn_split("down2.net.4", C_D2B, r32, 32, 192, h->p32_192h2.p));
+  TAP(3, h->p32_192h2.p, E32b, 32, 192);
+  TCS_CHECK(conv(C_DS2));
+  TCS_CHECK(pad_split(r16, 16, 192, h->p16_c.p));
+  TAP(3, h->p16_c.p, E16, 16, 192);
+  // ---- mid + attention -----------------------------------------------------------------------
+  TCS_CHECK(conv(C_MA));
+  TAP(0, r16, 0, 16, 192);
+  TCS_CHECK(gn_split("mid.net.1", C_MA, r16, 16, 192, h->p16_b.p));
+  TAP(3, h->p16_b.p, E16, 16, 192);
+  TCS_CHECK(conv(C_MB));
+  TAP(0, r16, 0, 16, 192);
+  TCS_CHECK(gn_f32("mid.net.4", C_MB, r16, 16, 192, h->p16_a.as<float>()));   // x_in of the attention block (fp32)
+  TAP(1, h->p16_a.p, 0, 16, 192);
+  ++h->launches;
+  TCS_CHECK(launch_gn_image16<float>(h->p16_a.as<float>(), B, gnw("attn.norm"), gnb("attn.norm"), h->p16_b.as<float>(), st));
+  TCS_CHECK(split_in(h->p16_b.as<float>(), 18 * 18 * 192, E16));
+  TCS_CHECK(conv(C_QKV));
+  TAP(2, h->qkv.p, 0, 16, 576);
+  ++h->launches;
+  TCS_CHECK(launch_attention<float>(h->qkv.as<float>(), B, h->atty.as<float>(), st));
+  TAP(2, h->atty.p, 0, 16, 192);
+  TCS_CHECK(split_in(h->atty.as<float>(), 256 * 192, static_cast<size_t>(h->chunk) * 256 * 192));
+  TCS_CHECK(conv(C_PROJ));
+  ++h->launches;
+  TCS_CHECK(launch_raw_to_padded(2, r16, nullptr, nullptr, nullptr, h->p16_a.as<float>(), B, 16, 16, 192, h->p16_c.p, 0, st));
+  TAP(1, h->p16_c.p, 0, 16, 192);
+  // ---- up2 -----------------------------------------------------------------------------------
+  ++h->launches;
+  TCS_CHECK(launch_upsample2x<float>(h->p16_c.as<float>(), B, 16, 16, 192, h->p32_192a.as<float>(), st));
+  TAP(1, h->p32_192a.p, 0, 32, 192);
+  TCS_CHECK(split_in(h->p32_192a.as<float>(), 34 * 34 * 192, E32b));
+  TCS_CHECK(conv(C_US2));
+  TCS_CHECK(pad_split(r32, 32, 192, h->p32_192b.p));
+  TAP(3, h->p32_192b.p, E32b, 32, 192);
+  TCS_CHECK(conv(C_U2A));
+  TAP(0, r32, 0, 32, 96);
+  TCS_CHECK(gn_split("up2.net.1", C_U2A, r32, 32, 96, h->p32_96a.p));
+  TAP(3, h->p32_96a.p, E32a, 32, 96);
+  TCS_CHECK(conv(C_U2B));
+  TAP(0, r32, 0, 32, 96);
+  TCS_CHECK(gn_f32("up2.net.4", C_U2B, r32, 32, 96, h->p32_96b.as<float>()));
+  TAP(1, h->p32_96b.p, 0, 32, 96);
+  // ---- up1 -----------------------------------------------------------------------------------
+  ++h->launches;
+  TCS_CHECK(launch_upsample2x<float>(h->p32_96b.as<float>(), B, 32, 32, 96, h->p64_a.as<float>(), st));
+  TAP(1, h->p64_a.p, 0, 64, 96);
+  TCS_CHECK(split_in(h->p64_a.as<float>(), 66 * 66 * 96, E64));
+  TCS_CHECK(conv(C_US1));
+  TCS_CHECK(pad_split(r64, 64, 96, h->p64_b.p));
+  TAP(3, h->p64_b.p, E64, 64, 96);
+  TCS_CHECK(conv(C_U1A));
+  TAP(0, r64, 0, 64, 96);
+  TCS_CHECK(gn_split("up1.net.1", C_U1A, r64, 64, 96, h->p64_a.p));
+  TAP(3, h->p64_a.p, E64, 64, 96);
+  TCS_CHECK(conv(C_U1B));
+  TAP(0, r64, 0, 64, 96);
+  TCS_CHECK(gn_f32("up1.net.4", C_U1B, r64, 64, 96, h->p64_b.as<float>()));
+  TAP(1, h->p64_b.p, 0, 64, 96);
+  ++h->launches;
+  TCS_CHECK(launch_out_conv<float>(h->p64_b.as<float>(), h->d_wout, h->out_bias, a.ns, a.dup, a.guidance, a.eps, st));
+  if (tap && tap->id == kNumTaps - 1) {
+    const int64_t cnt = static_cast<int64_t>(a.ns) * 4096;
+    if (cnt > tap->capacity) return fail(TCS_ERR_BAD_ARGUMENT, "tcs_debug_layer: output buffer too small");
+    TCS_CUDA(cudaMemcpyAsync(tap->out, a.eps, cnt * 4, cudaMemcpyDeviceToDevice, st));
+    tap->written = cnt;
+  }
+#undef TAP
+  return TCS_OK;
+}
+
+static int forward_one(tcs_handle* h, const PassArgs& a, cudaStream_t st, TapRequest* tap) {
+  if (h->split3) return forward_chunk_split3(h, a, st, tap);
+  if (h->bf16) return forward_chunk<__nv_bfloat16>(h, a, st, tap);
+  return forward_chunk<float>(h, a, st, tap);
+}
+
 // network over all n samples, chunk by chunk
 static int forward_all(tcs_handle* h, const float* x, const float* cvec, const float* tvec, int tvec_stride,
                        const int* step_ptr, int trow_off, int n, int dup, float guidance, float* eps, cudaStream_t st) {
@@ -476,8 +686,7 @@ static int forward_all(tcs_handle* h, const float* x, const float* cvec, const f
     a.step_ptr = step_ptr; a.trow_off = trow_off;
     a.guidance = guidance;
     a.eps = eps + static_cast<size_t>(i0) * 4096;
-    if (h->bf16) TCS_CHECK(forward_chunk<__nv_bfloat16>(h, a, st, nullptr));
-    else TCS_CHECK(forward_chunk<float>(h, a, st, nullptr));
+    TCS_CHECK(forward_one(h, a, st, nullptr));
   }
   return TCS_OK;
 }
@@ -598,11 +807,11 @@ int tcs_create(tcs_handle** out, const tcs_config* cfg) {
   h->esz = h->bf16 ? 2 : 4;
   int eng = cfg->engine;
   if (eng == TCS_ENGINE_AUTO) eng = h->bf16 ? TCS_ENGINE_TCGEN05 : TCS_ENGINE_SIMT;
-  if (eng == TCS_ENGINE_TCGEN05 && !h->bf16) return fail(TCS_ERR_UNSUPPORTED, "the tcgen05 engine needs precision = bf16");
   h->use_tc = eng == TCS_ENGINE_TCGEN05;
+  h->split3 = h->use_tc && !h->bf16;   // fp32 operands as bf16 hi + lo pairs, three MMAs per product (1e-4 parity mode)
   {
     const char* e = getenv("TCS_FUSE_GN");   // 0 = keep conv -> raw fp32 -> gn_apply (A/B switch)
-    h->fuse_gn = h->use_tc && cfg->fuse_gn != 0 && !(e && atoi(e) == 0);
+    h->fuse_gn = h->use_tc && !h->split3 && cfg->fuse_gn != 0 && !(e && atoi(e) == 0);
     h->fuse_first = !(e && atoi(e) == 0);
   }
   h->chunk = cfg->chunk > 0 ? cfg->chunk : 2048;
@@ -702,11 +911,12 @@ int tcs_finalize_weights(tcs_handle* h) {
   ew.n_types = h->cfg.n_types; ew.y_cont_dim = h->cfg.y_cont_dim;
   // conv weights for the active engine
   for (int id = 0; id < C_COUNT; ++id) {
-    const ConvGeom g = geom_of(id, 1, 1);
+    ConvGeom g = geom_of(id, 1, 1);
+    g.split3 = h->split3 ? 1 : 0;
     const HostTensor& w = h->host_w.at(std::string(kConv[id].key) + ".weight");
     if (h->use_tc) {
       std::vector<__nv_bfloat16> pk(conv_tc_packed_elems(g));
-      conv_tc_pack_weights(g, w.v.data(), pk.data());
+      conv_tc_pack_weights(g, EPI_PADDED, w.v.data(), pk.data());   // (any epilogue but EPI_EPS: same tile shape)
       TCS_CHECK(h->wpack[id].ensure(pk.size() * 2));
       TCS_CUDA(cudaMemcpy(h->wpack[id].p, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
     } else {
@@ -716,7 +926,7 @@ int tcs_finalize_weights(tcs_handle* h) {
       TCS_CUDA(cudaMemcpy(h->wpack[id].p, pk.data(), pk.size() * 4, cudaMemcpyHostToDevice));
     }
   }
-  if (h->use_tc) {   // out conv as a 16-channel GEMM: row 0 = out.weight, rows 1..15 zero
+  if (h->use_tc && !h->split3) {   // out conv as a 16-channel GEMM: row 0 = out.weight, rows 1..15 zero
     ConvGeom g = geom_of(C_U1B, 1, 1);
     g.ntot = 16;
     {
@@ -727,7 +937,7 @@ int tcs_finalize_weights(tcs_handle* h) {
     std::vector<float> w16(16 * 96 * 9, 0.f);
     for (int k = 0; k < 96 * 9; ++k) w16[k] = wo.v[k];
     std::vector<__nv_bfloat16> pk(conv_tc_packed_elems(g));
-    conv_tc_pack_weights(g, w16.data(), pk.data());
+    conv_tc_pack_weights(g, EPI_EPS, w16.data(), pk.data());
     TCS_CHECK(h->wpack_out.ensure(pk.size() * 2));
     TCS_CUDA(cudaMemcpy(h->wpack_out.p, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
   }
@@ -783,7 +993,7 @@ int tcs_score_profiled(tcs_handle* h, const float* x, const float* t, const int6
   a.trow_off = 0; a.ns = n; a.dup = dup; a.guidance = guidance; a.eps = eps_out;
   h->profiling = true;
   cudaError_t e0 = cudaEventRecord(h->prof_ev[30], st);
-  int rc = h->bf16 ? forward_chunk<__nv_bfloat16>(h, a, st, nullptr) : forward_chunk<float>(h, a, st, nullptr);
+  int rc = forward_one(h, a, st, nullptr);
   cudaError_t e1 = cudaEventRecord(h->prof_ev[31], st);
   h->profiling = false;
   TCS_CHECK(rc);
@@ -817,8 +1027,7 @@ int64_t tcs_debug_layer(tcs_handle* h, const char* name, const float* x, const f
   PassArgs a;
   a.x = x; a.cvec = h->cvec.as<float>(); a.tvec = h->tvec.as<float>(); a.tvec_stride = 1; a.step_ptr = nullptr;
   a.trow_off = 0; a.ns = n; a.dup = dup; a.guidance = dup == 2 ? 1.5f : 0.f; a.eps = h->eps.as<float>();
-  if (h->bf16) TCS_CHECK(forward_chunk<__nv_bfloat16>(h, a, st, &tap));
-  else TCS_CHECK(forward_chunk<float>(h, a, st, &tap));
+  TCS_CHECK(forward_one(h, a, st, &tap));
   TCS_CHECK(leave(h, user));
   return tap.written;
 }
@@ -1073,7 +1282,7 @@ static int debug_conv_t(bool use_tc, const ConvGeom& g, const float* in0, const 
   }
   if (use_tc) {
     std::vector<__nv_bfloat16> pk(conv_tc_packed_elems(g));
-    conv_tc_pack_weights(g, hw.data(), pk.data());
+    conv_tc_pack_weights(g, epi, hw.data(), pk.data());
     TCS_CHECK(wp.ensure(pk.size() * 2));
     TCS_CUDA(cudaMemcpy(wp.p, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
     ConvTcPlan pl;
@@ -1120,6 +1329,61 @@ static int debug_conv_t(bool use_tc, const ConvGeom& g, const float* in0, const 
   return TCS_OK;
 }
 
+// one convolution in bf16x3 mode: fp32 inputs -> padded fp32 -> split (hi, lo) -> tcgen05 (K tripled) -> raw fp32 + stats
+static int debug_conv_split3(const ConvGeom& g0, const float* in0, const float* in1, const float* weight, const float* bias,
+                             float* out, float* stats, int epi, cudaStream_t st) {
+  ConvGeom g = g0;
+  g.split3 = 1;
+  const int B = g.B, Hin = g.H * g.stride, Win = g.W * g.stride, pad = g.in_pad[0];
+  DevBuf f32[2], sp[2], wp, db, part;
+  const float* ins[2] = {in0, in1};
+  size_t elems[2] = {0, 0};
+  for (int s = 0; s < g.nsrc; ++s) {
+    elems[s] = static_cast<size_t>(B) * (Hin + 2 * pad) * (Win + 2 * pad) * g.csrc[s];
+    TCS_CHECK(f32[s].ensure(elems[s] * 4));
+    TCS_CHECK(sp[s].ensure(elems[s] * 4));
+    TCS_CHECK(launch_pad_from_plain<float>(ins[s], B, Hin, Win, g.csrc[s], pad, f32[s].as<float>(), st));
+    TCS_CHECK(launch_split(f32[s].as<float>(), elems[s], sp[s].as<__nv_bfloat16>(), elems[s], st));
+  }
+  int cin = 0;
+  for (int s = 0; s < g.nsrc; ++s) cin += g.csrc[s];
+  const size_t wcount = static_cast<size_t>(g.ntot) * cin * g.ksize * g.ksize;
+  std::vector<float> hw(wcount), hb(g.ntot);
+  TCS_CUDA(cudaMemcpy(hw.data(), weight, wcount * 4, cudaMemcpyDefault));
+  TCS_CUDA(cudaMemcpy(hb.data(), bias, g.ntot * 4, cudaMemcpyDefault));
+  TCS_CHECK(db.ensure(g.ntot * 4));
+  TCS_CUDA(cudaMemcpy(db.p, hb.data(), g.ntot * 4, cudaMemcpyHostToDevice));
+  std::vector<__nv_bfloat16> pk(conv_tc_packed_elems(g));
+  conv_tc_pack_weights(g, EPI_RAW_STATS, hw.data(), pk.data());
+  TCS_CHECK(wp.ensure(pk.size() * 2));
+  TCS_CUDA(cudaMemcpy(wp.p, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
+  const int slots = tc_slots(g.H, g.W);
+  TCS_CHECK(part.ensure(static_cast<size_t>(B) * slots * 16 * 4));
+  EpiArgs ea{};
+  ea.bias = db.as<float>(); ea.ldo = g.ntot; ea.slots = slots; ea.out = out; ea.partials = part.as<float>();
+  ConvTcPlan pl;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  TCS_CHECK(conv_tc_make_plan(&pl, g, sp[0].p, g.nsrc == 2 ? sp[1].p : nullptr, wp.as<__nv_bfloat16>(), EPI_RAW_STATS, ea, sms,
+                              sp[0].as<__nv_bfloat16>() + elems[0], g.nsrc == 2 ? sp[1].as<__nv_bfloat16>() + elems[1] : nullptr));
+  TCS_CHECK(conv_tc_launch(pl, st));
+  TCS_CUDA(cudaStreamSynchronize(st));
+  if (stats && epi == EPI_RAW_STATS) {
+    std::vector<float> hp(static_cast<size_t>(B) * slots * 16);
+    TCS_CUDA(cudaMemcpy(hp.data(), part.p, hp.size() * 4, cudaMemcpyDeviceToHost));
+    std::vector<float> hs(static_cast<size_t>(B) * 16);
+    for (int b = 0; b < B; ++b)
+      for (int k = 0; k < 16; ++k) {
+        double acc = 0;
+        for (int s = 0; s < slots; ++s) acc += hp[(static_cast<size_t>(b) * slots + s) * 16 + k];
+        hs[b * 16 + k] = static_cast<float>(acc);
+      }
+    TCS_CUDA(cudaMemcpy(stats, hs.data(), hs.size() * 4, cudaMemcpyDefault));
+  }
+  return TCS_OK;
+}
+
 extern "C" {
 
 int tcs_debug_conv(int32_t engine, int32_t precision, int32_t B, int32_t H_out, int32_t W_out, int32_t cin0,
@@ -1130,7 +1394,6 @@ int tcs_debug_conv(int32_t engine, int32_t precision, int32_t B, int32_t H_out, 
   if (H_out != W_out) return fail(TCS_ERR_UNSUPPORTED, "tcs_debug_conv: square outputs only");
   const bool bf16 = precision == TCS_BF16;
   const int eng = engine == TCS_ENGINE_AUTO ? (bf16 ? TCS_ENGINE_TCGEN05 : TCS_ENGINE_SIMT) : engine;
-  if (eng == TCS_ENGINE_TCGEN05 && !bf16) return fail(TCS_ERR_UNSUPPORTED, "the tcgen05 engine needs precision = bf16");
   ConvGeom g;
   g.B = B; g.H = H_out; g.W = W_out; g.ksize = ksize; g.stride = stride;
   g.nsrc = cin1 > 0 ? 2 : 1;
@@ -1138,6 +1401,8 @@ int tcs_debug_conv(int32_t engine, int32_t precision, int32_t B, int32_t H_out, 
   g.in_pad[0] = g.in_pad[1] = ksize == 1 ? 0 : 1;
   g.ntot = cout;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // fp32 on the tcgen05 engine = bf16x3 mode: always the raw fp32 epilogue (its padded / plain forms are separate kernels)
+  if (eng == TCS_ENGINE_TCGEN05 && !bf16) return debug_conv_split3(g, in0, in1, weight, bias, out, stats, epi, st);
   if (bf16) return debug_conv_t<__nv_bfloat16>(eng == TCS_ENGINE_TCGEN05, g, in0, in1, weight, bias, out, stats, epi, st);
   return debug_conv_t<float>(false, g, in0, in1, weight, bias, out, stats, epi, st);
 }

@@ -18,6 +18,7 @@ import ctypes as C
 import math
 import os
 import warnings
+import weakref
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
@@ -265,6 +266,8 @@ def adopt(model: nn.Module, precision: Optional[str] = None) -> CondUNetTiny:
     fast = fast.to(next(iter(sd.values())).device).eval()
     fast._key_by_checksum = True
     fast.refresh()
+    if hit is None:   # drop the libtcs twin (and its device workspace) together with the module it shadows
+        weakref.finalize(model, _adopted.pop, id(model), None)
     _adopted[id(model)] = (tuple(sorted(arch.items())), fast)
     return fast
 
