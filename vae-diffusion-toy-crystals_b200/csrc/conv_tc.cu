@@ -41,6 +41,13 @@ constexpr int UC = 96;                 // accumulator columns per epilogue warp 
 constexpr int BLK = 32;                // channels per staged output block (three blocks per warp and tile)
 constexpr int TC_THREADS = 64 + 32 * EPI_WARPS + 32;   // + a second MMA-issuing warp for the MSUB = 2 tiles
 constexpr int MAX_STAGES = 8;
+// K block of a pipeline stage: 64 input channels = one 128-byte row per pixel / per output channel (SWIZZLE_128B).
+// 128-byte rows instead of 64-byte ones halve the number of TMA / L2 requests per operand byte, which is what bounds the
+// operand feed (round 2: moving the weights from 64-byte to 512-byte rows alone was worth +8 %).  A source whose channel
+// count is not a multiple of 64 (96 = 64 + 32) ends in a half block: TMA zero-fills the missing channels without
+// requesting them and the issuer skips their two K steps.
+constexpr int KB = 64;
+constexpr uint32_t ROWB = KB * 2;
 constexpr int SLAB_BUFS = 2;                            // staging blocks per epilogue warp (1 frees an operand stage: measured no gain)
 constexpr uint32_t EPI_WARP_SLAB = SLAB_BUFS * 32 * BLK * 2;    // per epilogue warp: 32 px x BLK ch bf16 blocks
 constexpr uint32_t EPI_SLAB_BYTES = EPI_WARPS * EPI_WARP_SLAB;
@@ -301,22 +308,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 const uint32_t b_dst = a_dst + p.a_bytes;
                 if (CG == 2) {
                   // both CTAs' loads complete on the LEADER's full barrier; the leader arms it for both
-                  if (cta_rank == 0) ptx::mbar_expect_tx(full, 2 * (p.a_bytes + p.T * NB * 64));
-                  ptx::tma_load_4d_2sm(a_dst, mapA, full, cb * 32, kx + p.kxn + p.base_off[src],
+                  if (cta_rank == 0) ptx::mbar_expect_tx(full, 2 * (p.a_bytes + p.T * NB * ROWB));
+                  ptx::tma_load_4d_2sm(a_dst, mapA, full, cb * KB, kx + p.kxn + p.base_off[src],
                                        p.stride * y0 + kyg + p.base_off[src], b);
                   if (p.pair)
-                    ptx::tma_load_4d_2sm(a_dst + p.a_bytes / 2, mapA, full, cb * 32, kx + p.kxn + p.base_off[src],
+                    ptx::tma_load_4d_2sm(a_dst + p.a_bytes / 2, mapA, full, cb * KB, kx + p.kxn + p.base_off[src],
                                          p.stride * y0 + kyg + p.base_off[src], b + 1);
                   // weights: ONE box of 512-byte rows (the T taps of this CTA's N/2 rows, stored in global memory as the
                   // exact SWIZZLE_64B shared-memory image): 4x fewer TMA/L2 requests than 64-byte rows
                   ptx::tma_load_2d_2sm(b_dst, &mapW, full, 0,
                                        ((ks * p.n_ntiles + nt) * 2 + static_cast<int>(cta_rank)) * p.b_rows);
                 } else {
-                  ptx::mbar_expect_tx(full, p.a_bytes + p.T * N * 64);
-                  ptx::tma_load_4d(a_dst, mapA, full, cb * 32, kx + p.kxn + p.base_off[src],
+                  ptx::mbar_expect_tx(full, p.a_bytes + p.T * N * ROWB);
+                  ptx::tma_load_4d(a_dst, mapA, full, cb * KB, kx + p.kxn + p.base_off[src],
                                    p.stride * y0 + kyg + p.base_off[src], b);
                   if (p.pair)
-                    ptx::tma_load_4d(a_dst + p.a_bytes / 2, mapA, full, cb * 32, kx + p.kxn + p.base_off[src],
+                    ptx::tma_load_4d(a_dst + p.a_bytes / 2, mapA, full, cb * KB, kx + p.kxn + p.base_off[src],
                                      p.stride * y0 + kyg + p.base_off[src], b + 1);
                   ptx::tma_load_2d(b_dst, &mapW, full, 0, (ks * p.n_ntiles + nt) * p.b_rows);
                 }
@@ -335,7 +342,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     // are issued by two warps (sub 0: warp 1, sub 1: warp 10); each commits its own MMAs, so the stage / accumulator
     // barriers expect two arrivals.  The sub-tile range and the tap count are compile-time in mma_role.
     constexpr uint32_t idesc = make_idesc(128 * CG, N);
-    const uint32_t row_shift = p.W * 64;  // one image row inside the window
+    const uint32_t row_shift = p.W * ROWB;  // one image row inside the window
     const uint32_t sub_stride = p.pair ? p.a_bytes / 2 : p.Rt * row_shift;  // second sub-tile: next window / next rows
     const uint32_t a_inc_j = row_shift >> 4, a_inc_sub = sub_stride >> 4;
     auto run = [&](auto sub_lo_c, auto sub_hi_c) {
@@ -344,53 +351,68 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       const bool prof = TCS_KERNEL_PROFILE && (p.debug & 128) && blockIdx.x == 0 && warp == 1;
       long long w_empty = 0, w_full = 0, t_begin = prof ? clock64() : 0;
       int ntile = 0;
+      const int stages_per_cb = p.KYG * p.KW;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         long long c0 = prof ? clock64() : 0;
         ptx::mbar_wait(ptx::smem_u32(&bars.tmem_empty[acc]), acc_phase ^ 1);
         ptx::tc_fence_after();
         if (prof) { w_empty += clock64() - c0; ++ntile; }
-        for (int ks = 0; ks < p.kstages; ++ks) {
-          c0 = prof ? clock64() : 0;
-          ptx::mbar_wait(ptx::smem_u32(&bars.full[stage]), phase);
-          ptx::tc_fence_after();
-          if (prof) w_full += clock64() - c0;
-          if (lane == 0) {
-            // descriptors: one base per operand and stage, then 16-byte-unit increments
-            const uint32_t a_base = smem_base + stage * p.stage_bytes;
-            const uint64_t adesc = make_desc_sw64(a_base), bdesc = make_desc_sw64(a_base + p.a_bytes);
-            const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
-            // running 64-bit descriptors: one uniform 64-bit add per operand and MMA (the issuing thread is the
-            // bottleneck of this kernel, every instruction in this loop costs ~10 cycles of issue time per MMA)
-            uint64_t adj = adesc + static_cast<uint64_t>(SUB_LO * a_inc_sub), bdj = bdesc;
-            const uint64_t a_step = a_inc_j, a_sub = a_inc_sub;
-            for (int j = 0; j < p.T; ++j) {
-              uint64_t ad = adj;
+        int ks = 0;
+        for (int src = 0; src < p.nsrc; ++src)
+          for (int cb = 0; cb < p.cblk[src]; ++cb) {
+            // K steps (16 channels each) of this channel block: 4, or 2 for the half block that ends a 96-channel source
+            const int ksteps = (cb == p.cblk[src] - 1 && p.ctail[src]) ? 2 : 4;
+            for (int sc = 0; sc < stages_per_cb; ++sc, ++ks) {
+              c0 = prof ? clock64() : 0;
+              ptx::mbar_wait(ptx::smem_u32(&bars.full[stage]), phase);
+              ptx::tc_fence_after();
+              if (prof) w_full += clock64() - c0;
+              if (lane == 0) {
+                // descriptors: one base per operand and stage, then 16-byte-unit increments
+                const uint32_t a_base = smem_base + stage * p.stage_bytes;
+                const uint64_t adesc = make_desc_sw128(a_base), bdesc = make_desc_sw128(a_base + p.a_bytes);
+                const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
+                // running 64-bit descriptors: one uniform 64-bit add per operand and MMA (the issuing thread is the
+                // bottleneck of this kernel, every instruction in this loop costs ~10 cycles of issue time per MMA)
+                uint64_t adj = adesc + static_cast<uint64_t>(SUB_LO * a_inc_sub), bdj = bdesc;
+                const uint64_t a_step = a_inc_j, a_sub = a_inc_sub;
+                for (int j = 0; j < p.T; ++j) {
+                  uint64_t ad = adj;
 #pragma unroll
-              for (int sub = SUB_LO; sub < SUB_HI; ++sub) {
-                const uint32_t first = (ks | j) != 0 ? 1u : 0u;
-                if (CG == 2) {
-                  ptx::umma_bf16_2sm(d_tmem + sub * N, ad, bdj, idesc, first);
-                  ptx::umma_bf16_2sm(d_tmem + sub * N, ad + 2, bdj + 2, idesc, 1u);
-                } else {
-                  ptx::umma_bf16(d_tmem + sub * N, ad, bdj, idesc, first);
-                  ptx::umma_bf16(d_tmem + sub * N, ad + 2, bdj + 2, idesc, 1u);
+                  for (int sub = SUB_LO; sub < SUB_HI; ++sub) {
+                    const uint32_t first = (ks | j) != 0 ? 1u : 0u;
+                    if (CG == 2) {
+                      ptx::umma_bf16_2sm(d_tmem + sub * N, ad, bdj, idesc, first);
+                      ptx::umma_bf16_2sm(d_tmem + sub * N, ad + 2, bdj + 2, idesc, 1u);
+                      if (ksteps == 4) {
+                        ptx::umma_bf16_2sm(d_tmem + sub * N, ad + 4, bdj + 4, idesc, 1u);
+                        ptx::umma_bf16_2sm(d_tmem + sub * N, ad + 6, bdj + 6, idesc, 1u);
+                      }
+                    } else {
+                      ptx::umma_bf16(d_tmem + sub * N, ad, bdj, idesc, first);
+                      ptx::umma_bf16(d_tmem + sub * N, ad + 2, bdj + 2, idesc, 1u);
+                      if (ksteps == 4) {
+                        ptx::umma_bf16(d_tmem + sub * N, ad + 4, bdj + 4, idesc, 1u);
+                        ptx::umma_bf16(d_tmem + sub * N, ad + 6, bdj + 6, idesc, 1u);
+                      }
+                    }
+                    ad += a_sub;
+                  }
+                  adj += a_step;
+                  bdj += (NB * ROWB) >> 4;
                 }
-                ad += a_sub;
+                if (CG == 2) {
+                  ptx::umma_commit_2sm(ptx::smem_u32(&bars.empty[stage]));
+                  if (ks == p.kstages - 1) ptx::umma_commit_2sm(ptx::smem_u32(&bars.tmem_full[acc]));
+                } else {
+                  ptx::umma_commit(ptx::smem_u32(&bars.empty[stage]));
+                  if (ks == p.kstages - 1) ptx::umma_commit(ptx::smem_u32(&bars.tmem_full[acc]));
+                }
               }
-              adj += a_step;
-              bdj += (NB * 64) >> 4;
-            }
-            if (CG == 2) {
-              ptx::umma_commit_2sm(ptx::smem_u32(&bars.empty[stage]));
-              if (ks == p.kstages - 1) ptx::umma_commit_2sm(ptx::smem_u32(&bars.tmem_full[acc]));
-            } else {
-              ptx::umma_commit(ptx::smem_u32(&bars.empty[stage]));
-              if (ks == p.kstages - 1) ptx::umma_commit(ptx::smem_u32(&bars.tmem_full[acc]));
+              __syncwarp();
+              if (++stage == static_cast<uint32_t>(p.nstage)) { stage = 0; phase ^= 1; }
             }
           }
-          __syncwarp();
-          if (++stage == static_cast<uint32_t>(p.nstage)) { stage = 0; phase ^= 1; }
-        }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       if (prof && lane == 0)
@@ -855,14 +877,14 @@ int conv_tc_kstages(const ConvGeom& g) {
   int T, KYG, KW;
   stage_shape(g, &T, &KYG, &KW);
   int cb = 0;
-  for (int s = 0; s < g.nsrc; ++s) cb += g.csrc[s] / 32;
+  for (int s = 0; s < g.nsrc; ++s) cb += (g.csrc[s] + KB - 1) / KB;
   return cb * KYG * KW * (g.split3 ? 3 : 1);
 }
 
 size_t conv_tc_packed_elems(const ConvGeom& g) {
   int T, KYG, KW;
   stage_shape(g, &T, &KYG, &KW);
-  return static_cast<size_t>(conv_tc_kstages(g)) * T * g.ntot * 32;
+  return static_cast<size_t>(conv_tc_kstages(g)) * T * g.ntot * KB;
 }
 
 // N tile and CTA-pair choice of a layer (shared by the weight packer and the plan)
@@ -876,9 +898,10 @@ void conv_tc_tile_shape(const ConvGeom& g, int epi, int* N, int* cg) {
   if (epi == EPI_EPS && !(e && atoi(e) == 1) && !(e2 && atoi(e2) == 1)) *cg = 2;
 }
 
-// Packed layout: [K stage][N tile][CTA of the pair][tap][N/cg rows][32 channels], every 64-byte row with its 16-byte
-// chunks permuted as SWIZZLE_64B would place them (chunk ^ ((row >> 1) & 3)), i.e. the shared-memory image itself, so
-// that TMA can move a stage's weights as one box of 512-byte rows without swizzling.
+// Packed layout: [K stage][N tile][CTA of the pair][tap][N/cg rows][64 channels], every 128-byte row with its 16-byte
+// chunks permuted as SWIZZLE_128B would place them (chunk ^ (row & 7)), i.e. the shared-memory image itself, so that TMA
+// can move a stage's weights as one box of 512-byte rows without swizzling.  Channels past the end of a source (the
+// upper half of the block that ends a 96-channel source) are zero and never read by the MMAs.
 void conv_tc_pack_weights(const ConvGeom& g, int epi, const float* w, __nv_bfloat16* out) {
   int T, KYG, KW, N, cg;
   stage_shape(g, &T, &KYG, &KW);
@@ -892,22 +915,23 @@ void conv_tc_pack_weights(const ConvGeom& g, int epi, const float* w, __nv_bfloa
   const int nseg = g.split3 ? 3 : 1;          // K segments per logical source: [w_hi, w_lo, w_hi] against [a_hi, a_hi, a_lo]
   for (int s = 0; s < g.nsrc; ++s) {
     for (int seg = 0; seg < nseg; ++seg)
-      for (int cb = 0; cb < g.csrc[s] / 32; ++cb)
+      for (int cb = 0; cb < (g.csrc[s] + KB - 1) / KB; ++cb)
         for (int kyg = 0; kyg < KYG; ++kyg)
           for (int kx = 0; kx < KW; ++kx, ++ks)
             for (int j = 0; j < T; ++j) {
               const int ky = (g.ksize == 4) ? kyg + 2 * j : j;
               for (int n = 0; n < g.ntot; ++n)
-                for (int c = 0; c < 32; ++c) {
-                  const int ci = coff + cb * 32 + c;
+                for (int c = 0; c < KB; ++c) {
+                  const int ci = coff + cb * KB + c;
                   float v;
-                  if (g.kx_in_n) v = n < k ? w[((static_cast<size_t>(0) * cin_tot + ci) * k + ky) * k + n] : 0.f;   // column n = tap kx
+                  if (cb * KB + c >= g.csrc[s]) v = 0.f;
+                  else if (g.kx_in_n) v = n < k ? w[((static_cast<size_t>(0) * cin_tot + ci) * k + ky) * k + n] : 0.f;   // column n = tap kx
                   else v = w[((static_cast<size_t>(n) * cin_tot + ci) * k + ky) * k + kx];
                   __nv_bfloat16 hi = __float2bfloat16(v);
                   if (seg == 1) hi = __float2bfloat16(v - __bfloat162float(hi));   // w_lo
                   const int nt = n / N, nn = n % N, half = nn / NB, r = nn % NB;
-                  const int pc = (c / 8) ^ ((r >> 1) & 3);
-                  out[((((ks * n_ntiles + nt) * cg + half) * T + j) * NB + r) * 32 + pc * 8 + (c % 8)] = hi;
+                  const int pc = (c / 8) ^ (r & 7);
+                  out[((((ks * n_ntiles + nt) * cg + half) * T + j) * NB + r) * KB + pc * 8 + (c % 8)] = hi;
                 }
             }
     coff += g.csrc[s];
@@ -939,20 +963,20 @@ int conv_tc_make_pair(ConvTcPlan* pl, const void* src, int B) {
   p.WR = p.Rt + p.T - 1;
   p.tiles_per_img = p.H / p.Rt;                       // tiles per image PAIR
   p.n_mtiles = (B / 2) * p.tiles_per_img;
-  p.a_bytes = 2u * static_cast<uint32_t>(p.WR) * p.W * 64;
-  p.stage_bytes = (p.a_bytes + p.T * (pl->N / pl->cg) * 64 + 1023u) & ~1023u;
+  p.a_bytes = 2u * static_cast<uint32_t>(p.WR) * p.W * ROWB;
+  p.stage_bytes = (p.a_bytes + p.T * (pl->N / pl->cg) * ROWB + 1023u) & ~1023u;
   const size_t budget = 227 * 1024 - 2048 - 1024 - EPI_SLAB_BYTES - EPI_BIAS_BYTES - EPI_FUSED_BYTES;
   p.nstage = static_cast<int>(budget / p.stage_bytes);
   if (p.nstage > MAX_STAGES) p.nstage = MAX_STAGES;
   pl->smem = static_cast<size_t>(p.nstage) * p.stage_bytes + 1024 + EPI_SLAB_BYTES + EPI_BIAS_BYTES + EPI_FUSED_BYTES;
-  const cuuint64_t C = static_cast<cuuint64_t>(p.cblk[0]) * 32;
+  const cuuint64_t C = static_cast<cuuint64_t>(pl->cin[0]);
   const int Hin = p.H + 2, Win = p.W + 2;
   cuuint64_t dims[4] = {C, static_cast<cuuint64_t>(Win), static_cast<cuuint64_t>(Hin), static_cast<cuuint64_t>(B)};
   cuuint64_t strides[3] = {C * 2, C * 2 * Win, C * 2 * Win * Hin};
-  cuuint32_t box[4] = {32, static_cast<cuuint32_t>(p.W), static_cast<cuuint32_t>(p.WR), 1};
+  cuuint32_t box[4] = {KB, static_cast<cuuint32_t>(p.W), static_cast<cuuint32_t>(p.WR), 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = encode(&pl->mapA[0], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(src), dims, strides, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(TCS_ERR_CUDA, "cuTensorMapEncodeTiled(A pair) failed: " + std::to_string(r));
   for (int i = 1; i < 4; ++i) pl->mapA[i] = pl->mapA[0];
@@ -1130,6 +1154,7 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, con
   p.guidance = 0.f;
   p.WR = p.Rt * pl.msub + p.T - 1;
   p.nsrc = g.nsrc * (g.split3 ? 3 : 1);
+  pl.cin[0] = g.csrc[0]; pl.cin[1] = g.csrc[g.nsrc > 1 ? 1 : 0];
   if (g.split3 && (!lo0 || (g.nsrc == 2 && !lo1))) return fail(TCS_ERR_BAD_ARGUMENT, "conv_tc: bf16x3 mode needs the lo parts of its sources");
   if (g.split3 && epi != EPI_RAW_STATS) return fail(TCS_ERR_UNSUPPORTED, "conv_tc: bf16x3 mode writes fp32 (EPI_RAW_STATS) only");
   p.ntot = g.ntot;
@@ -1137,8 +1162,8 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, con
   p.n_mtiles = g.B * p.tiles_per_img;
   p.n_ntiles = g.ntot / pl.N;
   p.kstages = conv_tc_kstages(g);
-  p.a_bytes = static_cast<uint32_t>(p.WR) * g.W * 64;
-  p.stage_bytes = (p.a_bytes + p.T * (pl.N / pl.cg) * 64 + 1023u) & ~1023u;
+  p.a_bytes = static_cast<uint32_t>(p.WR) * g.W * ROWB;
+  p.stage_bytes = (p.a_bytes + p.T * (pl.N / pl.cg) * ROWB + 1023u) & ~1023u;
   const size_t budget = 227 * 1024 - 2048 - 1024 - EPI_SLAB_BYTES - EPI_BIAS_BYTES - EPI_FUSED_BYTES;
   p.nstage = static_cast<int>(budget / p.stage_bytes);
   if (p.nstage > MAX_STAGES) p.nstage = MAX_STAGES;
@@ -1167,7 +1192,9 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, con
     const int conv_pad = (g.ksize == 1) ? 0 : 1;           // halo 1, conv pad: 3x3 -> 1, 4x4/s2 -> 1, 1x1 -> 0
     p.base_off[ps] = g.in_pad[li] - conv_pad;
     if (p.base_off[ps] < 0) return fail(TCS_ERR_BAD_ARGUMENT, "conv_tc: a 3x3/4x4 conv needs a padded source");
-    p.cblk[ps] = g.csrc[li] / 32;
+    p.cblk[ps] = (g.csrc[li] + KB - 1) / KB;
+    p.ctail[ps] = (g.csrc[li] % KB) ? 1 : 0;
+    if (g.csrc[li] % 32) return fail(TCS_ERR_UNSUPPORTED, "conv_tc: source channels must be a multiple of 32");
     p.msel[ps] = g.split3 ? 2 * li + (ps % 3 == 2 ? 1 : 0) : li;   // [a_hi, a_hi, a_lo]
   }
   for (int s = 0; s < 4; ++s) {
@@ -1178,16 +1205,16 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, con
     const cuuint64_t C = g.csrc[si];
     cuuint64_t dims[4] = {C, static_cast<cuuint64_t>(Win), static_cast<cuuint64_t>(Hin), static_cast<cuuint64_t>(g.B)};
     cuuint64_t strides[3] = {C * 2, C * 2 * Win, C * 2 * Win * Hin};
-    cuuint32_t box[4] = {32, static_cast<cuuint32_t>(g.W * g.stride), static_cast<cuuint32_t>(p.WR * g.stride), 1};
+    cuuint32_t box[4] = {KB, static_cast<cuuint32_t>(g.W * g.stride), static_cast<cuuint32_t>(p.WR * g.stride), 1};
     cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(g.stride), static_cast<cuuint32_t>(g.stride), 1};
     CUresult r = encode(&pl.mapA[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(srcs[s]), dims, strides,
-                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(TCS_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed: " + std::to_string(r));
   }
   {
     // the packed weights ARE the swizzled shared-memory image: plain (unswizzled) 512-byte rows
-    const uint32_t stage_b = static_cast<uint32_t>(p.T) * (pl.N / pl.cg) * 64;     // bytes per stage and CTA
+    const uint32_t stage_b = static_cast<uint32_t>(p.T) * (pl.N / pl.cg) * ROWB;   // bytes per stage and CTA
     if (stage_b % 512) return fail(TCS_ERR_UNSUPPORTED, "conv_tc: weight stage is not a multiple of 512 bytes");
     p.b_rows = static_cast<int>(stage_b / 512);
     cuuint64_t dims[2] = {256, static_cast<cuuint64_t>(p.kstages) * p.n_ntiles * pl.cg * p.b_rows};

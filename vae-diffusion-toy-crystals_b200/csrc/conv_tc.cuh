@@ -15,6 +15,7 @@ struct ConvTcParams {
   int stride, WR;           // conv stride; window rows per stage
   int nsrc, cblk[6], base_off[6];   // PHYSICAL sources (K segments): 1-2 normally, 3 per logical source in bf16x3 mode
   int msel[6];              // tensor map (0..3) each physical source reads
+  int ctail[6];             // 1 = the source's last 64-channel block holds 32 channels only (two K steps instead of four)
   int ntot;                 // total output channels
   int kstages;              // pipeline stages (K iterations) per tile
   int b_rows;               // 512-byte rows of packed weights per stage and CTA
@@ -40,6 +41,7 @@ struct ConvTcPlan {
   int msub;    // 128-row sub-tiles per CTA tile
   int cg;      // 1 = one CTA per MMA, 2 = CTA pairs (tcgen05 cta_group::2, weights split across the pair)
   int grid;
+  int cin[2] = {0, 0};       // channels of the logical sources
   int max_ctas = 0;          // CTAs of this kernel the device holds at once (cudaOccupancyMaxActiveClusters x 2 for pairs)
   bool coop_cluster = false; // launch the fused-GroupNorm CTA pairs with the cooperative attribute as well
   size_t smem;
@@ -49,7 +51,7 @@ struct ConvTcPlan {
 // number of K stages and packed weight element count for a geometry
 int conv_tc_kstages(const ConvGeom& g);
 size_t conv_tc_packed_elems(const ConvGeom& g);
-// weight [ntot][cin_total][k][k] fp32 (PyTorch layout) -> bf16 [kstage][T][ntot][32]
+// weight [ntot][cin_total][k][k] fp32 (PyTorch layout) -> bf16 [kstage][N tile][CTA][tap][rows][64] (see conv_tc.cu)
 // (bf16x3 mode: per logical source the K segments [w_hi, w_lo, w_hi], matching the A segments [a_hi, a_hi, a_lo])
 void conv_tc_pack_weights(const ConvGeom& g, int epi, const float* w, __nv_bfloat16* out_host);
 void conv_tc_tile_shape(const ConvGeom& g, int epi, int* N, int* cg);
