@@ -40,7 +40,8 @@ constexpr int GRP_WARPS = EPI_WARPS / 2;
 constexpr int UC = 96;                 // accumulator columns per epilogue warp (4 lane quarters x 2 column units cover 192)
 constexpr int BLK = 32;                // channels per staged output block (three blocks per warp and tile)
 constexpr int TC_THREADS = 64 + 32 * EPI_WARPS + 32;   // + a second MMA-issuing warp for the MSUB = 2 tiles
-constexpr int MAX_STAGES = 8;
+constexpr int MAX_STAGES = 12;
+constexpr int MAX_A_STAGES = 4;
 // K block of a pipeline stage: 64 input channels = one 128-byte row per pixel / per output channel (SWIZZLE_128B).
 // 128-byte rows instead of 64-byte ones halve the number of TMA / L2 requests per operand byte, which is what bounds the
 // operand feed (round 2: moving the weights from 64-byte to 512-byte rows alone was worth +8 %).  A source whose channel
@@ -52,6 +53,9 @@ constexpr int SLAB_BUFS = 2;                            // staging blocks per ep
 constexpr uint32_t EPI_WARP_SLAB = SLAB_BUFS * 32 * BLK * 2;    // per epilogue warp: 32 px x BLK ch bf16 blocks
 constexpr uint32_t EPI_SLAB_BYTES = EPI_WARPS * EPI_WARP_SLAB;
 constexpr uint32_t EPI_BIAS_BYTES = 576 * 4;
+// shared memory a CTA may use: 227 KB minus the static part (barriers) and the worst-case 1024-byte alignment of the ring
+constexpr size_t TC_SMEM_MAX = 227 * 1024 - 512;
+__host__ __device__ constexpr uint32_t bias_bytes_of(int ntot) { return (static_cast<uint32_t>(ntot) * 4u + 127u) & ~127u; }
 struct EpiGroupSmem {          // per epilogue warp group (EPI_GN_FUSED)
   float scale[192], shift[192];
   float red[GRP_WARPS][16];    // per warp: (sum, sum of squares) of the 8 GroupNorm groups over its block
@@ -135,10 +139,14 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
 // W >= 32: the warp stages the 2 KB block in a SWIZZLE_64B slab (two halves, double buffered) and one lane TMA-stores it
 // (plus the wrapped row copy); only the lanes on the left/right image border write their column-halo copy themselves.
 // W == 16: plain per-lane 16-byte stores (the 16x16 layers are small).
+// GEO == 1: the 32 lanes are 4 image rows x 8 pixels (lane = 8 * row + pixel); one TMA store of an 8-pixel x 4-row box,
+// plus a one-row box (mapO1, geo_H = image height) when the block holds image row 0 or H - 1 (the wrapped halo rows).
+template <int GEO = 0>
 __device__ __forceinline__ void store_padded_block(const CUtensorMap* mapO, bool use_tma, uint32_t slab, uint32_t& slab_buf,
                                                    int lane, __nv_bfloat16* obase, size_t pix, int wy, int wx, int Wp,
                                                    int ldo, int ch, int img, int y, int x, const uint32_t* pk,
-                                                   long long* tacc = nullptr, int h16 = 0) {
+                                                   long long* tacc = nullptr, int h16 = 0,
+                                                   const CUtensorMap* mapO1 = nullptr, int geo_H = 0) {
   if (!use_tma) {
     store_with_halo(obase, pix, wy, wx, Wp, ldo, ch, pk);
     return;
@@ -156,7 +164,11 @@ __device__ __forceinline__ void store_padded_block(const CUtensorMap* mapO, bool
   __syncwarp();
   if (tacc) { const long long c1 = clock64(); tacc[1] += c1 - c0; c0 = c1; }
   if (lane == 0) {   // lane 0 holds the first pixel of the block: (y, x) -> padded (y+1, x+1)
-    if (h16 == 0) {
+    if (GEO == 1) {
+      tma_store_4d(mapO, base, ch, x + 1, y + 1, img);
+      if (y == 0) tma_store_4d(mapO1, base, ch, x + 1, geo_H + 1, img);                  // row 0 -> also padded row H + 1
+      if (y + 4 == geo_H) tma_store_4d(mapO1, base + 3 * 512, ch, x + 1, 0, img);        // row H - 1 -> also padded row 0
+    } else if (h16 == 0) {
       tma_store_4d(mapO, base, ch, x + 1, y + 1, img);
       if (wy) tma_store_4d(mapO, base, ch, x + 1, y + 1 + wy, img);
     } else {         // 16-pixel rows: the block is image rows y (lanes 0-15) and y + 1 (lanes 16-31), one 16-pixel box each
@@ -216,6 +228,8 @@ __device__ __forceinline__ void tile_to_mn(int tile, int n_ntiles, int& mt, int&
 struct __align__(8) TcBarriers {
   uint64_t full[MAX_STAGES];
   uint64_t empty[MAX_STAGES];
+  uint64_t fullA[MAX_A_STAGES];    // geo 1: the window ring
+  uint64_t emptyA[MAX_A_STAGES];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
@@ -225,12 +239,23 @@ struct __align__(8) TcBarriers {
 // its TMEM accumulators, its epilogue), but one tcgen05.mma.cta_group::2 of the leader drives both tensor cores
 // with M = 256 and reads the weight tile HALF from each CTA's shared memory: every CTA fetches only N/2 weight
 // rows per stage, which halves the dominant L2 -> SM operand stream.
-template <int N, int EPI, int MSUB, int CG>
+//
+// GEO = 1 (the 3x3 stride-1 layers, ~90 % of the FLOPs): "tap-shift" geometry.  A 128-row sub-tile is 16 image rows x 8
+// pixels, so that an 8-row core group of the UMMA descriptor is 8 consecutive pixels of ONE image row and the group
+// stride (SBO) is one row of the shared-memory window.  The window of a 64-channel block, (16 + 2) x (8 MSUB + 2) pixels
+// with the halo, is loaded ONCE and all nine taps are start-address shifts of (ky P + kx) * 128 B into it (the swizzle
+// is a function of the absolute shared-memory address, so neither the 128-byte shifts nor a window pitch that is not a
+// multiple of 1024 B need the descriptor's base-offset field: probed on the hardware by tools/umma_shift_test.cu).
+// GEO = 0 fetched a full-width window per kx (each input pixel 4.5 x per tile); GEO = 1 fetches it 1.27 x (MSUB = 2),
+// which halves the L2 -> SM operand stream that bounded the 64x64 layers (no-TMA experiment: +39 %).  The windows have
+// their own ring (fullA / emptyA); the weights stream through the stage ring in stages of p.tb taps.
+template <int N, int EPI, int MSUB, int CG, int GEO>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
                const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapO,
-               const ConvTcParams p) {
+               const __grid_constant__ CUtensorMap mapO1, const ConvTcParams p) {
+  static_assert(GEO == 0 || (EPI != EPI_EPS && EPI != EPI_PLAIN), "tap-shift geometry: padded / fp32 outputs only");
   constexpr int ACC_STRIDE = (N * MSUB <= 128) ? 128 : 256;  // TMEM columns per accumulator stage
   static_assert(N * MSUB <= 256, "accumulator does not fit a double-buffered TMEM stage");
 
@@ -243,10 +268,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   const int n_tiles = p.n_mtiles * p.n_ntiles;
   // after the operand ring: 16 epilogue warps x 2 x 2 KB staging blocks (fp16 stash of the fused epilogue, TMA-store
   // source of every bf16 output), then the bias
-  const uint32_t slab_base = smem_base + p.nstage * p.stage_bytes;
+  const uint32_t b_ring = smem_base + (GEO == 1 ? p.a_stages * p.a_bytes : 0u);   // geo 1: windows first, then weight stages
+  const uint32_t slab_base = b_ring + p.nstage * p.stage_bytes;
   float* bias_s = reinterpret_cast<float*>(smem_raw + (slab_base - ptx::smem_u32(smem_raw)) + EPI_SLAB_BYTES);
   for (int i = threadIdx.x; i < p.ntot; i += TC_THREADS) bias_s[i] = p.epi.bias[i];
-  EpiFusedSmem* fs = reinterpret_cast<EpiFusedSmem*>(reinterpret_cast<uint8_t*>(bias_s) + EPI_BIAS_BYTES);
+  EpiFusedSmem* fs = reinterpret_cast<EpiFusedSmem*>(reinterpret_cast<uint8_t*>(bias_s) + (GEO == 1 ? bias_bytes_of(p.ntot) : EPI_BIAS_BYTES));
   if constexpr (EPI == EPI_GN_FUSED)
     for (int i = threadIdx.x; i < N; i += TC_THREADS) { fs->gamma[i] = p.epi.gamma[i]; fs->beta[i] = p.epi.beta[i]; }
 
@@ -256,10 +282,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     if (p.nsrc > 2) { ptx::prefetch_tmap(&mapA2); ptx::prefetch_tmap(&mapA3); }
     ptx::prefetch_tmap(&mapW);
     if (EPI != EPI_EPS) ptx::prefetch_tmap(&mapO);
+    if (GEO == 1) ptx::prefetch_tmap(&mapO1);
     for (int s = 0; s < p.nstage; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bars.full[s]), 1);
       ptx::mbar_init(ptx::smem_u32(&bars.empty[s]), p.issuers);     // one tcgen05.commit per issuing thread
     }
+    if (GEO == 1)
+      for (int s = 0; s < p.a_stages; ++s) {
+        ptx::mbar_init(ptx::smem_u32(&bars.fullA[s]), 1);
+        ptx::mbar_init(ptx::smem_u32(&bars.emptyA[s]), p.issuers);
+      }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(ptx::smem_u32(&bars.tmem_full[a]), p.issuers);
       ptx::mbar_init(ptx::smem_u32(&bars.tmem_empty[a]), GRP_WARPS * CG);
@@ -278,7 +310,63 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   ptx::tc_fence_after();
   const uint32_t tmem_base = bars.tmem_base;
 
-  if (warp == 0) {
+  if (warp == 0 && GEO == 1) {
+    // ============================== TMA producer, tap-shift geometry ==========
+    uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+    const int b_stages_per_kx = 3 / p.tb;
+    const int b_rows_full = 3 * NB / 4;          // 512-byte rows of the three ky taps of one (block, kx) in the packed weights
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      int mt, nt;
+      tile_to_mn<CG>(tile, p.n_ntiles, mt, nt);
+      const int b = mt / p.tiles_per_img, t = mt - b * p.tiles_per_img;
+      const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
+      int ks = 0;
+      for (int src = 0; src < p.nsrc; ++src) {
+        const int ms = p.msel[src];
+        const CUtensorMap* mapA = ms == 0 ? &mapA0 : (ms == 1 ? &mapA1 : (ms == 2 ? &mapA2 : &mapA3));
+        for (int cb = 0; cb < p.cblk[src]; ++cb) {
+          ptx::mbar_wait(ptx::smem_u32(&bars.emptyA[sa]), pa ^ 1);
+          const bool stale = (p.debug & 8) && (pa || tile != static_cast<int>(blockIdx.x));   // experiment: no TMA
+          if (lane == 0) {
+            const uint32_t full = ptx::smem_u32(&bars.fullA[sa]);
+            const uint32_t a_dst = smem_base + sa * p.a_bytes;
+            if (stale) {
+              if (CG == 1 || cta_rank == 0) ptx::mbar_arrive(full);
+            } else if (CG == 2) {
+              if (cta_rank == 0) ptx::mbar_expect_tx(full, 2 * p.a_load_bytes);
+              ptx::tma_load_4d_2sm(a_dst, mapA, full, cb * KB, tx * 8 * MSUB + p.base_off[src], ty * 16 + p.base_off[src], b);
+            } else {
+              ptx::mbar_expect_tx(full, p.a_load_bytes);
+              ptx::tma_load_4d(a_dst, mapA, full, cb * KB, tx * 8 * MSUB + p.base_off[src], ty * 16 + p.base_off[src], b);
+            }
+          }
+          __syncwarp();
+          if (++sa == static_cast<uint32_t>(p.a_stages)) { sa = 0; pa ^= 1; }
+          for (int kx = 0; kx < 3; ++kx, ++ks)
+            for (int jb = 0; jb < b_stages_per_kx; ++jb) {
+              ptx::mbar_wait(ptx::smem_u32(&bars.empty[sb]), pb ^ 1);
+              const bool stale_b = (p.debug & 8) && (pb || tile != static_cast<int>(blockIdx.x));
+              if (lane == 0) {
+                const uint32_t full = ptx::smem_u32(&bars.full[sb]);
+                const uint32_t b_dst = b_ring + sb * p.stage_bytes;
+                const int row0 = ((ks * p.n_ntiles + nt) * CG + static_cast<int>(cta_rank)) * b_rows_full + jb * p.b_rows;
+                if (stale_b) {
+                  if (CG == 1 || cta_rank == 0) ptx::mbar_arrive(full);
+                } else if (CG == 2) {
+                  if (cta_rank == 0) ptx::mbar_expect_tx(full, 2 * p.tb * NB * ROWB);
+                  ptx::tma_load_2d_2sm(b_dst, &mapW, full, 0, row0);
+                } else {
+                  ptx::mbar_expect_tx(full, p.tb * NB * ROWB);
+                  ptx::tma_load_2d(b_dst, &mapW, full, 0, row0);
+                }
+              }
+              __syncwarp();
+              if (++sb == static_cast<uint32_t>(p.nstage)) { sb = 0; pb ^= 1; }
+            }
+        }
+      }
+    }
+  } else if (warp == 0) {
     // ============================== TMA producer ==============================
     uint32_t stage = 0, phase = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -342,6 +430,88 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     // are issued by two warps (sub 0: warp 1, sub 1: warp 10); each commits its own MMAs, so the stage / accumulator
     // barriers expect two arrivals.  The sub-tile range and the tap count are compile-time in mma_role.
     constexpr uint32_t idesc = make_idesc(128 * CG, N);
+    if constexpr (GEO == 1) {
+      // ---- tap-shift geometry: per 64-channel block one window, nine taps = start shifts; weights in stages of p.tb taps
+      auto run1 = [&](auto sub_lo_c, auto sub_hi_c) {
+        constexpr int SUB_LO = decltype(sub_lo_c)::value, SUB_HI = decltype(sub_hi_c)::value;
+        uint32_t sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, acc_phase = 0;
+        const int b_stages_per_kx = 3 / p.tb;
+        const uint32_t ky_inc = static_cast<uint32_t>(p.P) * (ROWB >> 4);   // one window row, in 16-byte units
+        int nblk = 0;
+        for (int src = 0; src < p.nsrc; ++src) nblk += p.cblk[src];
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+          ptx::mbar_wait(ptx::smem_u32(&bars.tmem_empty[acc]), acc_phase ^ 1);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
+          int blk = 0;
+          for (int src = 0; src < p.nsrc; ++src)
+            for (int cb = 0; cb < p.cblk[src]; ++cb, ++blk) {
+              const int ksteps = (cb == p.cblk[src] - 1 && p.ctail[src]) ? 2 : 4;
+              ptx::mbar_wait(ptx::smem_u32(&bars.fullA[sa]), pa);
+              const uint64_t adesc = make_desc_sw128_sbo(smem_base + sa * p.a_bytes, static_cast<uint32_t>(p.P) * ROWB) +
+                                     static_cast<uint64_t>(SUB_LO * 8 * (ROWB >> 4));
+              for (int kx = 0; kx < 3; ++kx)
+                for (int jb = 0; jb < b_stages_per_kx; ++jb) {
+                  ptx::mbar_wait(ptx::smem_u32(&bars.full[sb]), pb);
+                  ptx::tc_fence_after();
+                  if (lane == 0) {
+                    uint64_t bdj = make_desc_sw128(b_ring + sb * p.stage_bytes);
+                    uint64_t adj = adesc + static_cast<uint64_t>(kx * (ROWB >> 4) + jb * p.tb * ky_inc);
+                    for (int j = 0; j < p.tb; ++j) {
+                      uint64_t ad = adj;
+#pragma unroll
+                      for (int sub = SUB_LO; sub < SUB_HI; ++sub) {
+                        const uint32_t first = (blk | kx | jb | j) != 0 ? 1u : 0u;
+                        if (CG == 2) {
+                          ptx::umma_bf16_2sm(d_tmem + sub * N, ad, bdj, idesc, first);
+                          ptx::umma_bf16_2sm(d_tmem + sub * N, ad + 2, bdj + 2, idesc, 1u);
+                          if (ksteps == 4) {
+                            ptx::umma_bf16_2sm(d_tmem + sub * N, ad + 4, bdj + 4, idesc, 1u);
+                            ptx::umma_bf16_2sm(d_tmem + sub * N, ad + 6, bdj + 6, idesc, 1u);
+                          }
+                        } else {
+                          ptx::umma_bf16(d_tmem + sub * N, ad, bdj, idesc, first);
+                          ptx::umma_bf16(d_tmem + sub * N, ad + 2, bdj + 2, idesc, 1u);
+                          if (ksteps == 4) {
+                            ptx::umma_bf16(d_tmem + sub * N, ad + 4, bdj + 4, idesc, 1u);
+                            ptx::umma_bf16(d_tmem + sub * N, ad + 6, bdj + 6, idesc, 1u);
+                          }
+                        }
+                        ad += 8 * (ROWB >> 4);          // next sub-tile: 8 pixels to the right
+                      }
+                      adj += ky_inc;
+                      bdj += (NB * ROWB) >> 4;
+                    }
+                    const bool last_of_blk = kx == 2 && jb == b_stages_per_kx - 1;
+                    if (CG == 2) {
+                      ptx::umma_commit_2sm(ptx::smem_u32(&bars.empty[sb]));
+                      if (last_of_blk) ptx::umma_commit_2sm(ptx::smem_u32(&bars.emptyA[sa]));
+                      if (last_of_blk && blk == nblk - 1) ptx::umma_commit_2sm(ptx::smem_u32(&bars.tmem_full[acc]));
+                    } else {
+                      ptx::umma_commit(ptx::smem_u32(&bars.empty[sb]));
+                      if (last_of_blk) ptx::umma_commit(ptx::smem_u32(&bars.emptyA[sa]));
+                      if (last_of_blk && blk == nblk - 1) ptx::umma_commit(ptx::smem_u32(&bars.tmem_full[acc]));
+                    }
+                  }
+                  __syncwarp();
+                  if (++sb == static_cast<uint32_t>(p.nstage)) { sb = 0; pb ^= 1; }
+                }
+              if (++sa == static_cast<uint32_t>(p.a_stages)) { sa = 0; pa ^= 1; }
+            }
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+      };
+      using J0 = std::integral_constant<int, 0>;
+      using J1 = std::integral_constant<int, 1>;
+      using JM = std::integral_constant<int, MSUB>;
+      using JL = std::integral_constant<int, MSUB - 1>;
+      if (p.issuers == 2) {
+        if (warp == 1) run1(J0{}, J1{});
+        else run1(JL{}, JM{});
+      } else {
+        run1(J0{}, JM{});
+      }
+    } else {
     const uint32_t row_shift = p.W * ROWB;  // one image row inside the window
     const uint32_t sub_stride = p.pair ? p.a_bytes / 2 : p.Rt * row_shift;  // second sub-tile: next window / next rows
     const uint32_t a_inc_j = row_shift >> 4, a_inc_sub = sub_stride >> 4;
@@ -429,6 +599,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     } else {
       run(I0{}, IM{});
     }
+    }
   } else if (warp >= 2 && warp < 2 + EPI_WARPS) {
     // ============================== epilogue (2 groups x 8 warps) ================
     // What the clock64 profile (TCS_DEBUG=128) showed: the epilogue of a tile is a chain of latencies (TMEM loads of
@@ -456,6 +627,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     (void)use_tma_out; (void)slab;
     const int sub = (MSUB == 2) ? h : 0;
     const int col0 = (MSUB == 2) ? 0 : h * UC;   // first channel (inside the N tile) of this warp's columns
+    // accumulator row -> pixel.  GEO 0: a sub-tile is 128 consecutive pixels of the image in row-major order;
+    // GEO 1: a sub-tile is 16 image rows x 8 pixels (row i -> image row i / 8, pixel i % 8 of the sub-tile's 8)
+    auto pixel_of = [&](int mt_, int& img_, int& y_, int& x_) {
+      if (GEO == 1) {
+        img_ = mt_ / p.tiles_per_img;
+        const int t_ = mt_ - img_ * p.tiles_per_img;
+        const int ty_ = t_ / p.tiles_x, tx_ = t_ - ty_ * p.tiles_x;
+        y_ = ty_ * 16 + (row >> 3);
+        x_ = (tx_ * MSUB + sub) * 8 + (row & 7);
+      } else {
+        const int m_ = (mt_ * MSUB + sub) * 128 + row;
+        img_ = m_ / HW;
+        const int rem_ = m_ - img_ * HW;
+        y_ = rem_ / p.W;
+        x_ = rem_ - y_ * p.W;
+      }
+    };
     uint32_t it = 0;
     const bool prof = TCS_KERNEL_PROFILE && (p.debug & 128) && blockIdx.x == 0 && e == 0;
     long long pw_full = 0, p_ld = 0, p_a = 0, p_b = 0, p_c = 0, pc0 = 0, pc1 = 0, q_post = 0, q_poll = 0, q_npoll = 0, r_math = 0;
@@ -681,9 +869,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         epi_bar_sync(grp);
         if (prof) { pc1 = clock64(); p_b += pc1 - pc0; pc0 = pc1; }
         __nv_bfloat16* obase = static_cast<__nv_bfloat16*>(p.epi.out);
-        const int m = (mt * MSUB + sub) * 128 + row;
-        const int rem = m - img * HW;
-        const int y = rem / p.W, x = rem - y * p.W;
+        int img_px, y, x;
+        pixel_of(mt, img_px, y, x);
+        (void)img_px;
         const int wy = (y == 0) ? p.H : ((y == p.H - 1) ? -p.H : 0);
         const int wx = (x == 0) ? p.W : ((x == p.W - 1) ? -p.W : 0);
         const size_t pix = (static_cast<size_t>(img) * Hp + (y + 1)) * Wp + (x + 1);
@@ -714,14 +902,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             pk[i / 2 + 1] = pack_bf16x2(y2, y3);
           }
           if (!(p.debug & 2))
-            store_padded_block(&mapO, use_tma_out, slab, slab_buf, lane, obase, pix, wy, wx, Wp, p.epi.ldo, cc, img, y, x, pk,
-                               prof ? tacc : nullptr, h16);
+            store_padded_block<GEO>(&mapO, use_tma_out, slab, slab_buf, lane, obase, pix, wy, wx, Wp, p.epi.ldo, cc, img, y, x, pk,
+                                    prof ? tacc : nullptr, GEO == 1 ? 0 : h16, &mapO1, p.H);
           else if (pk[0] == 0x12345678u && pk[7] == 0x9abcdef0u) obase[0] = __float2bfloat16(0.f);
         }
         if (prof) r_math += clock64() - pc1;
       } else if constexpr (N >= 96) {
         const int n_off = nt * N + col0;                     // first output channel of this warp's columns
-        const int m = (mt * MSUB + sub) * 128 + row;         // global pixel index (b, y, x)
+        int b, y, x;
+        pixel_of(mt, b, y, x);
+        const int m = (b * p.H + y) * p.W + x;               // global pixel index (b, y, x)
         float vbuf[2][32];
         ptx::tmem_ld32(taddr, vbuf[0]);
         if constexpr (EPI == EPI_RAW_STATS) {
@@ -762,15 +952,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           if (lane == 0) {
             // slot layout [image][tile-in-image*MSUB + sub][quarter]; the column units of a row block write disjoint
             // groups of the same slot
-            const int b = m / HW;
             const int slot = ((mt * MSUB + sub) % (p.tiles_per_img * MSUB)) * 4 + q;
             float* dst = p.epi.partials + (static_cast<size_t>(b) * p.epi.slots + slot) * 16 + 2 * (col0 / CPGN);
 #pragma unroll
             for (int g = 0; g < NG; ++g) { dst[2 * g] = gs[g]; dst[2 * g + 1] = gq[g]; }
           }
         } else if constexpr (EPI == EPI_PADDED) {
-          const int b = m / HW, rem = m - b * HW;
-          const int y = rem / p.W, x = rem - y * p.W;
           const int wy = (y == 0) ? p.H : ((y == p.H - 1) ? -p.H : 0);
           const int wx = (x == 0) ? p.W : ((x == p.W - 1) ? -p.W : 0);
           __nv_bfloat16* obase = static_cast<__nv_bfloat16*>(p.epi.out);
@@ -804,7 +991,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
               pk[i / 2] = pack_bf16x2(v[i] + b4.x, v[i + 1] + b4.y);
               pk[i / 2 + 1] = pack_bf16x2(v[i + 2] + b4.z, v[i + 3] + b4.w);
             }
-            store_padded_block(&mapO, use_tma_out, slab, slab_buf, lane, obase, pix, wy, wx, Wp, p.epi.ldo, n_off + c0, b, y, x, pk, nullptr, h16);
+            store_padded_block<GEO>(&mapO, use_tma_out, slab, slab_buf, lane, obase, pix, wy, wx, Wp, p.epi.ldo, n_off + c0, b, y, x, pk,
+                                    nullptr, GEO == 1 ? 0 : h16, &mapO1, p.H);
           }
         } else {  // EPI_PLAIN: unpadded bf16 [pixel][ldo] rows; 32 px x 32 ch blocks staged in the warp's slabs and
                   // TMA-stored (a lane-per-row 16-byte store touches 32 different lines per instruction)
@@ -892,6 +1080,9 @@ void conv_tc_tile_shape(const ConvGeom& g, int epi, int* N, int* cg) {
   *N = (epi == EPI_EPS) ? 16 : ((g.ntot % 192 == 0) ? 192 : 96);
   const char* e = getenv("TCS_CG");   // 1 = single-CTA MMA everywhere (A/B switch)
   *cg = (*N >= 96 && !(e && atoi(e) == 1)) ? 2 : 1;
+  // (with 64-channel K blocks a single CTA cannot hold two stages of a whole weight tile of a 3x3 / 4x4 layer: under
+  // the switch only the 1x1 layers and the output conv run single-CTA MMAs)
+  if (*N >= 96 && g.ksize >= 3) *cg = 2;
   // the 96 -> 1 output conv is bound by MMA ISSUE (36 tiny N = 16 MMAs per tile at ~100 cycles each): as a CTA pair one
   // thread's MMA covers both CTAs' tiles, which halves the issue work per tile
   const char* e2 = getenv("TCS_EPS_CG");
@@ -1015,11 +1206,18 @@ static bool coop_cluster_supported() {
   return state == 1;
 }
 
-template <int N, int EPI, int MSUB, int CG>
+// tap-shift geometry (GEO = 1) for every 3x3 stride-1 layer; TCS_GEO=0 keeps the per-kx row windows (A/B switch)
+static int conv_tc_geo(const ConvGeom& g, int epi) {
+  const char* e = getenv("TCS_GEO");
+  if (e && atoi(e) == 0) return 0;
+  return (g.ksize == 3 && g.stride == 1 && !g.kx_in_n && epi != EPI_EPS && epi != EPI_PLAIN && g.H % 16 == 0) ? 1 : 0;
+}
+
+template <int N, int EPI, int MSUB, int CG, int GEO>
 static int set_smem_attr() {
   static bool attr_done = false;
   if (!attr_done) {
-    TCS_CUDA(cudaFuncSetAttribute(conv_tc_kernel<N, EPI, MSUB, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
+    TCS_CUDA(cudaFuncSetAttribute(conv_tc_kernel<N, EPI, MSUB, CG, GEO>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(TC_SMEM_MAX)));
     attr_done = true;
   }
   return TCS_OK;
@@ -1027,10 +1225,10 @@ static int set_smem_attr() {
 
 // CTAs of this kernel instance the device can hold at the same time (1 CTA per SM by shared memory; with CTA pairs,
 // whole clusters only: on a partitioned or partly occupied device fewer pairs fit than SMs / 2)
-template <int N, int EPI, int MSUB, int CG>
+template <int N, int EPI, int MSUB, int CG, int GEO>
 static int max_ctas_t(const ConvTcPlan& pl, int* out) {
-  TCS_CHECK((set_smem_attr<N, EPI, MSUB, CG>()));
-  auto kern = conv_tc_kernel<N, EPI, MSUB, CG>;
+  TCS_CHECK((set_smem_attr<N, EPI, MSUB, CG, GEO>()));
+  auto kern = conv_tc_kernel<N, EPI, MSUB, CG, GEO>;
   if (CG == 2) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = pl.smem; cfg.stream = nullptr;
@@ -1051,10 +1249,10 @@ static int max_ctas_t(const ConvTcPlan& pl, int* out) {
   return TCS_OK;
 }
 
-template <int N, int EPI, int MSUB, int CG>
+template <int N, int EPI, int MSUB, int CG, int GEO>
 static int launch_t(const ConvTcPlan& pl, cudaStream_t st) {
-  auto kern = conv_tc_kernel<N, EPI, MSUB, CG>;
-  TCS_CHECK((set_smem_attr<N, EPI, MSUB, CG>()));
+  auto kern = conv_tc_kernel<N, EPI, MSUB, CG, GEO>;
+  TCS_CHECK((set_smem_attr<N, EPI, MSUB, CG, GEO>()));
   if (EPI == EPI_GN_FUSED)   // the CTAs of an image group exchange (value, flag) words: flag 0 = not written yet
     TCS_CUDA(cudaMemsetAsync(pl.p.epi.partials, 0, sizeof(unsigned long long) * 16 * pl.p.n_mtiles, st));
   cudaLaunchConfig_t cfg{};
@@ -1075,17 +1273,19 @@ static int launch_t(const ConvTcPlan& pl, cudaStream_t st) {
     ++na;
   }
   cfg.attrs = at; cfg.numAttrs = na;
-  TCS_CUDA(cudaLaunchKernelEx(&cfg, kern, pl.mapA[0], pl.mapA[1], pl.mapA[2], pl.mapA[3], pl.mapW, pl.mapO, pl.p));
+  TCS_CUDA(cudaLaunchKernelEx(&cfg, kern, pl.mapA[0], pl.mapA[1], pl.mapA[2], pl.mapA[3], pl.mapW, pl.mapO, pl.mapO1, pl.p));
   TCS_CUDA(cudaGetLastError());
   return TCS_OK;
 }
 
 static int conv_tc_max_ctas(const ConvTcPlan& pl, int* out) {
 #define TCS_TC_CASE(NN, EE, MM)                                                        \
-  if (pl.N == NN && pl.epi == EE && pl.msub == MM) {                                    \
-    if (pl.cg == 2) { if constexpr (NN >= 96 || EE == EPI_EPS) return max_ctas_t<NN, EE, MM, 2>(pl, out); } \
-    else return max_ctas_t<NN, EE, MM, 1>(pl, out);                                     \
+  if (pl.geo == 0 && pl.N == NN && pl.epi == EE && pl.msub == MM) {                     \
+    if (pl.cg == 2) { if constexpr (NN >= 96 || EE == EPI_EPS) return max_ctas_t<NN, EE, MM, 2, 0>(pl, out); } \
+    else return max_ctas_t<NN, EE, MM, 1, 0>(pl, out);                                  \
   }
+#define TCS_TC_GEO1(NN, EE, MM)                                                        \
+  if (pl.geo == 1 && pl.cg == 2 && pl.N == NN && pl.epi == EE && pl.msub == MM) return max_ctas_t<NN, EE, MM, 2, 1>(pl, out);
   TCS_TC_CASE(96, EPI_RAW_STATS, 2)
   TCS_TC_CASE(96, EPI_PADDED, 2)
   TCS_TC_CASE(96, EPI_PLAIN, 2)
@@ -1095,17 +1295,26 @@ static int conv_tc_max_ctas(const ConvTcPlan& pl, int* out) {
   TCS_TC_CASE(192, EPI_PLAIN, 1)
   TCS_TC_CASE(192, EPI_GN_FUSED, 1)
   TCS_TC_CASE(16, EPI_EPS, 2)
+  TCS_TC_GEO1(96, EPI_RAW_STATS, 2)
+  TCS_TC_GEO1(96, EPI_PADDED, 2)
+  TCS_TC_GEO1(96, EPI_GN_FUSED, 2)
+  TCS_TC_GEO1(192, EPI_RAW_STATS, 1)
+  TCS_TC_GEO1(192, EPI_PADDED, 1)
+  TCS_TC_GEO1(192, EPI_GN_FUSED, 1)
 #undef TCS_TC_CASE
+#undef TCS_TC_GEO1
   return fail(TCS_ERR_UNSUPPORTED, "conv_tc: no kernel instance for this (N, epilogue, msub)");
 }
 
 int conv_tc_launch(const ConvTcPlan& pl, cudaStream_t st) {
   if (!pl.valid) return fail(TCS_ERR_STATE, "conv_tc_launch: plan not built");
 #define TCS_TC_CASE(NN, EE, MM)                                                        \
-  if (pl.N == NN && pl.epi == EE && pl.msub == MM) {                                    \
-    if (pl.cg == 2) { if constexpr (NN >= 96 || EE == EPI_EPS) return launch_t<NN, EE, MM, 2>(pl, st); } \
-    else return launch_t<NN, EE, MM, 1>(pl, st);                                        \
+  if (pl.geo == 0 && pl.N == NN && pl.epi == EE && pl.msub == MM) {                     \
+    if (pl.cg == 2) { if constexpr (NN >= 96 || EE == EPI_EPS) return launch_t<NN, EE, MM, 2, 0>(pl, st); } \
+    else return launch_t<NN, EE, MM, 1, 0>(pl, st);                                     \
   }
+#define TCS_TC_GEO1(NN, EE, MM)                                                        \
+  if (pl.geo == 1 && pl.cg == 2 && pl.N == NN && pl.epi == EE && pl.msub == MM) return launch_t<NN, EE, MM, 2, 1>(pl, st);
   TCS_TC_CASE(96, EPI_RAW_STATS, 2)
   TCS_TC_CASE(96, EPI_PADDED, 2)
   TCS_TC_CASE(96, EPI_PLAIN, 2)
@@ -1115,7 +1324,14 @@ int conv_tc_launch(const ConvTcPlan& pl, cudaStream_t st) {
   TCS_TC_CASE(192, EPI_PLAIN, 1)
   TCS_TC_CASE(192, EPI_GN_FUSED, 1)
   TCS_TC_CASE(16, EPI_EPS, 2)
+  TCS_TC_GEO1(96, EPI_RAW_STATS, 2)
+  TCS_TC_GEO1(96, EPI_PADDED, 2)
+  TCS_TC_GEO1(96, EPI_GN_FUSED, 2)
+  TCS_TC_GEO1(192, EPI_RAW_STATS, 1)
+  TCS_TC_GEO1(192, EPI_PADDED, 1)
+  TCS_TC_GEO1(192, EPI_GN_FUSED, 1)
 #undef TCS_TC_CASE
+#undef TCS_TC_GEO1
   return fail(TCS_ERR_UNSUPPORTED, "conv_tc_launch: no kernel instance for this (N, epilogue, msub)");
 }
 
@@ -1167,8 +1383,37 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, con
   const size_t budget = 227 * 1024 - 2048 - 1024 - EPI_SLAB_BYTES - EPI_BIAS_BYTES - EPI_FUSED_BYTES;
   p.nstage = static_cast<int>(budget / p.stage_bytes);
   if (p.nstage > MAX_STAGES) p.nstage = MAX_STAGES;
-  if (p.nstage < 2) return fail(TCS_ERR_UNSUPPORTED, "conv_tc: stage does not fit shared memory twice");
+  pl.geo = (pl.cg == 2) ? conv_tc_geo(g, epi) : 0;
+  if (!pl.geo && p.nstage < 2) return fail(TCS_ERR_UNSUPPORTED, "conv_tc: stage does not fit shared memory twice");
   pl.smem = static_cast<size_t>(p.nstage) * p.stage_bytes + 1024 + EPI_SLAB_BYTES + EPI_BIAS_BYTES + EPI_FUSED_BYTES;
+  p.geo = pl.geo;
+  p.P = p.tiles_x = p.a_stages = p.tb = 0;
+  p.a_load_bytes = 0;
+  if (pl.geo) {
+    // tap-shift geometry: CTA tile = 16 image rows x 8 MSUB pixels; one (16 + 2) x (8 MSUB + 2) pixel window per
+    // 64-channel block in a ring of its own, the weights in stages of tb taps (three ky taps of one kx, or single taps
+    // when three such stages would not fit: N = 192)
+    if (g.W % (8 * pl.msub) || g.H % 16) return fail(TCS_ERR_UNSUPPORTED, "conv_tc: image is not a multiple of the 16 x 8 tile");
+    const int NB = pl.N / pl.cg;
+    p.P = 8 * pl.msub + 2;
+    p.tiles_x = g.W / (8 * pl.msub);
+    p.WR = 18;
+    p.tiles_per_img = (g.H / 16) * p.tiles_x;
+    p.n_mtiles = g.B * p.tiles_per_img;
+    p.a_load_bytes = static_cast<uint32_t>(p.WR) * p.P * ROWB;
+    p.a_bytes = (p.a_load_bytes + 1023u) & ~1023u;
+    p.a_stages = 2;
+    const size_t budget1 = TC_SMEM_MAX - 1024 - EPI_SLAB_BYTES - bias_bytes_of(g.ntot) - EPI_FUSED_BYTES;
+    const size_t rest = budget1 - static_cast<size_t>(p.a_stages) * p.a_bytes;
+    p.tb = (rest / (3u * NB * ROWB) >= 3) ? 3 : 1;
+    if (getenv("TCS_TB")) p.tb = atoi(getenv("TCS_TB")) == 3 ? 3 : 1;
+    p.stage_bytes = (static_cast<uint32_t>(p.tb) * NB * ROWB + 1023u) & ~1023u;
+    p.nstage = static_cast<int>(rest / p.stage_bytes);
+    if (p.nstage > MAX_STAGES) p.nstage = MAX_STAGES;
+    if (p.nstage < 2) return fail(TCS_ERR_UNSUPPORTED, "conv_tc: weight stage does not fit shared memory twice");
+    pl.smem = static_cast<size_t>(p.a_stages) * p.a_bytes + static_cast<size_t>(p.nstage) * p.stage_bytes + 1024 +
+              EPI_SLAB_BYTES + bias_bytes_of(g.ntot) + EPI_FUSED_BYTES;
+  }
   p.epi = ea;
   TCS_CHECK(conv_tc_max_ctas(pl, &pl.max_ctas));
   if (getenv("TCS_MAX_CTAS")) pl.max_ctas = atoi(getenv("TCS_MAX_CTAS"));   // test hook: pretend part of the device is taken
@@ -1207,6 +1452,7 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, con
     cuuint64_t strides[3] = {C * 2, C * 2 * Win, C * 2 * Win * Hin};
     cuuint32_t box[4] = {KB, static_cast<cuuint32_t>(g.W * g.stride), static_cast<cuuint32_t>(p.WR * g.stride), 1};
     cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(g.stride), static_cast<cuuint32_t>(g.stride), 1};
+    if (pl.geo) { box[1] = static_cast<cuuint32_t>(p.P); box[2] = static_cast<cuuint32_t>(p.WR); }
     CUresult r = encode(&pl.mapA[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(srcs[s]), dims, strides,
                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1214,10 +1460,12 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, con
   }
   {
     // the packed weights ARE the swizzled shared-memory image: plain (unswizzled) 512-byte rows
-    const uint32_t stage_b = static_cast<uint32_t>(p.T) * (pl.N / pl.cg) * ROWB;   // bytes per stage and CTA
+    const uint32_t stage_b = static_cast<uint32_t>(p.T) * (pl.N / pl.cg) * ROWB;   // bytes per packed K stage and CTA
     if (stage_b % 512) return fail(TCS_ERR_UNSUPPORTED, "conv_tc: weight stage is not a multiple of 512 bytes");
     p.b_rows = static_cast<int>(stage_b / 512);
-    cuuint64_t dims[2] = {256, static_cast<cuuint64_t>(p.kstages) * p.n_ntiles * pl.cg * p.b_rows};
+    const cuuint64_t total_rows = static_cast<cuuint64_t>(p.kstages) * p.n_ntiles * pl.cg * p.b_rows;
+    if (pl.geo) p.b_rows = p.b_rows * p.tb / 3;     // rows one load takes: tb of the three ky taps of a packed stage
+    cuuint64_t dims[2] = {256, total_rows};
     cuuint64_t strides[1] = {512};
     cuuint32_t box[2] = {256, static_cast<cuuint32_t>(p.b_rows)};
     cuuint32_t estr[2] = {1, 1};
@@ -1227,6 +1475,7 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, con
     if (r != CUDA_SUCCESS) return fail(TCS_ERR_CUDA, "cuTensorMapEncodeTiled(W) failed: " + std::to_string(r));
   }
   pl.mapO = pl.mapW;
+  pl.mapO1 = pl.mapW;
   if (epi == EPI_PLAIN) {   // bf16 [M = B*H*W, ldo] output, 32-row x 32-channel boxes
     const cuuint64_t C = static_cast<cuuint64_t>(ea.ldo);
     cuuint64_t dims[2] = {C, static_cast<cuuint64_t>(g.B) * g.H * g.W};
@@ -1243,11 +1492,18 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, con
     cuuint64_t dims[4] = {C, static_cast<cuuint64_t>(g.W + 2), static_cast<cuuint64_t>(g.H + 2), static_cast<cuuint64_t>(g.B)};
     cuuint64_t strides[3] = {C * 2, C * 2 * (g.W + 2), C * 2 * (g.W + 2) * (g.H + 2)};
     cuuint32_t box[4] = {BLK, static_cast<cuuint32_t>(g.W >= 32 ? 32 : 16), 1, 1};
+    if (pl.geo) { box[1] = 8; box[2] = 4; }       // a warp's 32 rows = 4 image rows x 8 pixels
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = encode(&pl.mapO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ea.out, dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, BLK == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(TCS_ERR_CUDA, "cuTensorMapEncodeTiled(O padded) failed: " + std::to_string(r));
+    if (pl.geo) {
+      box[2] = 1;
+      r = encode(&pl.mapO1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ea.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(TCS_ERR_CUDA, "cuTensorMapEncodeTiled(O padded, one row) failed: " + std::to_string(r));
+    }
   }
   pl.valid = true;
   return TCS_OK;

@@ -27,6 +27,14 @@ struct ConvTcParams {
   double gn_inv_cnt;        // EPI_GN_FUSED: 1 / (H * W * channels per group)
   long long exch_timeout;   // EPI_GN_FUSED: cycles a CTA waits for its image group's partial sums before it traps
   int issuers;              // MMA-issuing warps: 2 = one per 128-row sub-tile (MSUB == 2), 1 otherwise
+  // geo = 1 ("tap-shift" geometry, 3x3 stride-1 layers): a 128-row sub-tile is 16 image rows x 8 pixels, the A operand
+  // of a 64-channel block is ONE (16 + 2) x (8 MSUB + 2) pixel window in its own ring, and the nine taps are descriptor
+  // start shifts into it; the weights stream through a second ring in stages of `tb` taps
+  int geo;
+  int P;                    // geo 1: window pixels per row (8 MSUB + 2); one window row = P * 128 B = the descriptor's SBO
+  int tiles_x;              // geo 1: CTA tiles per image row
+  int a_stages, tb;         // geo 1: A ring depth; taps per weight stage (3 or 1)
+  uint32_t a_load_bytes;    // geo 1: bytes one window load delivers (a_bytes is its 1024-byte-aligned slot size)
   int debug;                // TCS_DEBUG bits (timing experiments only): 1 = no inter-CTA wait, 2 = no pass-2 stores
   EpiArgs epi;
 };
@@ -35,6 +43,8 @@ struct ConvTcPlan {
   CUtensorMap mapA[4];   // [source] or, in bf16x3 mode, [hi0, lo0, hi1, lo1]
   CUtensorMap mapW;
   CUtensorMap mapO;   // EPI_PADDED / EPI_GN_FUSED: padded bf16 output, TMA-stored in 32-pixel x 32-channel boxes
+  CUtensorMap mapO1;  // geo 1: the same tensor with a one-image-row box (the wrapped copies of rows 0 and H - 1)
+  int geo = 0;
   ConvTcParams p;
   int N;       // N tile (96 or 192)
   int epi;     // Epilogue

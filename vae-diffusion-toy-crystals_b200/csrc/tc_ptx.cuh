@@ -221,4 +221,18 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// The same with a caller-chosen stride between 8-row groups (bytes, a multiple of 16): conv_tc's tap-shift geometry sets
+// it to one row of its shared-memory window.  The swizzle XOR is taken from the absolute shared-memory address of every
+// 16-byte chunk, so the start address may sit on any 128-byte row and the stride need not be a multiple of 1024 B
+// (base-offset field left 0; measured with tools/umma_shift_test.cu: setting it to (start >> 7) & 7 gives wrong results).
+__device__ __forceinline__ uint64_t make_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
 }  // namespace tcs
