@@ -733,7 +733,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const uint32_t srow = slab + lane * 64;        // this lane's row inside a staging block
         const int ssw = (lane >> 1) & 3;
         const uint32_t sb0 = slab_buf;                 // staging block that pass 2 fills first
-        if (use_tma_out) {                             // the previous tile's TMA stores have left the staging blocks
+        // TCS_STASH_TMEM (default): column blocks 0 and 1 of the stash live in the 64 TMEM columns an accumulator set
+        // leaves free (192 of 256), 32 per warp unit, instead of the staging blocks: tcgen05.st / ld do not touch shared
+        // memory, whose bandwidth the MMA operand reads of an N = 96 layer already use to ~90 %
+        const bool stash_tmem = !(p.debug & 32);
+        const uint32_t tstash = tbase + N * MSUB + h * 32;
+        if (use_tma_out && !stash_tmem) {              // the previous tile's TMA stores have left the staging blocks
           const long long cl0 = prof ? clock64() : 0;
           if (lane == 0) ptx::bulk_wait_read<0>();
           __syncwarp();
@@ -769,14 +774,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 hw[u / 2] = pack_f16x2_sat(t0, t1);
                 hw[u / 2 + 1] = pack_f16x2_sat(t2, t3);
               }
-              if (k < 2) {
+              if (k < 2 && !stash_tmem) {
                 st_shared_u4(sblk + (((i / 8) ^ ssw) << 4), hw[0], hw[1], hw[2], hw[3]);
               } else {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) stash2[i / 2 + u] = hw[u];
               }
             }
+            if (k < 2 && stash_tmem) ptx::tmem_st16(tstash + k * 16, stash2);
           }
+          if (stash_tmem) ptx::tmem_st_wait();
           // fp16 stash range guard, for free: a row whose sum of squares over a group stays below 65504^2 cannot hold a
           // value that saturated in cvt.rn.satfinite.  Otherwise flag the launch: the host re-runs the evaluation on the
           // unfused path (conv -> fp32 -> GroupNorm kernel) instead of returning a clipped activation.
@@ -879,7 +886,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         for (int k = 0; k < 3; ++k) {
           const int cc = col0 + k * 32;
           uint32_t hv[16];
-          if (k < 2) {
+          if (k < 2 && stash_tmem) {
+            ptx::tmem_ld16(tstash + k * 16, reinterpret_cast<float*>(hv));
+            ptx::tmem_ld_wait();
+          } else if (k < 2) {
             const uint32_t sblk = srow + ((sb0 ^ k) * 2048);   // = the block store_padded_block fills next (in place)
 #pragma unroll
             for (int j = 0; j < 4; ++j) ld_shared_u4(sblk + ((j ^ ssw) << 4), hv[4 * j], hv[4 * j + 1], hv[4 * j + 2], hv[4 * j + 3]);
