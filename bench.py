@@ -77,11 +77,24 @@ def max_over_ranks(value: float, device) -> float:
 def nccl_logging():
     """stdout carries the ONE JSON line; NCCL's log (communicator init: 'comm ... rank r nranks N', NVLS, rings) goes to
     stderr via NCCL_DEBUG_FILE, so whoever launched the job can check that all N ranks joined.  An NCCL_DEBUG level set
-    by the launcher is kept; without one the init subsystem is logged at INFO."""
-    os.environ.setdefault("NCCL_DEBUG", "INFO")
-    if os.environ["NCCL_DEBUG"].upper() == "INFO":
+    by the launcher is kept; below INFO the init subsystem is logged at INFO.  report_comm() adds one line per rank of its own."""
+    if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):   # (this image presets NCCL_DEBUG=VERSION)
+        os.environ["NCCL_DEBUG"] = "INFO"
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
+
+def report_comm(rank, world, local_rank, dev):
+    """One line per rank on stderr once the communicator exists (whatever NCCL's own log level is): an all-reduce of ones
+    over the new communicator must return the world size on every rank."""
+    import torch
+    import torch.distributed as dist
+    t = torch.ones(1, device=dev)
+    dist.all_reduce(t)
+    ver = ".".join(str(v) for v in torch.cuda.nccl.version())
+    print(f"[bench] NCCL {ver} comm rank {rank} nranks {world} cudaDev {local_rank} all_reduce(1) = {int(t.item())} "
+          f"NCCL_DEBUG={os.environ.get('NCCL_DEBUG')} NCCL_DEBUG_FILE={os.environ.get('NCCL_DEBUG_FILE')}", file=sys.stderr, flush=True)
+    assert int(t.item()) == world
 
 
 def load_peaks():
@@ -333,6 +346,7 @@ def run_gpu_prior(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         nccl_logging()
         dist.init_process_group("nccl", device_id=dev)
+        report_comm(rank, world, local_rank, dev)
     n = args.n or 4096
     n_total = n * world
     lo, hi = shard_range(n_total, rank, world)
@@ -510,6 +524,7 @@ def run_gpu(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         nccl_logging()
         dist.init_process_group("nccl", device_id=dev)
+        report_comm(rank, world, local_rank, dev)
     strong = args.scaling == "strong"
     if strong:       # BASELINE configs[2]: a fixed job (n_total) sharded over the ranks
         n_total = args.n_total or 65536
