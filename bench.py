@@ -37,6 +37,7 @@ TC_CONV_MMAC = [339.74, 151.00, 169.87, 339.74, 151.00, 84.93, 84.93, 28.31, 9.4
                 679.48, 339.74]
 TC_CONV_NAMES = ["down1.net.3", "ds1", "down2.net.0", "down2.net.3", "ds2", "mid.net.0", "mid.net.3", "attn.qkv",
                  "attn.proj", "us2_conv", "up2.net.0", "up2.net.3", "us1_conv", "up1.net.0", "up1.net.3"]
+ATTN_SDPA_MMAC = 25.17                   # q k^T and p v of the 4 heads, not part of the conv figure
 SDE_STEPS, CFG, T_END = 300, 1.5, 0.005
 PEAKS_FALLBACK = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
@@ -750,7 +751,12 @@ def profile_kernels(model, sde, dev, n=1024):
     images = 2 * n
     conv_ms = [a / reps for a in acc]
     flops = [2e6 * m * images for m in TC_CONV_MMAC]
-    per_layer = {k: round(f / (ms * 1e-3) / 1e12, 1) for k, f, ms in zip(TC_CONV_NAMES, flops, conv_ms)}
+    per_layer = {k: round(f / (ms * 1e-3) / 1e12, 1) for k, f, ms in zip(TC_CONV_NAMES, flops, conv_ms) if ms > 1e-4}
+    iq, ip = TC_CONV_NAMES.index("attn.qkv"), TC_CONV_NAMES.index("attn.proj")
+    if conv_ms[ip] <= 1e-4:   # fused attention block (attn_tc.cu): norm + qkv + softmax(q k^T) v + proj in the attn.qkv slot
+        per_layer.pop("attn.qkv", None)
+        blk = flops[iq] + flops[ip] + 2e6 * ATTN_SDPA_MMAC * images
+        per_layer["attn.block(norm+qkv+sdpa+proj)"] = round(blk / (conv_ms[iq] * 1e-3) / 1e12, 1)
     traffic, traffic_source = None, None   # DRAM bytes of the same 15 launches from the committed `ncu --set full` capture
     for name in ("r2_conv_ncu_full.json", "r1_conv_ncu_full.json"):
         tp = os.path.join(ROOT, "profiles", name)

@@ -174,6 +174,15 @@ int tcs_debug_conv(int32_t engine, int32_t precision, int32_t B, int32_t H_out, 
                    int32_t cin1, int32_t cout, int32_t ksize, int32_t stride, const float* in0, const float* in1,
                    const float* weight, const float* bias, float* out, float* stats, int32_t epi, void* stream);
 
+/* Run the fused attention block (csrc/attn_tc.cu: GroupNorm -> qkv -> softmax(q k^T / sqrt(48)) v -> proj -> + x,
+ * SelfAttention2d.forward, sde_score_model.py:136-167) in isolation, bf16 / tcgen05.  Device fp32 pointers:
+ *   x, out  : NHWC [B,16,16,192];  gn_w, gn_b [192];  qkv_w [576,192], qkv_b [576];  proj_w [192,192], proj_b [192]
+ *   dbg     : NULL, or 246784 floats receiving intermediates of image 0: normalised input [256][192], q|k|v + bias
+ *             [256][576], attention output [256][192], softmax denominators (base-2 scaled) [256][4].  Synchronous. */
+int tcs_debug_attn_block(int32_t B, const float* x, const float* gn_w, const float* gn_b, const float* qkv_w,
+                         const float* qkv_b, const float* proj_w, const float* proj_b, float* out, float* dbg,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

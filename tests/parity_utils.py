@@ -78,6 +78,46 @@ def debug_conv(engine, precision, in0, in1, w, b, ksize, stride, epi):
     return out, stats
 
 
+ATTN_DBG_FLOATS = 256 * 192 + 256 * 576 + 256 * 192 + 256 * 4
+ATTN_PROF_SLOTS = 96   # clock64 stamps (int64) of the control lane and of one worker lane follow the float dump
+
+
+def debug_attn_block(x, gn_w, gn_b, qkv_w, qkv_b, proj_w, proj_b, want_dbg=False):
+    """The fused attention block (csrc/attn_tc.cu) in isolation.  x NHWC fp32 [B,16,16,192] on CUDA, weights in the
+    PyTorch layouts.  Returns (out NHWC fp32, dbg dict of image-0 intermediates or None)."""
+    L = _cabi.lib()
+    B = x.shape[0]
+    out = torch.full((B, 16, 16, 192), float("nan"), device="cuda")
+    dbg = torch.zeros((ATTN_DBG_FLOATS + 2 * 2 * ATTN_PROF_SLOTS,), device="cuda") if want_dbg else None
+    ts = [t.contiguous().float().cuda() for t in (x, gn_w, gn_b, qkv_w.reshape(576, 192), qkv_b, proj_w.reshape(192, 192), proj_b)]
+    torch.cuda.synchronize()
+    _cabi.check(L.tcs_debug_attn_block(B, *[t.data_ptr() for t in ts], out.data_ptr(),
+                                       None if dbg is None else dbg.data_ptr(), None))
+    torch.cuda.synchronize()
+    d = None
+    if dbg is not None:
+        o = [0, 256 * 192, 256 * 192 + 256 * 576, 256 * 192 + 256 * 576 + 256 * 192]
+        d = {"xn": dbg[o[0]:o[1]].reshape(256, 192), "qkv": dbg[o[1]:o[2]].reshape(256, 576),
+             "y": dbg[o[2]:o[3]].reshape(256, 192), "l": dbg[o[3]:ATTN_DBG_FLOATS].reshape(256, 4),
+             "prof": dbg[ATTN_DBG_FLOATS:].view(torch.int64).reshape(2, ATTN_PROF_SLOTS).cpu()}
+    return out, d
+
+
+def attn_block_reference(x, gn_w, gn_b, qkv_w, qkv_b, proj_w, proj_b):
+    """fp64 SelfAttention2d.forward (sde_score_model.py:136-167) on NHWC input; returns NHWC out + the intermediates."""
+    B = x.shape[0]
+    xd = x.double().permute(0, 3, 1, 2)
+    xn = F.group_norm(xd, 8, gn_w.double(), gn_b.double(), eps=1e-5)
+    qkv = F.conv2d(xn, qkv_w.double().reshape(576, 192, 1, 1), qkv_b.double())
+    q, k, v = torch.chunk(qkv, 3, dim=1)
+    sh = lambda t: t.reshape(B, 4, 48, 256).transpose(2, 3)
+    y = F.scaled_dot_product_attention(sh(q), sh(k), sh(v))
+    y = y.transpose(2, 3).contiguous().reshape(B, 192, 16, 16)
+    out = xd + F.conv2d(y, proj_w.double().reshape(192, 192, 1, 1), proj_b.double())
+    to_tok = lambda t: t.permute(0, 2, 3, 1).reshape(B, 256, -1)
+    return out.permute(0, 2, 3, 1).contiguous(), {"xn": to_tok(xn), "qkv": to_tok(qkv), "y": to_tok(y)}
+
+
 def debug_layer(m: CondUNetTiny, name, x, t, y_cat, y_cont, C_out, res):
     h = m.engine_handle()
     n = x.shape[0]

@@ -52,6 +52,31 @@ def test_conv_layer(case, precision, engine):
             assert pu.rel_l2(stats, want) < 1e-4, (case, precision, engine, "stats")
 
 
+# ---- the fused attention block (attn_tc.cu) in isolation -------------------------------------------------------
+@pytest.mark.parametrize("B", [1, 3, 150])
+def test_fused_attention_block(B):
+    """GroupNorm -> qkv -> softmax(q k^T) v -> proj -> + x in one tcgen05 kernel against an fp64 SelfAttention2d
+    (sde_score_model.py:136-167).  Inputs and weights are bf16-representable so that the gate measures the kernel's own
+    rounding (bf16 Xn / q / k / v / P / y operands, fp32 accumulation, bf16 output); B = 150 > 74 clusters exercises
+    the persistent image loop (weight re-fetch, barrier phases) and the halo is verified inside the hook."""
+    pu = _pu()
+    g = torch.Generator().manual_seed(100 + B)
+    bf = lambda t: t.bfloat16().float()
+    x = bf(torch.randn((B, 16, 16, 192), generator=g) * 1.5 + 0.3)
+    gn_w, gn_b = 1.0 + 0.2 * torch.randn(192, generator=g), 0.1 * torch.randn(192, generator=g)
+    qkv_w, qkv_b = bf(torch.randn((576, 192), generator=g) * (2.0 / math.sqrt(192))), 0.1 * torch.randn(576, generator=g)
+    proj_w, proj_b = bf(torch.randn((192, 192), generator=g) / math.sqrt(192)), 0.1 * torch.randn(192, generator=g)
+    args = (x, gn_w, gn_b, qkv_w, qkv_b, proj_w, proj_b)
+    want, wd = pu.attn_block_reference(*args)
+    got, d = pu.debug_attn_block(*args, want_dbg=True)
+    errs = {k: pu.rel_l2(d[k].cpu(), wd[k][0]) for k in ("xn", "qkv", "y")}
+    err = pu.rel_l2(got.cpu(), want)
+    branch = pu.rel_l2(got.cpu().double() - x.double(), want - x.double())   # the attention branch without the residual
+    print(f"fused attention B={B}: out {err:.2e}, branch {branch:.2e}, stages {errs}")
+    assert errs["xn"] < 4e-3 and errs["qkv"] < 6e-3 and errs["y"] < 1.5e-2, errs
+    assert err < 1e-2 and branch < 2e-2, (err, branch)
+
+
 # ---- per-layer activations against the oracle's taps ---------------------------------------------------
 @pytest.mark.parametrize("precision,engine", MODES)
 def test_layers_against_oracle(precision, engine):

@@ -18,7 +18,7 @@ OUT_DIR = os.path.join(HERE, "toycrystals_b200")
 LIB = os.path.join(OUT_DIR, "libtcs.so")
 OBJ_DIR = os.path.join(HERE, "build")
 SOURCES = ["tcs_api.cu", "conv_tc.cu", "kernels_simt.cu", "kernels_split.cu", "kernels_embed.cu", "kernels_step.cu",
-           "prior_api.cu", "linear_tc.cu", "kernels_prior.cu"]
+           "prior_api.cu", "linear_tc.cu", "kernels_prior.cu", "attn_tc.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]

@@ -196,6 +196,42 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
 __device__ __forceinline__ void tmem_ld1(uint32_t taddr, float* v) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=f"(*v) : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand lives in tensor memory (bf16 packed two per 32-bit column, lane = row,
+// written with tcgen05.st; 8 columns per K = 16 step).  Probed on B200 by tools/umma_attn_probe.cu.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 1-D bulk copy global -> shared (no tensor map), completing on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// generic-proxy writes (own or a peer CTA's shared memory) -> visible to the async proxy (TMA, tcgen05.mma operands)
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 }  // namespace ptx
@@ -244,5 +280,20 @@ __device__ __forceinline__ uint64_t make_desc_sw128_sbo(uint32_t smem_addr, uint
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+
+// MN-major SWIZZLE_128B descriptor (the operand's M/N index is the contiguous one): rows of 128 B = one K index each,
+// 64 M/N elements per row; SBO = stride between groups of 8 K rows (1024 B for dense rows), LBO = stride between
+// 64-element M/N blocks (unused while N <= 64).  Pair with bit 16 (B) / bit 15 (A) of the instruction descriptor.
+// Probed on B200 by tools/umma_attn_probe.cu (N = 48: a partial 64-element atom is fine).
+__device__ __forceinline__ uint64_t make_desc_sw128_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1024 >> 4) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+constexpr uint32_t IDESC_B_MN_MAJOR = 1u << 16;
 
 }  // namespace tcs

@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 
+#include "attn_tc.cuh"
 #include "conv_tc.cuh"
 #include "kernels.cuh"
 
@@ -97,6 +98,8 @@ struct tcs_handle {
   tcs_config cfg;
   int sm_count = 148;
   bool bf16 = false, use_tc = false, fuse_gn = false, fuse_first = true;
+  bool fuse_attn = false;   // the attention block as one tcgen05 kernel (attn_tc.cu); TCS_FUSE_ATTN=0 keeps the four launches
+  DevBuf attn_wpack;
   bool split3 = false;   // precision fp32 on the tcgen05 engine: conv operands as bf16 (hi, lo) pairs (kernels_split.cu)
   size_t esz = 4;
   cudaStream_t stream = nullptr;   // internal stream all work runs on
@@ -461,14 +464,35 @@ static int forward_chunk(tcs_handle* h, const PassArgs& a, cudaStream_t st, TapR
   // ---- mid + attention ---------------------------------------------------------------------
   CONV_GN(C_MA, h->raw16.p, 16, 192);
   CONV_GN(C_MB, h->raw16.p, 16, 192);   // -> p16_a = x_in of the attention block
-  ++h->launches;   // attn.norm: statistics + normalisation of the 16x16x192 image in one kernel
-  TCS_CHECK(launch_gn_image16<T>(h->p16_a.as<T>(), B, gnw("attn.norm"), gnb("attn.norm"), h->p16_b.as<T>(), st));
-  TCS_CHECK(run_conv<T>(h, C_QKV, B, st));
-  TAP(2, h->qkv.p, 16, 16, 576);
-  ++h->launches;
-  TCS_CHECK(launch_attention<T>(h->qkv.as<T>(), B, h->atty.as<T>(), st));
-  TAP(2, h->atty.p, 16, 16, 192);
-  TCS_CHECK(run_conv<T>(h, C_PROJ, B, st));   // + residual x_in -> p16_c
+  if (h->fuse_attn && sizeof(T) == 2 && !(tap && (tap->id == tap_idx || tap->id == tap_idx + 1))) {
+    // GroupNorm -> qkv -> softmax(q k^T) v -> proj -> + x_in in ONE tcgen05 kernel (q, k, v and the scores stay on the SM)
+    ++h->launches;
+    AttnTcParams ap{};
+    ap.x = h->p16_a.as<__nv_bfloat16>(); ap.out = h->p16_c.as<__nv_bfloat16>();
+    ap.wpack = h->attn_wpack.as<uint8_t>();
+    ap.bias_qkv = h->dw.at("attn.qkv.bias"); ap.bias_proj = h->dw.at("attn.proj.bias");
+    ap.gamma = gnw("attn.norm"); ap.beta = gnb("attn.norm");
+    ap.B = B;
+    if (h->profiling) {   // the block is reported in the attn.qkv slot, attn.proj reads 0
+      TCS_CUDA(cudaEventRecord(h->prof_ev[2 * C_QKV], st));
+    }
+    TCS_CHECK(launch_attn_block_tc(ap, h->sm_count, st));
+    if (h->profiling) {
+      TCS_CUDA(cudaEventRecord(h->prof_ev[2 * C_QKV + 1], st));
+      TCS_CUDA(cudaEventRecord(h->prof_ev[2 * C_PROJ], st));
+      TCS_CUDA(cudaEventRecord(h->prof_ev[2 * C_PROJ + 1], st));
+    }
+    tap_idx += 2;
+  } else {
+    ++h->launches;   // attn.norm: statistics + normalisation of the 16x16x192 image in one kernel
+    TCS_CHECK(launch_gn_image16<T>(h->p16_a.as<T>(), B, gnw("attn.norm"), gnb("attn.norm"), h->p16_b.as<T>(), st));
+    TCS_CHECK(run_conv<T>(h, C_QKV, B, st));
+    TAP(2, h->qkv.p, 16, 16, 576);
+    ++h->launches;
+    TCS_CHECK(launch_attention<T>(h->qkv.as<T>(), B, h->atty.as<T>(), st));
+    TAP(2, h->atty.p, 16, 16, 192);
+    TCS_CHECK(run_conv<T>(h, C_PROJ, B, st));   // + residual x_in -> p16_c
+  }
   TAP(1, h->p16_c.p, 16, 16, 192);
   // ---- up2 ---------------------------------------------------------------------------------
   ++h->launches;
@@ -813,6 +837,8 @@ int tcs_create(tcs_handle** out, const tcs_config* cfg) {
     const char* e = getenv("TCS_FUSE_GN");   // 0 = keep conv -> raw fp32 -> gn_apply (A/B switch)
     h->fuse_gn = h->use_tc && !h->split3 && cfg->fuse_gn != 0 && !(e && atoi(e) == 0);
     h->fuse_first = !(e && atoi(e) == 0);
+    const char* ea = getenv("TCS_FUSE_ATTN");
+    h->fuse_attn = h->use_tc && !h->split3 && !(ea && atoi(ea) == 0);
   }
   h->chunk = cfg->chunk > 0 ? cfg->chunk : 2048;
   if (h->chunk % 2) h->chunk += 1;
@@ -940,6 +966,12 @@ int tcs_finalize_weights(tcs_handle* h) {
     conv_tc_pack_weights(g, EPI_EPS, w16.data(), pk.data());
     TCS_CHECK(h->wpack_out.ensure(pk.size() * 2));
     TCS_CUDA(cudaMemcpy(h->wpack_out.p, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
+  }
+  if (h->fuse_attn) {
+    std::vector<uint8_t> pk(attn_tc_wpack_bytes());
+    attn_tc_pack_weights(h->host_w.at("attn.qkv.weight").v.data(), h->host_w.at("attn.proj.weight").v.data(), pk.data());
+    TCS_CHECK(h->attn_wpack.ensure(pk.size()));
+    TCS_CUDA(cudaMemcpy(h->attn_wpack.p, pk.data(), pk.size(), cudaMemcpyHostToDevice));
   }
   TCS_CHECK(alloc_workspace(h));
   TCS_CHECK(build_plans(h));
@@ -1405,6 +1437,54 @@ int tcs_debug_conv(int32_t engine, int32_t precision, int32_t B, int32_t H_out, 
   if (eng == TCS_ENGINE_TCGEN05 && !bf16) return debug_conv_split3(g, in0, in1, weight, bias, out, stats, epi, st);
   if (bf16) return debug_conv_t<__nv_bfloat16>(eng == TCS_ENGINE_TCGEN05, g, in0, in1, weight, bias, out, stats, epi, st);
   return debug_conv_t<float>(false, g, in0, in1, weight, bias, out, stats, epi, st);
+}
+
+// The fused attention block in isolation (halo of the padded output verified like tcs_debug_conv's).
+int tcs_debug_attn_block(int32_t B, const float* x, const float* gn_w, const float* gn_b, const float* qkv_w,
+                         const float* qkv_b, const float* proj_w, const float* proj_b, float* out, float* dbg,
+                         void* stream) {
+  if (!x || !gn_w || !gn_b || !qkv_w || !qkv_b || !proj_w || !proj_b || !out || B < 1)
+    return fail(TCS_ERR_BAD_ARGUMENT, "tcs_debug_attn_block: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  using T = __nv_bfloat16;
+  DevBuf din, dout, wp, small;
+  const size_t pbytes = static_cast<size_t>(B) * 18 * 18 * 192 * sizeof(T);
+  TCS_CHECK(din.ensure(pbytes));
+  TCS_CHECK(dout.ensure(pbytes));
+  TCS_CUDA(cudaMemsetAsync(dout.p, 0xff, pbytes, st));
+  TCS_CHECK(launch_pad_from_plain<T>(x, B, 16, 16, 192, 1, din.as<T>(), st));
+  std::vector<float> hq(576 * 192), hp(192 * 192);
+  TCS_CUDA(cudaMemcpy(hq.data(), qkv_w, hq.size() * 4, cudaMemcpyDefault));
+  TCS_CUDA(cudaMemcpy(hp.data(), proj_w, hp.size() * 4, cudaMemcpyDefault));
+  std::vector<uint8_t> pk(attn_tc_wpack_bytes());
+  attn_tc_pack_weights(hq.data(), hp.data(), pk.data());
+  TCS_CHECK(wp.ensure(pk.size()));
+  TCS_CUDA(cudaMemcpy(wp.p, pk.data(), pk.size(), cudaMemcpyHostToDevice));
+  TCS_CHECK(small.ensure((576 + 192 * 3) * 4));
+  float* sp = small.as<float>();
+  TCS_CUDA(cudaMemcpy(sp, qkv_b, 576 * 4, cudaMemcpyDefault));
+  TCS_CUDA(cudaMemcpy(sp + 576, proj_b, 192 * 4, cudaMemcpyDefault));
+  TCS_CUDA(cudaMemcpy(sp + 768, gn_w, 192 * 4, cudaMemcpyDefault));
+  TCS_CUDA(cudaMemcpy(sp + 960, gn_b, 192 * 4, cudaMemcpyDefault));
+  AttnTcParams ap{};
+  ap.x = din.as<T>(); ap.out = dout.as<T>(); ap.wpack = wp.as<uint8_t>();
+  ap.bias_qkv = sp; ap.bias_proj = sp + 576; ap.gamma = sp + 768; ap.beta = sp + 960;
+  ap.B = B; ap.dbg = dbg;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  TCS_CHECK(launch_attn_block_tc(ap, sms, st));
+  TCS_CHECK(launch_unpad_to_f32<T>(dout.as<T>(), B, 16, 16, 192, 1, out, st));
+  DevBuf ref;
+  TCS_CHECK(ref.ensure(pbytes));
+  TCS_CHECK(launch_pad_from_plain<T>(out, B, 16, 16, 192, 1, ref.as<T>(), st));
+  TCS_CUDA(cudaStreamSynchronize(st));
+  std::vector<uint8_t> a(pbytes), b(pbytes);
+  TCS_CUDA(cudaMemcpy(a.data(), dout.p, pbytes, cudaMemcpyDeviceToHost));
+  TCS_CUDA(cudaMemcpy(b.data(), ref.p, pbytes, cudaMemcpyDeviceToHost));
+  if (memcmp(a.data(), b.data(), pbytes) != 0)
+    return fail(TCS_ERR_STATE, "tcs_debug_attn_block: circular halo of the padded output is wrong");
+  return TCS_OK;
 }
 
 }  // extern "C"

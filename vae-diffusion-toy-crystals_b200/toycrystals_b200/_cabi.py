@@ -102,6 +102,7 @@ SIGNATURES = {
     "tcs_debug_conv": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "tcs_debug_attn_block": (C.c_int, [C.c_int32] + [C.c_void_p] * 10),
 }
 
 _lib: Optional[C.CDLL] = None
