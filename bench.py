@@ -751,9 +751,9 @@ def profile_kernels(model, sde, dev, n=1024):
     images = 2 * n
     conv_ms = [a / reps for a in acc]
     flops = [2e6 * m * images for m in TC_CONV_MMAC]
-    per_layer = {k: round(f / (ms * 1e-3) / 1e12, 1) for k, f, ms in zip(TC_CONV_NAMES, flops, conv_ms) if ms > 1e-4}
+    per_layer = {k: round(f / (ms * 1e-3) / 1e12, 1) for k, f, ms in zip(TC_CONV_NAMES, flops, conv_ms) if ms > 5e-3}
     iq, ip = TC_CONV_NAMES.index("attn.qkv"), TC_CONV_NAMES.index("attn.proj")
-    if conv_ms[ip] <= 1e-4:   # fused attention block (attn_tc.cu): norm + qkv + softmax(q k^T) v + proj in the attn.qkv slot
+    if conv_ms[ip] <= 5e-3:   # fused attention block (attn_tc.cu): norm + qkv + softmax(q k^T) v + proj in the attn.qkv slot
         per_layer.pop("attn.qkv", None)
         blk = flops[iq] + flops[ip] + 2e6 * ATTN_SDPA_MMAC * images
         per_layer["attn.block(norm+qkv+sdpa+proj)"] = round(blk / (conv_ms[iq] * 1e-3) / 1e12, 1)

@@ -18,12 +18,12 @@ args = (x, 1.0 + 0.2 * torch.randn(192, generator=g), 0.1 * torch.randn(192, gen
         torch.randn((576, 192), generator=g) * (2.0 / math.sqrt(192)), 0.1 * torch.randn(576, generator=g),
         torch.randn((192, 192), generator=g) / math.sqrt(192), 0.1 * torch.randn(192, generator=g))
 out, d = pu.debug_attn_block(*args, want_dbg=True)
-CTRL = ["start", "phase0"] + [f"h{h}:{n}" for h in range(4) for n in
-                              ("W ready", "qkv issued", "qkv done+next W", "sync A", "S issued", "blk sync", "PV issued", "sync B")] + \
-       ["proj issued", "proj done"]
-WORK = ["start", "phase0"] + [f"h{h}:{n}" for h in range(4) for n in
-                              ("qkv ready", "converted", "fences", "sync A", "S ready", "pass1", "wbar", "pass2", "blk sync",
-                               "O ready", "O conv", "sync B")] + ["Y ready", "epilogue"]
+CTRL = ["start", "phase0", "qkv0 done, W1 req"] + [f"h{h}:{n}" for h in range(4) for n in
+                                                  ("keys here", "S issued", "V pushed, qkv+1 issued", "PV issued", "head done")] + \
+       ["proj issued", "image done"]
+WORK = ["start", "phase0", "head 0 converted"] + [f"h{h}:{n}" for h in range(4) for n in
+                                                 ("S ready", "softmax", "q,k next", "O ready", "head done")] + \
+       ["Y ready", "rows staged", "written"]
 for role, names in ((0, CTRL), (1, WORK)):
     t = d["prof"][role].tolist()
     print("control lane" if role == 0 else "worker lane (warp 1)")

@@ -39,6 +39,7 @@ constexpr uint32_t XN_OFF = 0, W_OFF = 49152, K_OFF = 104448, V_OFF = 137216, O_
 constexpr uint32_t KBLK = 16384;                       // a 128-row x 64-channel K block of an A operand
 constexpr uint32_t WH_KB = 144 * 128, WH_BYTES = 3 * WH_KB;       // per-head q|k|v weights
 constexpr uint32_t WP_KB = 192 * 128, WP_BYTES = 3 * WP_KB;       // projection weights
+constexpr uint32_t R_OFF = K_OFF;                     // epilogue staging rows [128][384 B] over the idle K / V regions
 constexpr uint32_t S_COL = 0, QKV_COL = 256, Q_COL = 400, O_COL = 424;
 constexpr float QSCALE = 0.14433756729740643f * 1.4426950408889634f;   // log2(e) / sqrt(48)
 static_assert(W_OFF % 1024 == 0 && K_OFF % 1024 == 0 && V_OFF % 1024 == 0 && O_OFF % 1024 == 0, "swizzle atoms");
@@ -61,12 +62,45 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
 __device__ __forceinline__ uint4 pack8(const float* f) {
   return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
 }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
 __device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ int halo_wrap16(int v) { return v == 0 ? 16 : (v == 15 ? -16 : 0); }
 
+// ---- cluster helpers ------------------------------------------------------------------------------------------------
+// arrive on the PEER CTA's copy of a barrier; relaxed: it only says "my MMAs have finished reading your rows"
+__device__ __forceinline__ void mbar_arrive_peer(uint32_t bar, uint32_t peer) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(peer) : "memory");
+}
+// bulk copy own shared memory -> the same offset in the peer CTA, completing (bytes) on the peer's barrier
+__device__ __forceinline__ void bulk_push_to_peer(uint32_t addr, uint32_t bytes, uint32_t bar, uint32_t peer) {
+  asm volatile(
+      "{\n\t.reg .b32 rd, rb;\n\t"
+      "mapa.shared::cluster.u32 rd, %0, %3;\n\t"
+      "mapa.shared::cluster.u32 rb, %2, %3;\n\t"
+      "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [rd], [%0], %1, [rb];\n\t}"
+      ::"r"(addr), "r"(bytes), "r"(bar), "r"(peer) : "memory");
+}
+
+struct AttnBars {
+  uint64_t w, qkv, s, o, y;          // weights landed / qkv_h, S, O_h, Y accumulators complete (tcgen05.commit)
+  uint64_t klocal, vlocal;           // this CTA's workers have stored Q' + their K rows / their V rows (8 warp arrivals)
+  uint64_t kfull, vfull;             // the peer's 128 K / V rows have landed here (bulk push, 16 KB each)
+  uint64_t kfree, vfree;             // the peer's MMAs are done with the rows this CTA pushed (remote arrive)
+  uint64_t odone;                    // all heads' attention outputs are in shared memory (8 warp arrivals)
+  uint64_t pready[4];                // softmax chunk i of every worker warp is in tensor memory (8 warp arrivals)
+};
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AT_THREADS, 1) attn_block_tc_kernel(const AttnTcParams p) {
   extern __shared__ uint8_t at_raw[];
-  __shared__ uint64_t bar_w, bar_qkv, bar_s, bar_o, bar_y;
+  __shared__ AttnBars bars;
   __shared__ uint32_t tmem_slot;
   __shared__ float s_part[AT_THREADS][2];
   __shared__ float s_mine[16], s_peer[16];
@@ -81,15 +115,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AT_THREADS, 1) attn_
   const bool ctrl = warp == 0;
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const uint32_t sb = ptx::smem_u32(sm);
-  uint8_t* sm_peer = cluster.map_shared_rank(sm, peer);
   float* peer_part = cluster.map_shared_rank(&s_peer[0], peer);
-  const uint32_t b_w = ptx::smem_u32(&bar_w), b_qkv = ptx::smem_u32(&bar_qkv), b_s = ptx::smem_u32(&bar_s),
-                 b_o = ptx::smem_u32(&bar_o), b_y = ptx::smem_u32(&bar_y);
+  const uint32_t b_w = ptx::smem_u32(&bars.w), b_qkv = ptx::smem_u32(&bars.qkv), b_s = ptx::smem_u32(&bars.s),
+                 b_o = ptx::smem_u32(&bars.o), b_y = ptx::smem_u32(&bars.y), b_kl = ptx::smem_u32(&bars.klocal),
+                 b_vl = ptx::smem_u32(&bars.vlocal), b_kf = ptx::smem_u32(&bars.kfull), b_vf = ptx::smem_u32(&bars.vfull),
+                 b_kfree = ptx::smem_u32(&bars.kfree), b_vfree = ptx::smem_u32(&bars.vfree),
+                 b_od = ptx::smem_u32(&bars.odone), b_p0 = ptx::smem_u32(&bars.pready[0]);
 
   for (int i = tid; i < 576; i += AT_THREADS) s_bqkv[i] = p.bias_qkv[i];
   for (int i = tid; i < 192; i += AT_THREADS) { s_bproj[i] = p.bias_proj[i]; s_gamma[i] = p.gamma[i]; s_beta[i] = p.beta[i]; }
   if (tid == 0) {
-    ptx::mbar_init(b_w, 1); ptx::mbar_init(b_qkv, 1); ptx::mbar_init(b_s, 1); ptx::mbar_init(b_o, 1); ptx::mbar_init(b_y, 1);
+    for (uint32_t b : {b_w, b_qkv, b_s, b_o, b_y, b_kf, b_vf, b_kfree, b_vfree}) ptx::mbar_init(b, 1);
+    for (uint32_t b : {b_kl, b_vl, b_od}) ptx::mbar_init(b, 8);
+    for (int i = 0; i < 4; ++i) ptx::mbar_init(b_p0 + 8 * i, 8);
     ptx::fence_barrier_init();
   }
   if (ctrl) ptx::tmem_alloc_512(ptx::smem_u32(&tmem_slot));
@@ -97,21 +135,43 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AT_THREADS, 1) attn_
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  cluster.sync();   // the peer is running: its shared memory may be written from here on
+  cluster.sync();   // the peer is running and its barriers are initialised: its shared memory may be written from here on
 
   const int ncl = gridDim.x >> 1, cl = blockIdx.x >> 1;
-  uint32_t ph_w = 0, ph_qkv = 0, ph_s = 0, ph_o = 0, ph_y = 0;
+  // phase parities, one set per waiting role (control lane / workers); every wait flips its own bit
+  uint32_t ph_w = 0, ph_qkv = 0, ph_s = 0, ph_o = 0, ph_y = 0, ph_kl = 0, ph_vl = 0, ph_kf = 0, ph_vf = 0, ph_kfree = 0,
+           ph_vfree = 0, ph_od = 0, ph_p = 0;
   if (ctrl && lane == 0 && cl < p.B) {
     ptx::mbar_expect_tx(b_w, WH_BYTES);
     ptx::bulk_load_1d(sb + W_OFF, p.wpack, WH_BYTES, b_w);
+    // the peer's 128 K / V rows of a head land here: each phase is armed as soon as the previous one has completed, i.e.
+    // always before this CTA lets the peer push again (kfree / vfree, or the per-image cluster barrier)
+    ptx::mbar_expect_tx(b_kf, 16384);
+    ptx::mbar_expect_tx(b_vf, 16384);
   }
   // worker coordinates (meaningless for the control warp)
   const int wq = warp & 3, hf = (warp - 1) >> 2;
   const int row = wq * 32 + lane;                    // token inside this CTA = TMEM lane
   const int gt = static_cast<int>(rank) * AT_TOK + row;   // token inside the image = key index
+  const int wt = tid - 32;                           // worker thread index 0..255
   const uint32_t lane_addr = tmem + (static_cast<uint32_t>(wq * 32) << 16);
   // phase-0 coordinates: thread = (16-byte channel chunk, token lane)
   const int c0 = tid % 24, tl = tid / 24;
+
+  // raw x of this CTA's 128 tokens of image `im` -> the Xn slots (normalised in place by phase 0) or -> the staging rows
+  // of the epilogue (residual); worker threads only, 16-byte cp.async per (token, chunk), coalesced in global memory
+  auto fetch_x = [&](int im, bool to_xn) {
+    const __nv_bfloat16* src = p.x + static_cast<size_t>(im) * AT_PIMG;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+      const int i = wt + 256 * k, tok = i / 24, ch = i - tok * 24;
+      const int g_t = static_cast<int>(rank) * AT_TOK + tok, y = g_t >> 4, x = g_t & 15;
+      const uint32_t dst = to_xn ? sb + XN_OFF + (ch >> 3) * KBLK + sw128(tok, ch & 7) : sb + R_OFF + tok * 384 + ((ch ^ (tok & 7)) << 4);
+      cp_async16(dst, src + ((y + 1) * 18 + x + 1) * 192 + ch * 8);
+    }
+    cp_async_commit();
+  };
+  if (!ctrl && cl < p.B) fetch_x(cl, true);
 
   for (int img = cl; img < p.B; img += ncl) {
     // clock64 phase profile (tests / tuning only): control lane and the first worker lane of CTA 0, second image of its loop
@@ -120,19 +180,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AT_THREADS, 1) attn_
     int prof_i = 0;
 #define AT_PROF() { if (prof && prof_i < ATTN_PROF_SLOTS) prof[prof_i++] = clock64(); }
     AT_PROF();
-    const __nv_bfloat16* xb = p.x + static_cast<size_t>(img) * AT_PIMG;
     __nv_bfloat16* ob = p.out + static_cast<size_t>(img) * AT_PIMG;
     float* dbg = (p.dbg && img == 0) ? p.dbg : nullptr;
-    // ---- phase 0: GroupNorm of the image (statistics over both CTAs' halves) -> Xn, the A operand of the projections
+    // ---- phase 0 (all threads): GroupNorm statistics over both CTAs' halves, Xn normalised in place -----------------
     {
       uint4 v[11];
+      cp_async_wait<0>();
+      __syncthreads();      // the prefetched rows (fetch_x of the previous image's tail) are visible to every thread
 #pragma unroll
       for (int k = 0; k < 11; ++k) {
         const int tok = tl + 12 * k;
-        if (tok < AT_TOK) {
-          const int g_t = static_cast<int>(rank) * AT_TOK + tok, y = g_t >> 4, x = g_t & 15;
-          v[k] = __ldg(reinterpret_cast<const uint4*>(xb + ((y + 1) * 18 + x + 1) * 192 + c0 * 8));
-        }
+        if (tok < AT_TOK) v[k] = *reinterpret_cast<const uint4*>(sm + XN_OFF + (c0 >> 3) * KBLK + sw128(tok, c0 & 7));
       }
       float s = 0.f, q = 0.f;
 #pragma unroll
@@ -146,15 +204,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AT_THREADS, 1) attn_
       }
       s_part[tid][0] = s; s_part[tid][1] = q;
       __syncthreads();
-      if (tid < 16) {   // fixed-order combine: run-to-run bit-identical
-        const int g = tid >> 1, which = tid & 1;
+      if (tid < 64) {   // fixed-order combine (run-to-run bit-identical): 4 lanes x 9 partials per (group, sum | sum of squares)
+        const int pair = tid >> 2, part = tid & 3, g = pair >> 1, which = pair & 1;
         float a = 0.f;
-        for (int t2 = 0; t2 < 12; ++t2)
-          for (int cc = 0; cc < 3; ++cc) a += s_part[t2 * 24 + g * 3 + cc][which];
-        s_mine[tid] = a;
-        peer_part[tid] = a;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+          const int idx = part * 9 + j;
+          a += s_part[(idx / 3) * 24 + g * 3 + idx % 3][which];
+        }
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        if (part == 0) { s_mine[pair] = a; peer_part[pair] = a; }
       }
-      cluster.sync();
+      cluster.sync();   // also: both CTAs have finished the previous image (no stale traffic into reused buffers)
       if (tid < 8) {
         const float sa = rank == 0 ? s_mine[2 * tid] : s_peer[2 * tid], sb2 = rank == 0 ? s_peer[2 * tid] : s_mine[2 * tid];
         const float qa = rank == 0 ? s_mine[2 * tid + 1] : s_peer[2 * tid + 1], qb = rank == 0 ? s_peer[2 * tid + 1] : s_mine[2 * tid + 1];
@@ -163,7 +225,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AT_THREADS, 1) attn_
         double var = (static_cast<double>(qa) + static_cast<double>(qb)) * inv - mean * mean;
         var = var < 0.0 ? 0.0 : var;
         s_mean[tid] = static_cast<float>(mean);
-        s_rstd[tid] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(GN_EPS)));
+        s_rstd[tid] = rsqrtf(static_cast<float>(var) + GN_EPS);
       }
       __syncthreads();
       const int g = c0 / 3;
@@ -189,18 +251,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AT_THREADS, 1) attn_
           }
         }
       }
-      ptx::fence_proxy_async_all();
+      ptx::fence_proxy_async();
       ptx::tc_fence_before();
       __syncthreads();
-      AT_PROF();   // 1: phase 0 done
+      AT_PROF();   // phase 0 done
     }
-    // ---- per head -------------------------------------------------------------------------------------------------
-    for (int h = 0; h < N_HEADS; ++h) {
-      // (a) q|k|v of the head for this CTA's tokens
-      if (ctrl) {
-        if (lane == 0) {
-          ptx::mbar_wait(b_w, ph_w);
-          AT_PROF();   // c: weights there
+    if (ctrl) {
+      // ================= control lane: every MMA, the weight loads, the K / V pushes to the peer =====================
+      if (lane == 0) {
+        ptx::tc_fence_after();
+        auto issue_qkv = [&]() {   // qkv_h [128 x 144] = Xn . W_h^T (weights of the head must have landed)
+          ptx::mbar_wait(b_w, ph_w); ph_w ^= 1;
           ptx::tc_fence_after();
           const uint32_t idesc = make_idesc(128, 144);
 #pragma unroll
@@ -210,80 +271,161 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AT_THREADS, 1) attn_
             for (int ks = 0; ks < 4; ++ks) ptx::umma_bf16(tmem + QKV_COL, ad + 2 * ks, bd + 2 * ks, idesc, (kb | ks) ? 1u : 0u);
           }
           ptx::umma_commit(b_qkv);
-          AT_PROF();   // c: qkv issued
-          ptx::mbar_wait(b_qkv, ph_qkv);   // the weights (and, after the last head, Xn) are consumed: fetch the next set
-          if (h < N_HEADS - 1) {
+        };
+        auto load_weights = [&](int hn) {   // after qkv_{hn-1} has completed: head hn's weights, or the projection's
+          ptx::mbar_wait(b_qkv, ph_qkv); ph_qkv ^= 1;
+          if (hn < N_HEADS) {
             ptx::mbar_expect_tx(b_w, WH_BYTES);
-            ptx::bulk_load_1d(sb + W_OFF, p.wpack + static_cast<size_t>(h + 1) * WH_BYTES, WH_BYTES, b_w);
-          } else {
+            ptx::bulk_load_1d(sb + W_OFF, p.wpack + static_cast<size_t>(hn) * WH_BYTES, WH_BYTES, b_w);
+          } else {   // Xn is dead as well: the third K block of Wproj goes there
             const uint8_t* wp = p.wpack + static_cast<size_t>(N_HEADS) * WH_BYTES;
             ptx::mbar_expect_tx(b_w, WP_BYTES);
             ptx::bulk_load_1d(sb + W_OFF, wp, 2 * WP_KB, b_w);
             ptx::bulk_load_1d(sb + XN_OFF, wp + 2 * WP_KB, WP_KB, b_w);
           }
-          AT_PROF();   // c: qkv done, next weights requested
-        }
-        __syncwarp();
-      } else {
-        ptx::mbar_wait(b_qkv, ph_qkv);
-        AT_PROF();   // w: qkv accumulator ready
-        ptx::tc_fence_after();
-        // columns [72 hf, 72 hf + 72): 8-column chunks cj = 9 hf + j; chunks 0-5 are q, 6-11 k, 12-17 v
-        float f[72];
-        const uint32_t src = lane_addr + QKV_COL + 72 * hf;
-        ptx::tmem_ld32(src, f);
-        ptx::tmem_ld32(src + 32, f + 32);
-        ptx::tmem_ld8(src + 64, f + 64);
-        ptx::tmem_ld_wait();
+        };
+        issue_qkv();
+        load_weights(1);
+        AT_PROF();   // c: qkv_0 done, W_1 requested
+        for (int h = 0; h < N_HEADS; ++h) {
+          // K rows (and Q' in tensor memory) of my tokens are stored: push my K rows, then S as soon as the peer's are here
+          ptx::mbar_wait(b_kl, ph_kl); ph_kl ^= 1;
+          if (h > 0) { ptx::mbar_wait(b_kfree, ph_kfree); ph_kfree ^= 1; }
+          bulk_push_to_peer(sb + K_OFF + rank * 16384, 16384, b_kf, peer);
+          ptx::mbar_wait(b_kf, ph_kf); ph_kf ^= 1;
+          ptx::mbar_expect_tx(b_kf, 16384);
+          AT_PROF();   // c: all keys here
+          ptx::tc_fence_after();
+          {
+            const uint32_t idesc = make_idesc(128, 256);
+            const uint64_t kd = make_desc_sw128(sb + K_OFF);
 #pragma unroll
-        for (int j = 0; j < 9; ++j) {
-          const int cj = 9 * hf + j, kind = cj / 6, within = cj - kind * 6;
-          const float* bsrc = s_bqkv + kind * 192 + h * 48 + within * 8;
+            for (int ks = 0; ks < 3; ++ks) ptx::umma_bf16_ts(tmem + S_COL, tmem + Q_COL + 8 * ks, kd + 2 * ks, idesc, ks ? 1u : 0u);
+            ptx::umma_commit(b_s);
+          }
+          AT_PROF();   // c: S issued
+          ptx::mbar_wait(b_vl, ph_vl); ph_vl ^= 1;
+          if (h > 0) { ptx::mbar_wait(b_vfree, ph_vfree); ph_vfree ^= 1; }
+          bulk_push_to_peer(sb + V_OFF + rank * 16384, 16384, b_vf, peer);
+          if (h < N_HEADS - 1) issue_qkv();   // next head's projection runs under this head's softmax (qkv_h has been read)
+          ptx::mbar_wait(b_s, ph_s); ph_s ^= 1;                       // S_h complete: the peer may overwrite its K rows here
+          if (h < N_HEADS - 1) mbar_arrive_peer(b_kfree, peer);
+          AT_PROF();   // c: V pushed, next qkv issued
+          ptx::mbar_wait(b_vf, ph_vf); ph_vf ^= 1;
+          ptx::mbar_expect_tx(b_vf, 16384);
+          {
+            const uint32_t idesc = make_idesc(128, 48) | IDESC_B_MN_MAJOR;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {   // O_h += P V_h for the 64 keys of softmax chunk i, as soon as that chunk is stored
+              ptx::mbar_wait(b_p0 + 8 * i, ph_p);
+              ptx::tc_fence_after();
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int ks = (j >> 1) * 8 + 2 * i + (j & 1);             // 16-key step: halves 0 / 1 hold keys 0-127 / 128-255
+                const uint32_t a_col = S_COL + (j >> 1) * 128 + 16 * i + 8 * (j & 1);
+                ptx::umma_bf16_ts(tmem + O_COL, tmem + a_col, make_desc_sw128_mn(sb + V_OFF + ks * 2048), idesc, (i | j) ? 1u : 0u);
+              }
+            }
+            ph_p ^= 1;
+            ptx::umma_commit(b_o);
+          }
+          AT_PROF();   // c: PV issued
+          if (h < N_HEADS - 1) load_weights(h + 2);                    // qkv_{h+1} complete -> W_{h+2} / Wproj
+          ptx::mbar_wait(b_o, ph_o); ph_o ^= 1;                       // O_h complete: the S / P columns and V rows are free
+          if (h < N_HEADS - 1) mbar_arrive_peer(b_vfree, peer);
+          AT_PROF();   // c: head done
+        }
+        // projection
+        ptx::mbar_wait(b_od, ph_od); ph_od ^= 1;
+        ptx::mbar_wait(b_w, ph_w); ph_w ^= 1;
+        ptx::tc_fence_after();
+        {
+          const uint32_t idesc = make_idesc(128, 192);
+#pragma unroll
+          for (int kb = 0; kb < 3; ++kb) {
+            const uint64_t ad = make_desc_sw128(sb + O_OFF + kb * KBLK);
+            const uint64_t bd = make_desc_sw128(kb < 2 ? sb + W_OFF + kb * WP_KB : sb + XN_OFF);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) ptx::umma_bf16(tmem + S_COL, ad + 2 * ks, bd + 2 * ks, idesc, (kb | ks) ? 1u : 0u);
+          }
+          ptx::umma_commit(b_y);
+        }
+        AT_PROF();   // c: projection issued
+        ptx::mbar_wait(b_y, ph_y); ph_y ^= 1;
+        if (img + ncl < p.B) {   // first head's weights of the next image
+          ptx::mbar_expect_tx(b_w, WH_BYTES);
+          ptx::bulk_load_1d(sb + W_OFF, p.wpack, WH_BYTES, b_w);
+        }
+        AT_PROF();   // c: image done
+      }
+      __syncwarp();
+    } else {
+      // ================= workers =====================================================================================
+      // q|k|v of head hh: Q' (hf 0) -> tensor memory, K rows (hf 1) -> shared memory; then (second call) the V rows
+      auto convert_qk = [&](int hh) {
+        ptx::mbar_wait(b_qkv, ph_qkv); ph_qkv ^= 1;
+        ptx::tc_fence_after();
+        float f[48];
+        const uint32_t src = lane_addr + QKV_COL + 48 * hf;
+        ptx::tmem_ld32(src, f);
+        ptx::tmem_ld16(src + 32, f + 32);
+        ptx::tmem_ld_wait();
+        const float* bsrc = s_bqkv + hf * 192 + hh * 48;
+        // the K rows of the previous head were the source of a push: the peer's "S complete" also says that push has landed
+        if (hh > 0) { ptx::mbar_wait(b_kfree, ph_kfree); ph_kfree ^= 1; }
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
           float g8[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) g8[i] = f[8 * j + i] + bsrc[i];
+          for (int i = 0; i < 8; ++i) g8[i] = f[8 * j + i] + bsrc[8 * j + i];
           if (dbg) {
-            for (int i = 0; i < 8; ++i) dbg[ATTN_DBG_QKV + static_cast<size_t>(gt) * 576 + kind * 192 + h * 48 + within * 8 + i] = g8[i];
+            for (int i = 0; i < 8; ++i) dbg[ATTN_DBG_QKV + static_cast<size_t>(gt) * 576 + hf * 192 + hh * 48 + j * 8 + i] = g8[i];
           }
-          if (kind == 0) {
+          if (hf == 0) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) g8[i] *= QSCALE;
             const uint4 u = pack8(g8);
-            ptx::tmem_st4(lane_addr + Q_COL + within * 4, reinterpret_cast<const uint32_t*>(&u));
+            ptx::tmem_st4(lane_addr + Q_COL + j * 4, reinterpret_cast<const uint32_t*>(&u));
           } else {
-            const uint4 u = pack8(g8);
-            const uint32_t off = (kind == 1 ? K_OFF : V_OFF) + sw128(gt, within);
-            *reinterpret_cast<uint4*>(sm + off) = u;
-            *reinterpret_cast<uint4*>(sm_peer + off) = u;
+            *reinterpret_cast<uint4*>(sm + K_OFF + sw128(gt, j)) = pack8(g8);
           }
         }
-        ptx::tmem_st_wait();
-        AT_PROF();   // w: q, k, v converted and stored
-        ptx::fence_proxy_async_all();
+        if (hf == 0) ptx::tmem_st_wait(); else ptx::fence_proxy_async();
         ptx::tc_fence_before();
-        AT_PROF();   // w: fences
-      }
-      ph_w ^= 1; ph_qkv ^= 1;
-      cluster.sync();   // all 256 key / value rows of the head are in both CTAs' shared memory
-      AT_PROF();   // both: cluster sync A passed
-      // (b) S = Q' K^T
-      if (ctrl) {
-        if (lane == 0) {
-          ptx::fence_proxy_async_all();
-          ptx::tc_fence_after();
-          const uint32_t idesc = make_idesc(128, 256);
-          const uint64_t kd = make_desc_sw128(sb + K_OFF);
-#pragma unroll
-          for (int ks = 0; ks < 3; ++ks) ptx::umma_bf16_ts(tmem + S_COL, tmem + Q_COL + 8 * ks, kd + 2 * ks, idesc, ks ? 1u : 0u);
-          ptx::umma_commit(b_s);
-          AT_PROF();   // c: S issued
-        }
         __syncwarp();
-      } else {
-        ptx::mbar_wait(b_s, ph_s);
+        if (lane == 0) ptx::mbar_arrive(b_kl);
+      };
+      auto convert_v = [&](int hh) {
+        float f[24];
+        const uint32_t src = lane_addr + QKV_COL + 96 + 24 * hf;
+        ptx::tmem_ld16(src, f);
+        ptx::tmem_ld8(src + 16, f + 16);
+        ptx::tmem_ld_wait();
+        const float* bsrc = s_bqkv + 384 + hh * 48 + 24 * hf;
+        if (hh > 0) { ptx::mbar_wait(b_vfree, ph_vfree); ph_vfree ^= 1; }   // same for the V rows (the peer's O complete)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          float g8[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) g8[i] = f[8 * j + i] + bsrc[8 * j + i];
+          if (dbg) {
+            for (int i = 0; i < 8; ++i) dbg[ATTN_DBG_QKV + static_cast<size_t>(gt) * 576 + 384 + hh * 48 + 24 * hf + j * 8 + i] = g8[i];
+          }
+          *reinterpret_cast<uint4*>(sm + V_OFF + sw128(gt, 3 * hf + j)) = pack8(g8);
+        }
+        ptx::fence_proxy_async();
+        ptx::tc_fence_before();     // the qkv_h columns have been read: the control lane may issue the next projection
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(b_vl);
+      };
+      convert_qk(0);
+      convert_v(0);
+      AT_PROF();   // w: head 0 converted
+      for (int h = 0; h < N_HEADS; ++h) {
+        // ---- softmax over keys [128 hf, 128 hf + 128) of row `row`; P (bf16) overwrites the first half of those columns
+        ptx::mbar_wait(b_s, ph_s); ph_s ^= 1;
         AT_PROF();   // w: S ready
         ptx::tc_fence_after();
-        // softmax over keys [128 hf, 128 hf + 128) of row `row`; P (bf16) overwrites the first half of those columns
         const uint32_t sc = lane_addr + S_COL + 128 * hf;
         float m = -INFINITY;
 #pragma unroll
@@ -295,9 +437,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AT_THREADS, 1) attn_
           for (int j = 0; j < 32; ++j) m = fmaxf(m, sv[j]);
         }
         s_max[hf][row] = m;
-        AT_PROF();   // w: pass 1 (max) done
         worker_bar();
-        AT_PROF();   // w: worker barrier
         m = fmaxf(s_max[0][row], s_max[1][row]);
         float l = 0.f;
 #pragma unroll
@@ -313,89 +453,59 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AT_THREADS, 1) attn_
             pk[j] = pack2(p0, p1);
           }
           ptx::tmem_st16(sc + 16 * i, pk);
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(b_p0 + 8 * i);
         }
         s_sum[hf][row] = l;
-        ptx::tmem_st_wait();
-        ptx::tc_fence_before();
-        AT_PROF();   // w: pass 2 (exp, P stored) done
-      }
-      ph_s ^= 1;
-      __syncthreads();
-      AT_PROF();   // both: block sync after softmax
-      // (c) O_h = P V_h
-      if (ctrl) {
-        if (lane == 0) {
-          ptx::tc_fence_after();
-          const uint32_t idesc = make_idesc(128, 48) | IDESC_B_MN_MAJOR;
-#pragma unroll
-          for (int ks = 0; ks < 16; ++ks) {
-            const uint32_t a_col = S_COL + (ks < 8 ? 8 * ks : 128 + 8 * (ks - 8));
-            ptx::umma_bf16_ts(tmem + O_COL, tmem + a_col, make_desc_sw128_mn(sb + V_OFF + ks * 2048), idesc, ks ? 1u : 0u);
-          }
-          ptx::umma_commit(b_o);
-          AT_PROF();   // c: PV issued
-        }
-        __syncwarp();
-      } else {
-        ptx::mbar_wait(b_o, ph_o);
+        AT_PROF();   // w: softmax done
+        // ---- next head's Q' and K rows (S_h is complete, so Q' and this CTA's K rows may be overwritten) ---------------
+        if (h < N_HEADS - 1) convert_qk(h + 1);
+        AT_PROF();   // w: next q, k converted
+        // ---- O_h / l -> shared memory (A operand of the projection) ----------------------------------------------------
+        ptx::mbar_wait(b_o, ph_o); ph_o ^= 1;
         AT_PROF();   // w: O ready
         ptx::tc_fence_after();
-        float o[24];
-        ptx::tmem_ld16(lane_addr + O_COL + 24 * hf, o);
-        ptx::tmem_ld8(lane_addr + O_COL + 24 * hf + 16, o + 16);
-        ptx::tmem_ld_wait();
-        const float lsum = s_sum[0][row] + s_sum[1][row];
-        const float inv = 1.0f / lsum;
-        if (dbg && hf == 0) dbg[ATTN_DBG_L + static_cast<size_t>(gt) * 4 + h] = lsum;
+        {
+          float o[24];
+          ptx::tmem_ld16(lane_addr + O_COL + 24 * hf, o);
+          ptx::tmem_ld8(lane_addr + O_COL + 24 * hf + 16, o + 16);
+          ptx::tmem_ld_wait();
+          const float lsum = s_sum[0][row] + s_sum[1][row];
+          const float inv = 1.0f / lsum;
+          if (dbg && hf == 0) dbg[ATTN_DBG_L + static_cast<size_t>(gt) * 4 + h] = lsum;
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          float g8[8];
+          for (int j = 0; j < 3; ++j) {
+            float g8[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) g8[i] = o[8 * j + i] * inv;
-          const int gc = h * 6 + 3 * hf + j;   // 16-byte chunk of the 192-channel row
-          *reinterpret_cast<uint4*>(sm + O_OFF + (gc >> 3) * KBLK + sw128(row, gc & 7)) = pack8(g8);
-          if (dbg) {
-            for (int i = 0; i < 8; ++i) dbg[ATTN_DBG_Y + static_cast<size_t>(gt) * 192 + gc * 8 + i] = g8[i];
+            for (int i = 0; i < 8; ++i) g8[i] = o[8 * j + i] * inv;
+            const int gc = h * 6 + 3 * hf + j;   // 16-byte chunk of the 192-channel row
+            *reinterpret_cast<uint4*>(sm + O_OFF + (gc >> 3) * KBLK + sw128(row, gc & 7)) = pack8(g8);
+            if (dbg) {
+              for (int i = 0; i < 8; ++i) dbg[ATTN_DBG_Y + static_cast<size_t>(gt) * 192 + gc * 8 + i] = g8[i];
+            }
           }
         }
-        ptx::fence_proxy_async_all();
-        ptx::tc_fence_before();
-        AT_PROF();   // w: O converted
-      }
-      ph_o ^= 1;
-      cluster.sync();   // the peer's MMAs have read this head's K / V rows: the next head may overwrite them
-      AT_PROF();   // both: cluster sync B passed
-    }
-    // ---- projection + residual ------------------------------------------------------------------------------------
-    if (ctrl) {
-      if (lane == 0) {
-        ptx::mbar_wait(b_w, ph_w);
-        ptx::fence_proxy_async_all();
-        ptx::tc_fence_after();
-        const uint32_t idesc = make_idesc(128, 192);
-#pragma unroll
-        for (int kb = 0; kb < 3; ++kb) {
-          const uint64_t ad = make_desc_sw128(sb + O_OFF + kb * KBLK);
-          const uint64_t bd = make_desc_sw128(kb < 2 ? sb + W_OFF + kb * WP_KB : sb + XN_OFF);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) ptx::umma_bf16(tmem + S_COL, ad + 2 * ks, bd + 2 * ks, idesc, (kb | ks) ? 1u : 0u);
+        // ---- next head's V rows (O_h is complete, so the V rows may be overwritten) ------------------------------------
+        if (h < N_HEADS - 1) {
+          convert_v(h + 1);
+        } else {
+          ptx::fence_proxy_async();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(b_od);
         }
-        ptx::umma_commit(b_y);
-        AT_PROF();   // c: projection issued
-        ptx::mbar_wait(b_y, ph_y);
-        if (img + ncl < p.B) {   // first head's weights of the next image
-          ptx::mbar_expect_tx(b_w, WH_BYTES);
-          ptx::bulk_load_1d(sb + W_OFF, p.wpack, WH_BYTES, b_w);
-        }
+        AT_PROF();   // w: head done
       }
-      __syncwarp();
-    } else {
-      ptx::mbar_wait(b_y, ph_y);
+      // ---- projection epilogue: y + bias + x -> bf16, staged in the idle K / V regions, then coalesced stores ---------
+      fetch_x(img, false);   // residual rows (the peer pushes nothing more for this image)
+      ptx::mbar_wait(b_y, ph_y); ph_y ^= 1;
       AT_PROF();   // w: Y ready
       ptx::tc_fence_after();
-      const int y = gt >> 4, x = gt & 15;
-      const size_t pix = static_cast<size_t>((y + 1) * 18 + x + 1) * 192 + 96 * hf;
-      const long long wy = static_cast<long long>(halo_wrap16(y)) * 18 * 192, wx = static_cast<long long>(halo_wrap16(x)) * 192;
+      if (img + ncl < p.B) fetch_x(img + ncl, true); else cp_async_commit();   // Wproj consumed: prefetch the next image
+      cp_async_wait<1>();    // the residual rows (the group before the prefetch)
+      worker_bar();
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
         float yv[32];
@@ -403,28 +513,36 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AT_THREADS, 1) attn_
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int ch = 32 * i + 8 * j;
+          const int ch = 12 * hf + 4 * i + j;   // 16-byte chunk of the 192-channel row
+          uint4* slot = reinterpret_cast<uint4*>(sm + R_OFF + row * 384 + ((ch ^ (row & 7)) << 4));
           float r[8], g8[8];
-          unpack8(__ldg(reinterpret_cast<const uint4*>(xb + pix + ch)), r);
+          unpack8(*slot, r);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) g8[e] = yv[8 * j + e] + s_bproj[96 * hf + ch + e] + r[e];
-          const uint4 u = pack8(g8);
-          __nv_bfloat16* dst = ob + pix + ch;
-          *reinterpret_cast<uint4*>(dst) = u;
-          if (wy) *reinterpret_cast<uint4*>(dst + wy) = u;
-          if (wx) *reinterpret_cast<uint4*>(dst + wx) = u;
-          if (wy && wx) *reinterpret_cast<uint4*>(dst + wy + wx) = u;
+          for (int e = 0; e < 8; ++e) g8[e] = yv[8 * j + e] + s_bproj[ch * 8 + e] + r[e];
+          *slot = pack8(g8);
         }
       }
       ptx::tc_fence_before();
+      worker_bar();
+      AT_PROF();   // w: output rows staged
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {   // staging rows -> padded global tensor, coalesced; border pixels also go to the opposite halo
+        const int i = wt + 256 * k, tok = i / 24, ch = i - tok * 24;
+        const uint4 u = *reinterpret_cast<const uint4*>(sm + R_OFF + tok * 384 + ((ch ^ (tok & 7)) << 4));
+        const int g_t = static_cast<int>(rank) * AT_TOK + tok, y = g_t >> 4, x = g_t & 15;
+        __nv_bfloat16* dst = ob + static_cast<size_t>((y + 1) * 18 + x + 1) * 192 + ch * 8;
+        const long long wy = static_cast<long long>(halo_wrap16(y)) * 18 * 192, wx = static_cast<long long>(halo_wrap16(x)) * 192;
+        *reinterpret_cast<uint4*>(dst) = u;
+        if (wy) *reinterpret_cast<uint4*>(dst + wy) = u;
+        if (wx) *reinterpret_cast<uint4*>(dst + wx) = u;
+        if (wy && wx) *reinterpret_cast<uint4*>(dst + wy + wx) = u;
+      }
+      AT_PROF();   // w: image written
     }
-    AT_PROF();   // both: epilogue / projection done
-    ph_w ^= 1; ph_y ^= 1;
-    __syncthreads();   // Y has been read and the projection weights consumed: the next image may overwrite Xn / S
   }
 #undef AT_PROF
   ptx::tc_fence_before();
-  cluster.sync();      // no DSMEM store may target a CTA that has exited
+  cluster.sync();      // no remote arrive / push may target a CTA that has exited
   if (ctrl) ptx::tmem_dealloc_512(tmem);
 }
 
