@@ -21,6 +21,7 @@
 // were probed on B200 first: tools/umma_attn_probe.cu, profiles/r2_attn_probe.txt.
 #include <cooperative_groups.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -62,12 +63,6 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
 __device__ __forceinline__ uint4 pack8(const float* f) {
   return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
 }
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N_>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
 __device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ int halo_wrap16(int v) { return v == 0 ? 16 : (v == 15 ? -16 : 0); }
 
@@ -89,16 +84,30 @@ __device__ __forceinline__ void bulk_push_to_peer(uint32_t addr, uint32_t bytes,
       ::"r"(addr), "r"(bytes), "r"(bar), "r"(peer) : "memory");
 }
 
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+// tensor maps of the padded [B,18,18,192] bf16 input / output (SWIZZLE_128B, 64-channel boxes)
+struct AttnTcMaps {
+  CUtensorMap x;         // box 64 ch x 16 px x 8 rows: one CTA's rows of a K block
+  CUtensorMap out;       // the same box over the output tensor
+  CUtensorMap out_row;   // box 64 ch x 16 px x 1 row (the wrapped halo rows)
+};
+
 struct AttnBars {
   uint64_t w, qkv, s, o, y;          // weights landed / qkv_h, S, O_h, Y accumulators complete (tcgen05.commit)
   uint64_t klocal, vlocal;           // this CTA's workers have stored Q' + their K rows / their V rows (8 warp arrivals)
   uint64_t kfull, vfull;             // the peer's 128 K / V rows have landed here (bulk push, 16 KB each)
   uint64_t kfree, vfree;             // the peer's MMAs are done with the rows this CTA pushed (remote arrive)
   uint64_t odone;                    // all heads' attention outputs are in shared memory (8 warp arrivals)
+  uint64_t resid;                    // this image's input rows (residual) have landed in the staging rows (3 TMA boxes)
+  uint64_t xrows;                    // the next image's raw input rows have landed in the O region (8 bulk copies)
   uint64_t pready[4];                // softmax chunk i of every worker warp is in tensor memory (8 warp arrivals)
 };
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AT_THREADS, 1) attn_block_tc_kernel(const AttnTcParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AT_THREADS, 1) attn_block_tc_kernel(const __grid_constant__ AttnTcMaps maps, const AttnTcParams p) {
   extern __shared__ uint8_t at_raw[];
   __shared__ AttnBars bars;
   __shared__ uint32_t tmem_slot;
@@ -120,16 +129,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AT_THREADS, 1) attn_
                  b_o = ptx::smem_u32(&bars.o), b_y = ptx::smem_u32(&bars.y), b_kl = ptx::smem_u32(&bars.klocal),
                  b_vl = ptx::smem_u32(&bars.vlocal), b_kf = ptx::smem_u32(&bars.kfull), b_vf = ptx::smem_u32(&bars.vfull),
                  b_kfree = ptx::smem_u32(&bars.kfree), b_vfree = ptx::smem_u32(&bars.vfree),
-                 b_od = ptx::smem_u32(&bars.odone), b_p0 = ptx::smem_u32(&bars.pready[0]);
+                 b_od = ptx::smem_u32(&bars.odone), b_p0 = ptx::smem_u32(&bars.pready[0]), b_x = ptx::smem_u32(&bars.xrows), b_r = ptx::smem_u32(&bars.resid);
 
   for (int i = tid; i < 576; i += AT_THREADS) s_bqkv[i] = p.bias_qkv[i];
   for (int i = tid; i < 192; i += AT_THREADS) { s_bproj[i] = p.bias_proj[i]; s_gamma[i] = p.gamma[i]; s_beta[i] = p.beta[i]; }
   if (tid == 0) {
-    for (uint32_t b : {b_w, b_qkv, b_s, b_o, b_y, b_kf, b_vf, b_kfree, b_vfree}) ptx::mbar_init(b, 1);
+    for (uint32_t b : {b_w, b_qkv, b_s, b_o, b_y, b_kf, b_vf, b_kfree, b_vfree, b_x, b_r}) ptx::mbar_init(b, 1);
     for (uint32_t b : {b_kl, b_vl, b_od}) ptx::mbar_init(b, 8);
     for (int i = 0; i < 4; ++i) ptx::mbar_init(b_p0 + 8 * i, 8);
     ptx::fence_barrier_init();
   }
+  if (tid == 32) { ptx::prefetch_tmap(&maps.x); ptx::prefetch_tmap(&maps.out); ptx::prefetch_tmap(&maps.out_row); }
   if (ctrl) ptx::tmem_alloc_512(ptx::smem_u32(&tmem_slot));
   ptx::tc_fence_before();
   __syncthreads();
@@ -138,9 +148,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AT_THREADS, 1) attn_
   cluster.sync();   // the peer is running and its barriers are initialised: its shared memory may be written from here on
 
   const int ncl = gridDim.x >> 1, cl = blockIdx.x >> 1;
+  if (p.stagger > 0) {   // de-synchronise the clusters: their memory phases (image boundaries) then hit L2 / HBM at different times
+    const long long t0 = clock64(), d = static_cast<long long>(cl & 15) * p.stagger;
+    while (clock64() - t0 < d) { }
+  }
   // phase parities, one set per waiting role (control lane / workers); every wait flips its own bit
   uint32_t ph_w = 0, ph_qkv = 0, ph_s = 0, ph_o = 0, ph_y = 0, ph_kl = 0, ph_vl = 0, ph_kf = 0, ph_vf = 0, ph_kfree = 0,
-           ph_vfree = 0, ph_od = 0, ph_p = 0;
+           ph_vfree = 0, ph_od = 0, ph_p = 0, ph_x = 0, ph_r = 0;
   if (ctrl && lane == 0 && cl < p.B) {
     ptx::mbar_expect_tx(b_w, WH_BYTES);
     ptx::bulk_load_1d(sb + W_OFF, p.wpack, WH_BYTES, b_w);
@@ -158,20 +172,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AT_THREADS, 1) attn_
   // phase-0 coordinates: thread = (16-byte channel chunk, token lane)
   const int c0 = tid % 24, tl = tid / 24;
 
-  // raw x of this CTA's 128 tokens of image `im` -> the Xn slots (normalised in place by phase 0) or -> the staging rows
-  // of the epilogue (residual); worker threads only, 16-byte cp.async per (token, chunk), coalesced in global memory
-  auto fetch_x = [&](int im, bool to_xn) {
+  // raw x of this CTA's 8 image rows of image `im` -> the O region as plain [token][384 B] rows: one 6144-byte bulk copy
+  // per image row (16 pixels are contiguous in the padded tensor); phase 0 normalises them into the Xn slots
+  auto fetch_x = [&](int im) {
     const __nv_bfloat16* src = p.x + static_cast<size_t>(im) * AT_PIMG;
+    ptx::mbar_expect_tx(b_x, 8 * 6144);
 #pragma unroll
-    for (int k = 0; k < 12; ++k) {
-      const int i = wt + 256 * k, tok = i / 24, ch = i - tok * 24;
-      const int g_t = static_cast<int>(rank) * AT_TOK + tok, y = g_t >> 4, x = g_t & 15;
-      const uint32_t dst = to_xn ? sb + XN_OFF + (ch >> 3) * KBLK + sw128(tok, ch & 7) : sb + R_OFF + tok * 384 + ((ch ^ (tok & 7)) << 4);
-      cp_async16(dst, src + ((y + 1) * 18 + x + 1) * 192 + ch * 8);
-    }
-    cp_async_commit();
+    for (int r = 0; r < 8; ++r)
+      ptx::bulk_load_1d(sb + O_OFF + r * 6144, src + ((static_cast<int>(rank) * 8 + r + 1) * 18 + 1) * 192, 6144, b_x);
   };
-  if (!ctrl && cl < p.B) fetch_x(cl, true);
+  if (ctrl && lane == 0 && cl < p.B) fetch_x(cl);
 
   for (int img = cl; img < p.B; img += ncl) {
     // clock64 phase profile (tests / tuning only): control lane and the first worker lane of CTA 0, second image of its loop
@@ -185,12 +195,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AT_THREADS, 1) attn_
     // ---- phase 0 (all threads): GroupNorm statistics over both CTAs' halves, Xn normalised in place -----------------
     {
       uint4 v[11];
-      cp_async_wait<0>();
-      __syncthreads();      // the prefetched rows (fetch_x of the previous image's tail) are visible to every thread
+      ptx::mbar_wait(b_x, ph_x); ph_x ^= 1;   // the raw rows (fetch_x in the previous image's tail)
 #pragma unroll
       for (int k = 0; k < 11; ++k) {
         const int tok = tl + 12 * k;
-        if (tok < AT_TOK) v[k] = *reinterpret_cast<const uint4*>(sm + XN_OFF + (c0 >> 3) * KBLK + sw128(tok, c0 & 7));
+        if (tok < AT_TOK) v[k] = *reinterpret_cast<const uint4*>(sm + O_OFF + tok * 384 + c0 * 16);
       }
       float s = 0.f, q = 0.f;
 #pragma unroll
@@ -253,6 +262,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AT_THREADS, 1) attn_
       }
       ptx::fence_proxy_async();
       ptx::tc_fence_before();
+      ptx::bulk_wait_read<0>();   // the previous image's output rows have left the staging rows (= the K / V regions)
       __syncthreads();
       AT_PROF();   // phase 0 done
     }
@@ -332,7 +342,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AT_THREADS, 1) attn_
           AT_PROF();   // c: PV issued
           if (h < N_HEADS - 1) load_weights(h + 2);                    // qkv_{h+1} complete -> W_{h+2} / Wproj
           ptx::mbar_wait(b_o, ph_o); ph_o ^= 1;                       // O_h complete: the S / P columns and V rows are free
-          if (h < N_HEADS - 1) mbar_arrive_peer(b_vfree, peer);
+          if (h < N_HEADS - 1) {
+            mbar_arrive_peer(b_vfree, peer);
+          } else {   // the K / V regions are idle until the next image: this image's input rows (the residual) go there, as
+                     // three 64-channel boxes in the K-block layout (conflict-free for one token per lane)
+            ptx::mbar_expect_tx(b_r, 3 * KBLK);
+#pragma unroll
+            for (int kb = 0; kb < 3; ++kb)
+              ptx::tma_load_4d(sb + R_OFF + kb * KBLK, &maps.x, b_r, kb * 64, 1, 1 + 8 * static_cast<int>(rank), img);
+          }
           AT_PROF();   // c: head done
         }
         // projection
@@ -352,7 +370,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AT_THREADS, 1) attn_
         }
         AT_PROF();   // c: projection issued
         ptx::mbar_wait(b_y, ph_y); ph_y ^= 1;
-        if (img + ncl < p.B) {   // first head's weights of the next image
+        if (img + ncl < p.B) {   // next image: raw rows into the O region (the projection has read it), first head's weights
+          fetch_x(img + ncl);
           ptx::mbar_expect_tx(b_w, WH_BYTES);
           ptx::bulk_load_1d(sb + W_OFF, p.wpack, WH_BYTES, b_w);
         }
@@ -498,14 +517,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AT_THREADS, 1) attn_
         }
         AT_PROF();   // w: head done
       }
-      // ---- projection epilogue: y + bias + x -> bf16, staged in the idle K / V regions, then coalesced stores ---------
-      fetch_x(img, false);   // residual rows (the peer pushes nothing more for this image)
+      // ---- projection epilogue: y + bias + x -> bf16, in place in the staging rows (K-block layout, SWIZZLE_128B), then
+      // three TMA tensor stores (+ three for the wrapped halo row); border columns are written by their own threads -------
+      const int ty = gt >> 4, tx = gt & 15;
+      const long long wy = static_cast<long long>(halo_wrap16(ty)) * 18 * 192, wx = static_cast<long long>(halo_wrap16(tx)) * 192;
+      __nv_bfloat16* dcol = ob + static_cast<size_t>((ty + 1) * 18 + tx + 1) * 192 + 96 * hf;
       ptx::mbar_wait(b_y, ph_y); ph_y ^= 1;
       AT_PROF();   // w: Y ready
       ptx::tc_fence_after();
-      if (img + ncl < p.B) fetch_x(img + ncl, true); else cp_async_commit();   // Wproj consumed: prefetch the next image
-      cp_async_wait<1>();    // the residual rows (the group before the prefetch)
-      worker_bar();
+      ptx::mbar_wait(b_r, ph_r); ph_r ^= 1;
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
         float yv[32];
@@ -514,33 +534,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AT_THREADS, 1) attn_
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int ch = 12 * hf + 4 * i + j;   // 16-byte chunk of the 192-channel row
-          uint4* slot = reinterpret_cast<uint4*>(sm + R_OFF + row * 384 + ((ch ^ (row & 7)) << 4));
+          uint4* slot = reinterpret_cast<uint4*>(sm + R_OFF + (ch >> 3) * KBLK + sw128(row, ch & 7));
           float r[8], g8[8];
           unpack8(*slot, r);
 #pragma unroll
           for (int e = 0; e < 8; ++e) g8[e] = yv[8 * j + e] + s_bproj[ch * 8 + e] + r[e];
-          *slot = pack8(g8);
+          const uint4 u = pack8(g8);
+          *slot = u;
+          if (wx) {   // left / right border pixel: its copy on the opposite halo column (and the corner)
+            *reinterpret_cast<uint4*>(dcol + wx + (4 * i + j) * 8) = u;
+            if (wy) *reinterpret_cast<uint4*>(dcol + wx + wy + (4 * i + j) * 8) = u;
+          }
         }
       }
+      ptx::fence_proxy_async();
       ptx::tc_fence_before();
       worker_bar();
       AT_PROF();   // w: output rows staged
+      if (wt == 0) {
 #pragma unroll
-      for (int k = 0; k < 12; ++k) {   // staging rows -> padded global tensor, coalesced; border pixels also go to the opposite halo
-        const int i = wt + 256 * k, tok = i / 24, ch = i - tok * 24;
-        const uint4 u = *reinterpret_cast<const uint4*>(sm + R_OFF + tok * 384 + ((ch ^ (tok & 7)) << 4));
-        const int g_t = static_cast<int>(rank) * AT_TOK + tok, y = g_t >> 4, x = g_t & 15;
-        __nv_bfloat16* dst = ob + static_cast<size_t>((y + 1) * 18 + x + 1) * 192 + ch * 8;
-        const long long wy = static_cast<long long>(halo_wrap16(y)) * 18 * 192, wx = static_cast<long long>(halo_wrap16(x)) * 192;
-        *reinterpret_cast<uint4*>(dst) = u;
-        if (wy) *reinterpret_cast<uint4*>(dst + wy) = u;
-        if (wx) *reinterpret_cast<uint4*>(dst + wx) = u;
-        if (wy && wx) *reinterpret_cast<uint4*>(dst + wy + wx) = u;
+        for (int kb = 0; kb < 3; ++kb) {
+          const uint32_t src = sb + R_OFF + kb * KBLK;
+          tma_store_4d(&maps.out, src, kb * 64, 1, 1 + 8 * static_cast<int>(rank), img);
+          if (rank == 0) tma_store_4d(&maps.out_row, src, kb * 64, 1, 17, img);                 // image row 0 -> padded row 17
+          else tma_store_4d(&maps.out_row, src + 112 * 128, kb * 64, 1, 0, img);                // image row 15 -> padded row 0
+        }
+        ptx::bulk_commit();
       }
       AT_PROF();   // w: image written
     }
   }
 #undef AT_PROF
+  ptx::bulk_wait_all();
   ptx::tc_fence_before();
   cluster.sync();      // no remote arrive / push may target a CTA that has exited
   if (ctrl) ptx::tmem_dealloc_512(tmem);
@@ -591,7 +616,36 @@ int launch_attn_block_tc(const AttnTcParams& p, int sm_count, cudaStream_t st) {
   if (max_clusters > 0 && max_clusters < ncl) ncl = max_clusters;
   if (ncl > p.B) ncl = p.B;
   if (ncl < 1) ncl = 1;
-  attn_block_tc_kernel<<<2 * ncl, AT_THREADS, smem, st>>>(p);
+  typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static PFN_encodeTiled encode = nullptr;
+  if (!encode) {
+    void* fp = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) != cudaSuccess || !fp)
+      return fail(TCS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    encode = reinterpret_cast<PFN_encodeTiled>(fp);
+  }
+  AttnTcMaps maps;
+  {
+    const cuuint64_t dims[4] = {192, 18, 18, static_cast<cuuint64_t>(p.B)};
+    const cuuint64_t strides[3] = {384, 18 * 384, 18 * 18 * 384};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    const cuuint32_t box8[4] = {64, 16, 8, 1}, box1[4] = {64, 16, 1, 1};
+    auto mk = [&](CUtensorMap* m, const void* base, const cuuint32_t* box) {
+      return encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    };
+    if (mk(&maps.x, p.x, box8) != CUDA_SUCCESS || mk(&maps.out, p.out, box8) != CUDA_SUCCESS ||
+        mk(&maps.out_row, p.out, box1) != CUDA_SUCCESS)
+      return fail(TCS_ERR_CUDA, "attn_tc: cuTensorMapEncodeTiled failed");
+  }
+  AttnTcParams pp = p;
+  static const int stagger = getenv("TCS_ATTN_STAGGER") ? atoi(getenv("TCS_ATTN_STAGGER")) : 0;
+  pp.stagger = stagger;
+  attn_block_tc_kernel<<<2 * ncl, AT_THREADS, smem, st>>>(maps, pp);
   TCS_CUDA(cudaGetLastError());
   return TCS_OK;
 }

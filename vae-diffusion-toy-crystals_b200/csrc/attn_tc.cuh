@@ -13,6 +13,7 @@ struct AttnTcParams {
   const float* gamma;        // attn.norm.weight [192]
   const float* beta;         // attn.norm.bias [192]
   int B;
+  int stagger;               // cycles of start delay per (cluster index mod 16); 0 = none
   float* dbg;                // tests only (or null): intermediates of image 0, see ATTN_DBG_* offsets
 };
 
