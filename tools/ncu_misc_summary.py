@@ -19,6 +19,8 @@ KEYS = {"us": "gpu__time_duration.sum", "dram_read": "dram__bytes_read.sum", "dr
         "alu_pipe_pct": "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
         "lsu_pipe_pct": "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
         "dram_throughput_pct": "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "tensor_pipe_active_pct": "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+        "xu_pipe_pct": "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
         "regs": "launch__registers_per_thread", "grid": "launch__grid_size", "block": "launch__block_size"}
 
 

@@ -889,202 +889,11 @@ __global__ void __launch_bounds__(ATT_TOK) attention_kernel(const T* __restrict_
     ov.store(orow + d8);
   }
 }
-// ------------------------------------------------------------------------------------------
-// bf16 attention on the tensor cores (mma.sync m16n8k16, fp32 accumulate), flash-style:
-// block = (image, head), 8 warps x 32 query rows; K and V of the head live in shared memory
-// (112-byte rows: conflict-free ldmatrix); keys are consumed in chunks of 64 with an online
-// softmax in base 2.  The whole problem per block is 256 x 256 x 48, so nothing is tiled further.
-// ------------------------------------------------------------------------------------------
-constexpr int ATT_STRIDE = 56;  // bf16 elements per K/V row in shared memory (48 + 8 pad)
-
-__device__ __forceinline__ void mma_bf16_16816(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t* r) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x2(uint32_t addr, uint32_t* r) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t* r) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-__device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
-  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<const uint32_t*>(&h);
-}
-
-// MT = 16-row query tiles per warp.  MT = 1 (a block = one HALF of the queries of an (image, head), grid doubled) keeps the
-// kernel near 100 registers so that two blocks share an SM and hide each other's latencies; MT = 2 was 178 registers, 1 block.
-constexpr int ATT_MT = 1;
-__global__ void __launch_bounds__(256, 2) attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv,
-                                                           __nv_bfloat16* __restrict__ yout) {
-  extern __shared__ __align__(16) uint8_t att_raw[];
-  __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(att_raw);
-  __nv_bfloat16* Vs = Ks + ATT_TOK * ATT_STRIDE;
-  constexpr int MT = ATT_MT, QPB = 8 * 16 * MT;          // queries per block
-  constexpr int BPH = ATT_TOK / QPB;                      // blocks per (image, head)
-  const int bh = blockIdx.x / BPH, qpart = blockIdx.x - bh * BPH;
-  const int b = bh >> 2, head = bh & 3;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
-  const __nv_bfloat16* base = qkv + static_cast<size_t>(b) * ATT_TOK * (3 * ATT_C) + head * ATT_D;
-  // K and V of the four 64-key chunks arrive as four cp.async groups, so the first chunk's MMAs start while the
-  // other three are still in flight (the plain load + barrier kept the block idle for a whole L2/HBM round trip)
-  {
-    const uint32_t ks_sh = static_cast<uint32_t>(__cvta_generic_to_shared(Ks)), vs_sh = static_cast<uint32_t>(__cvta_generic_to_shared(Vs));
-#pragma unroll
-    for (int cch = 0; cch < ATT_TOK / 64; ++cch) {
-      for (int e = tid; e < 64 * 6; e += 256) {
-        const int tok = cch * 64 + e / 6, ch = e % 6;
-        const __nv_bfloat16* src = base + static_cast<size_t>(tok) * (3 * ATT_C) + ATT_C + ch * 8;
-        const uint32_t off = static_cast<uint32_t>((tok * ATT_STRIDE + ch * 8) * 2);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ks_sh + off), "l"(src) : "memory");
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(vs_sh + off), "l"(src + ATT_C) : "memory");
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    }
-  }
-  // Q fragments: 2 m-tiles x 3 k-steps, straight from global memory
-  uint32_t qf[MT][3][4];
-  const int row0 = qpart * QPB + warp * 16 * MT;
-#pragma unroll
-  for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-    for (int ks = 0; ks < 3; ++ks) {
-      const __nv_bfloat16* q0 = base + static_cast<size_t>(row0 + mt * 16 + g) * (3 * ATT_C) + ks * 16 + 2 * t4;
-      const __nv_bfloat16* q1 = q0 + 8 * (3 * ATT_C);
-      qf[mt][ks][0] = *reinterpret_cast<const uint32_t*>(q0);
-      qf[mt][ks][1] = *reinterpret_cast<const uint32_t*>(q1);
-      qf[mt][ks][2] = *reinterpret_cast<const uint32_t*>(q0 + 8);
-      qf[mt][ks][3] = *reinterpret_cast<const uint32_t*>(q1 + 8);
-    }
-  const uint32_t ks_addr = static_cast<uint32_t>(__cvta_generic_to_shared(Ks));
-  const uint32_t vs_addr = static_cast<uint32_t>(__cvta_generic_to_shared(Vs));
-  const float c = 0.14433756729740643f * 1.4426950408889634f;  // (1/sqrt(48)) * log2(e)
-  float o[MT][6][4];
-  float mrow[MT][2], lrow[MT][2];
-#pragma unroll
-  for (int mt = 0; mt < MT; ++mt) {
-    mrow[mt][0] = mrow[mt][1] = -INFINITY;
-    lrow[mt][0] = lrow[mt][1] = 0.f;
-#pragma unroll
-    for (int nt = 0; nt < 6; ++nt)
-#pragma unroll
-      for (int k = 0; k < 4; ++k) o[mt][nt][k] = 0.f;
-  }
-  for (int kc = 0; kc < ATT_TOK; kc += 64) {
-    if (kc == 0) asm volatile("cp.async.wait_group 3;" ::: "memory");
-    else if (kc == 64) asm volatile("cp.async.wait_group 2;" ::: "memory");
-    else if (kc == 128) asm volatile("cp.async.wait_group 1;" ::: "memory");
-    else asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();        // every thread's copies of this chunk are in shared memory
-    float sacc[MT][8][4];
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) sacc[mt][nt][k] = 0.f;
-    // ---- S = Q K^T for 64 keys ------------------------------------------------------------------
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      uint32_t kb[6];
-      const uint32_t rowaddr = ks_addr + static_cast<uint32_t>((kc + nt * 8 + (lane & 7)) * ATT_STRIDE * 2);
-      ldsm_x4(rowaddr + (lane >> 3) * 16, kb);             // d chunks 0..3 -> (b0,b1) of k-steps 0,1
-      ldsm_x2(rowaddr + (4 + ((lane >> 3) & 1)) * 16, kb + 4);  // d chunks 4,5 -> k-step 2
-#pragma unroll
-      for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-        for (int ks = 0; ks < 3; ++ks) mma_bf16_16816(sacc[mt][nt], qf[mt][ks], kb[2 * ks], kb[2 * ks + 1]);
-    }
-    // ---- online softmax (base 2) --------------------------------------------------------------------
-    uint32_t pf[MT][4][4];
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt) {
-      float mx0 = mrow[mt][0], mx1 = mrow[mt][1];
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        mx0 = fmaxf(mx0, fmaxf(sacc[mt][nt][0], sacc[mt][nt][1]));
-        mx1 = fmaxf(mx1, fmaxf(sacc[mt][nt][2], sacc[mt][nt][3]));
-      }
-      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-      const float corr0 = exp2f((mrow[mt][0] - mx0) * c), corr1 = exp2f((mrow[mt][1] - mx1) * c);
-      mrow[mt][0] = mx0; mrow[mt][1] = mx1;
-      const float off0 = mx0 * c, off1 = mx1 * c;
-      float ps0 = 0.f, ps1 = 0.f;
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        const float p0 = exp2f(fmaf(sacc[mt][nt][0], c, -off0)), p1 = exp2f(fmaf(sacc[mt][nt][1], c, -off0));
-        const float p2 = exp2f(fmaf(sacc[mt][nt][2], c, -off1)), p3 = exp2f(fmaf(sacc[mt][nt][3], c, -off1));
-        ps0 += p0 + p1; ps1 += p2 + p3;
-        pf[mt][nt >> 1][(nt & 1) * 2] = pack2_bf16(p0, p1);
-        pf[mt][nt >> 1][(nt & 1) * 2 + 1] = pack2_bf16(p2, p3);
-      }
-      lrow[mt][0] = lrow[mt][0] * corr0 + ps0;
-      lrow[mt][1] = lrow[mt][1] * corr1 + ps1;
-#pragma unroll
-      for (int nt = 0; nt < 6; ++nt) {
-        o[mt][nt][0] *= corr0; o[mt][nt][1] *= corr0;
-        o[mt][nt][2] *= corr1; o[mt][nt][3] *= corr1;
-      }
-    }
-    // ---- O += P V ---------------------------------------------------------------------------------------
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {      // 16 keys per k-step
-#pragma unroll
-      for (int np = 0; np < 3; ++np) {    // pairs of d-tiles
-        uint32_t vb[4];
-        const int key = kc + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-        ldsm_x4_trans(vs_addr + static_cast<uint32_t>(key * ATT_STRIDE * 2 + (np * 2 + (lane >> 4)) * 16), vb);
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          mma_bf16_16816(o[mt][np * 2], pf[mt][kk], vb[0], vb[1]);
-          mma_bf16_16816(o[mt][np * 2 + 1], pf[mt][kk], vb[2], vb[3]);
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int mt = 0; mt < MT; ++mt) {
-    float l0 = lrow[mt][0], l1 = lrow[mt][1];
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
-    __nv_bfloat16* y0 = yout + (static_cast<size_t>(b) * ATT_TOK + row0 + mt * 16 + g) * ATT_C + head * ATT_D + 2 * t4;
-    __nv_bfloat16* y1 = y0 + 8 * ATT_C;
-#pragma unroll
-    for (int nt = 0; nt < 6; ++nt) {
-      *reinterpret_cast<uint32_t*>(y0 + nt * 8) = pack2_bf16(o[mt][nt][0] * i0, o[mt][nt][1] * i0);
-      *reinterpret_cast<uint32_t*>(y1 + nt * 8) = pack2_bf16(o[mt][nt][2] * i1, o[mt][nt][3] * i1);
-    }
-  }
-}
-
-int launch_attention_mma(const __nv_bfloat16* qkv, int B, __nv_bfloat16* y, cudaStream_t st) {
-  if (B <= 0) return TCS_OK;
-  const size_t smem = 2 * ATT_TOK * ATT_STRIDE * sizeof(__nv_bfloat16);
-  static bool done = false;
-  if (!done) {
-    TCS_CUDA(cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    done = true;
-  }
-  attention_mma_kernel<<<B * N_HEADS * (ATT_TOK / (128 * ATT_MT)), 256, smem, st>>>(qkv, y);
-  TCS_CUDA(cudaGetLastError());
-  return TCS_OK;
-}
-
+// (The bf16 mma.sync version of this kernel is gone: the tcgen05 engine runs the whole attention block in attn_tc.cu;
+// this CUDA-core kernel serves the fp32 mode, the CUDA-core cross-check engine and the attn.qkv / attn.y debug taps.)
 template <typename T>
 int launch_attention(const T* qkv, int B, T* y, cudaStream_t st) {
   if (B <= 0) return TCS_OK;
-  if constexpr (sizeof(T) == 2) {
-    static const bool simt = getenv("TCS_ATT_SIMT") && atoi(getenv("TCS_ATT_SIMT")) == 1;
-    if (!simt) return launch_attention_mma(qkv, B, y, st);
-  }
   const size_t smem = 2 * ATT_TOK * ATT_D * sizeof(float);
   static bool done = false;
   if (!done) {
