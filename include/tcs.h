@@ -174,6 +174,12 @@ int tcs_debug_conv(int32_t engine, int32_t precision, int32_t B, int32_t H_out, 
                    int32_t cin1, int32_t cout, int32_t ksize, int32_t stride, const float* in0, const float* in1,
                    const float* weight, const float* bias, float* out, float* stats, int32_t epi, void* stream);
 
+/* us1_conv / us2_conv with the bilinear x2 upsample fused into the conv (tcgen05 engine, bf16): in_lowres is fp32 NHWC
+ * [B, H_out/2, W_out/2, cin]; out = conv3x3_circular(upsample_bilinear_x2(in_lowres)) + bias, fp32 NHWC [B,H_out,W_out,cout]
+ * (nn.Upsample + nn.Conv2d(padding_mode="circular"), sde_score_model.py:217-222,256-262).  Synchronous. */
+int tcs_debug_conv_ups(int32_t B, int32_t H_out, int32_t W_out, int32_t cin, int32_t cout, const float* in_lowres,
+                       const float* weight, const float* bias, float* out, void* stream);
+
 /* Run the fused attention block (csrc/attn_tc.cu: GroupNorm -> qkv -> softmax(q k^T / sqrt(48)) v -> proj -> + x,
  * SelfAttention2d.forward, sde_score_model.py:136-167) in isolation, bf16 / tcgen05.  Device fp32 pointers:
  *   x, out  : NHWC [B,16,16,192];  gn_w, gn_b [192];  qkv_w [576,192], qkv_b [576];  proj_w [192,192], proj_b [192]

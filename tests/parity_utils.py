@@ -118,6 +118,19 @@ def attn_block_reference(x, gn_w, gn_b, qkv_w, qkv_b, proj_w, proj_b):
     return out.permute(0, 2, 3, 1).contiguous(), {"xn": to_tok(xn), "qkv": to_tok(qkv), "y": to_tok(y)}
 
 
+def debug_conv_ups(in_lo, w, b):
+    """conv3x3_circular(bilinear x2 (in_lo)) with the upsample fused into the tcgen05 conv.  in_lo NHWC fp32 CUDA."""
+    L = _cabi.lib()
+    B, h, wd, cin = in_lo.shape
+    cout = w.shape[0]
+    out = torch.full((B, 2 * h, 2 * wd, cout), float("nan"), device="cuda")
+    torch.cuda.synchronize()
+    _cabi.check(L.tcs_debug_conv_ups(B, 2 * h, 2 * wd, cin, cout, in_lo.contiguous().data_ptr(), w.contiguous().data_ptr(),
+                                     b.data_ptr(), out.data_ptr(), None))
+    torch.cuda.synchronize()
+    return out
+
+
 def debug_layer(m: CondUNetTiny, name, x, t, y_cat, y_cont, C_out, res):
     h = m.engine_handle()
     n = x.shape[0]

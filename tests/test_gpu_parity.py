@@ -52,6 +52,30 @@ def test_conv_layer(case, precision, engine):
             assert pu.rel_l2(stats, want) < 1e-4, (case, precision, engine, "stats")
 
 
+# ---- us1_conv / us2_conv with the bilinear x2 upsample fused into the conv's operand path ----------------------------
+@pytest.mark.parametrize("case", [(96, 96, 32), (192, 192, 16)])   # (cin, cout, low resolution): us1_conv, us2_conv
+def test_conv_with_fused_upsample(case):
+    """nn.Upsample(scale_factor=2, mode="bilinear") + 3x3 circular conv (sde_score_model.py:217-222): the upsample clamps
+    at the image edge, the conv wraps around it; B = 5 images x every tile position covers all border cases."""
+    pu = _pu()
+    cin, cout, lo = case
+    g = torch.Generator().manual_seed(cin + lo)
+    B = 5
+    x = torch.randn((B, lo, lo, cin), generator=g).bfloat16().float()
+    w = (torch.randn((cout, cin, 3, 3), generator=g) / math.sqrt(cin * 9)).bfloat16().float()
+    b = torch.randn((cout,), generator=g)
+    up = torch.nn.functional.interpolate(x.permute(0, 3, 1, 2).double(), scale_factor=2, mode="bilinear", align_corners=False)
+    up16 = up.float().bfloat16().double()      # the stand-alone kernel rounded the upsampled tensor to bf16; so does the fused path
+    want = pu.conv_reference(up16.permute(0, 2, 3, 1).float(), None, w, b, 3, 1)
+    got = pu.debug_conv_ups(x.cuda(), w.cuda(), b.cuda())
+    err = pu.rel_l2(got.cpu(), want)
+    # rows / columns next to the image edge separately: that is where clamp (upsample) and wrap (conv) meet
+    ring = torch.ones(2 * lo, 2 * lo, dtype=torch.bool); ring[2:-2, 2:-2] = False
+    err_ring = pu.rel_l2(got.cpu()[:, ring], want[:, ring])
+    print(f"fused upsample {case}: rel-L2 {err:.2e}, border ring {err_ring:.2e}")
+    assert err < 6e-3 and err_ring < 6e-3, (case, err, err_ring)
+
+
 # ---- the fused attention block (attn_tc.cu) in isolation -------------------------------------------------------
 @pytest.mark.parametrize("B", [1, 3, 150])
 def test_fused_attention_block(B):

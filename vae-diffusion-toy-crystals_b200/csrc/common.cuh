@@ -59,6 +59,8 @@ struct ConvGeom {
   int ntot;       // total output channels
   int split3 = 0;  // fp32 mode on the tensor pipe: operands as bf16 (hi, lo) pairs, a*w ~= a_hi*w_hi + a_hi*w_lo + a_lo*w_hi
                    // accumulated in fp32 (the dropped a_lo*w_lo term and the representation error are ~2^-17 relative)
+  int ups = 0;     // tcgen05 engine, 3x3 stride-1 layers with a padded bf16 output: the source is the HALF-resolution padded
+                   // tensor [B, H/2+2, W/2+2, C] and the bilinear x2 upsample (edge clamp) is blended on the way into shared memory
   int kx_in_n = 0; // 96 -> 1 output conv only: the three kx taps are three GEMM columns sharing ONE (unshifted) window per
                    // channel block; the epilogue sums column kx of pixel x + kx - 1 (circular in x)
 };

@@ -40,6 +40,9 @@ constexpr int GRP_WARPS = EPI_WARPS / 2;
 constexpr int UC = 96;                 // accumulator columns per epilogue warp (4 lane quarters x 2 column units cover 192)
 constexpr int BLK = 32;                // channels per staged output block (three blocks per warp and tile)
 constexpr int TC_THREADS = 64 + 32 * EPI_WARPS + 32;   // + a second MMA-issuing warp for the MSUB = 2 tiles
+// UPS kernels: warps 19..22 blend the upsampled windows (two more padding warps, so that none of them shares a scheduler
+// with the MMA-issuing warps 1 and 18, cost more than they gain: 800 threads leave 72 registers per thread)
+constexpr int UPS_EXTRA_THREADS = 4 * 32;
 constexpr int MAX_STAGES = 12;
 constexpr int MAX_A_STAGES = 4;
 // K block of a pipeline stage: 64 input channels = one 128-byte row per pixel / per output channel (SWIZZLE_128B).
@@ -230,6 +233,8 @@ struct __align__(8) TcBarriers {
   uint64_t empty[MAX_STAGES];
   uint64_t fullA[MAX_A_STAGES];    // geo 1: the window ring
   uint64_t emptyA[MAX_A_STAGES];
+  uint64_t fullL[2];               // UPS: the low-resolution window ring
+  uint64_t emptyL[2];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
@@ -249,13 +254,20 @@ struct __align__(8) TcBarriers {
 // GEO = 0 fetched a full-width window per kx (each input pixel 4.5 x per tile); GEO = 1 fetches it 1.27 x (MSUB = 2),
 // which halves the L2 -> SM operand stream that bounded the 64x64 layers (no-TMA experiment: +39 %).  The windows have
 // their own ring (fullA / emptyA); the weights stream through the stage ring in stages of p.tb taps.
-template <int N, int EPI, int MSUB, int CG, int GEO>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// UPS = 1 (us1_conv / us2_conv): the source is the HALF-resolution padded tensor and nn.Upsample(scale_factor=2,
+// mode="bilinear") (sde_score_model.py:217,221) happens on the way into shared memory: the TMA producer loads the
+// (8 + 2) x (4 MSUB + 2) low-resolution window of a 64-channel block into a ring of its own, four extra warps
+// (19..22) blend it into the (16 + 2) x (8 MSUB + 2) tap-shift window (edge clamp of the upsample, circular wrap of the
+// conv: the first / last window rows and columns of border tiles are plain copies) and arrive on the window's barrier.
+// The upsampled tensor never exists in memory (it was 4x the size of the input, written and read back once per pass).
+template <int N, int EPI, int MSUB, int CG, int GEO, int UPS = 0>
+__global__ void __launch_bounds__(TC_THREADS + UPS_EXTRA_THREADS * UPS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
                const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapO,
                const __grid_constant__ CUtensorMap mapO1, const ConvTcParams p) {
   static_assert(GEO == 0 || (EPI != EPI_EPS && EPI != EPI_PLAIN), "tap-shift geometry: padded / fp32 outputs only");
+  static_assert(UPS == 0 || (GEO == 1 && CG == 2 && EPI == EPI_PADDED), "fused upsample: tap-shift CTA pairs, padded output");
   constexpr int ACC_STRIDE = (N * MSUB <= 128) ? 128 : 256;  // TMEM columns per accumulator stage
   static_assert(N * MSUB <= 256, "accumulator does not fit a double-buffered TMEM stage");
 
@@ -268,13 +280,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   const int n_tiles = p.n_mtiles * p.n_ntiles;
   // after the operand ring: 16 epilogue warps x 2 x 2 KB staging blocks (fp16 stash of the fused epilogue, TMA-store
   // source of every bf16 output), then the bias
-  const uint32_t b_ring = smem_base + (GEO == 1 ? p.a_stages * p.a_bytes : 0u);   // geo 1: windows first, then weight stages
+  const uint32_t l_ring = smem_base + (GEO == 1 ? p.a_stages * p.a_bytes : 0u);   // UPS: low-resolution windows after the window ring
+  const uint32_t b_ring = l_ring + (UPS ? p.l_stages * p.l_bytes : 0u);           // geo 1: windows first, then weight stages
   const uint32_t slab_base = b_ring + p.nstage * p.stage_bytes;
   float* bias_s = reinterpret_cast<float*>(smem_raw + (slab_base - ptx::smem_u32(smem_raw)) + EPI_SLAB_BYTES);
-  for (int i = threadIdx.x; i < p.ntot; i += TC_THREADS) bias_s[i] = p.epi.bias[i];
+  for (int i = threadIdx.x; i < p.ntot; i += blockDim.x) bias_s[i] = p.epi.bias[i];
   EpiFusedSmem* fs = reinterpret_cast<EpiFusedSmem*>(reinterpret_cast<uint8_t*>(bias_s) + (GEO == 1 ? bias_bytes_of(p.ntot) : EPI_BIAS_BYTES));
   if constexpr (EPI == EPI_GN_FUSED)
-    for (int i = threadIdx.x; i < N; i += TC_THREADS) { fs->gamma[i] = p.epi.gamma[i]; fs->beta[i] = p.epi.beta[i]; }
+    for (int i = threadIdx.x; i < N; i += blockDim.x) { fs->gamma[i] = p.epi.gamma[i]; fs->beta[i] = p.epi.beta[i]; }
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&mapA0);
@@ -289,8 +302,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     }
     if (GEO == 1)
       for (int s = 0; s < p.a_stages; ++s) {
-        ptx::mbar_init(ptx::smem_u32(&bars.fullA[s]), 1);
+        ptx::mbar_init(ptx::smem_u32(&bars.fullA[s]), UPS ? 4 * CG : 1);   // UPS: one arrival per blending warp of the pair
         ptx::mbar_init(ptx::smem_u32(&bars.emptyA[s]), p.issuers);
+      }
+    if (UPS)
+      for (int s = 0; s < p.l_stages; ++s) {
+        ptx::mbar_init(ptx::smem_u32(&bars.fullL[s]), 1);
+        ptx::mbar_init(ptx::smem_u32(&bars.emptyL[s]), 4);
       }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(ptx::smem_u32(&bars.tmem_full[a]), p.issuers);
@@ -325,6 +343,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int ms = p.msel[src];
         const CUtensorMap* mapA = ms == 0 ? &mapA0 : (ms == 1 ? &mapA1 : (ms == 2 ? &mapA2 : &mapA3));
         for (int cb = 0; cb < p.cblk[src]; ++cb) {
+          if constexpr (UPS) {   // low-resolution window -> its own ring (this CTA's barrier); warps 19..22 fill the A ring
+            ptx::mbar_wait(ptx::smem_u32(&bars.emptyL[sa]), pa ^ 1);
+            if (lane == 0) {
+              const uint32_t full = ptx::smem_u32(&bars.fullL[sa]);
+              ptx::mbar_expect_tx(full, p.l_load_bytes);
+              ptx::tma_load_4d(l_ring + sa * p.l_bytes, mapA, full, cb * KB, tx * 4 * MSUB + p.base_off[src], ty * 8 + p.base_off[src], b);
+            }
+            __syncwarp();
+            if (++sa == static_cast<uint32_t>(p.l_stages)) { sa = 0; pa ^= 1; }
+          } else {
           ptx::mbar_wait(ptx::smem_u32(&bars.emptyA[sa]), pa ^ 1);
           const bool stale = (p.debug & 8) && (pa || tile != static_cast<int>(blockIdx.x));   // experiment: no TMA
           if (lane == 0) {
@@ -342,6 +370,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           }
           __syncwarp();
           if (++sa == static_cast<uint32_t>(p.a_stages)) { sa = 0; pa ^= 1; }
+          }
           for (int kx = 0; kx < 3; ++kx, ++ks)
             for (int jb = 0; jb < b_stages_per_kx; ++jb) {
               ptx::mbar_wait(ptx::smem_u32(&bars.empty[sb]), pb ^ 1);
@@ -447,7 +476,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           for (int src = 0; src < p.nsrc; ++src)
             for (int cb = 0; cb < p.cblk[src]; ++cb, ++blk) {
               const int ksteps = (cb == p.cblk[src] - 1 && p.ctail[src]) ? 2 : 4;
-              ptx::mbar_wait(ptx::smem_u32(&bars.fullA[sa]), pa);
+              if (UPS) ptx::mbar_wait_cluster(ptx::smem_u32(&bars.fullA[sa]), pa);   // the peer's blending warps wrote its window
+              else ptx::mbar_wait(ptx::smem_u32(&bars.fullA[sa]), pa);
               const uint64_t adesc = make_desc_sw128_sbo(smem_base + sa * p.a_bytes, static_cast<uint32_t>(p.P) * ROWB) +
                                      static_cast<uint64_t>(SUB_LO * 8 * (ROWB >> 4));
               for (int kx = 0; kx < 3; ++kx)
@@ -599,6 +629,88 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     } else {
       run(I0{}, IM{});
     }
+    }
+  } else if (UPS && warp >= 3 + EPI_WARPS) {
+    // ============================== bilinear x2 into the window ring (UPS) ==============
+    // thread = (16-byte channel chunk k, cell slot); a CELL is the 2 x 2 block of window pixels (2 cm + {0,1}, 2 cn + {0,1})
+    // that blends the same four low-resolution pixels (cm + {0,1}, cn + {0,1}): rows / columns 2c and 2c + 1 weigh them
+    // (3/4, 1/4) and (1/4, 3/4).  On a border tile the outermost cell row / column straddles the image edge: there the
+    // upsample clamps and the conv wraps, and both are plain copies (weights (1, 0) and (0, 1)) because the low-resolution
+    // halo already holds the wrapped pixel.  fp32 math, one rounding to bf16 (as the stand-alone upsample kernel did).
+    if constexpr (UPS) {
+      constexpr int P = 8 * MSUB + 2, CW = P / 2, LP = CW + 1;
+      const int t128 = (warp - (3 + EPI_WARPS)) * 32 + lane;
+      uint32_t sa = 0, pa = 0, sl = 0, pl = 0;
+      // blend one cell (packed fp32x2 math: t = a + w (b - a), so that w = 0 / 1 copy a / b): chunk k of cell (cm, cn)
+      auto blend_cell = [&](uint32_t lbase, uint32_t abase, uint32_t k, int cm, int cn, float wy0, float wy1, float wx0, float wx1) {
+        const uint32_t pA = cm * LP + cn, pB = pA + 1, pC = pA + LP, pD = pC + 1;
+        uint32_t a[4], bq[4], c[4], d[4];
+        ld_shared_u4(lbase + pA * 128 + ((k ^ (pA & 7)) << 4), a[0], a[1], a[2], a[3]);
+        ld_shared_u4(lbase + pB * 128 + ((k ^ (pB & 7)) << 4), bq[0], bq[1], bq[2], bq[3]);
+        ld_shared_u4(lbase + pC * 128 + ((k ^ (pC & 7)) << 4), c[0], c[1], c[2], c[3]);
+        ld_shared_u4(lbase + pD * 128 + ((k ^ (pD & 7)) << 4), d[0], d[1], d[2], d[3]);
+        uint32_t o00[4], o01[4], o10[4], o11[4];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const float al = __uint_as_float(a[w] << 16), ah = __uint_as_float(a[w] & 0xffff0000u);
+          const float bl = __uint_as_float(bq[w] << 16), bh = __uint_as_float(bq[w] & 0xffff0000u);
+          const float cl = __uint_as_float(c[w] << 16), ch = __uint_as_float(c[w] & 0xffff0000u);
+          const float dl = __uint_as_float(d[w] << 16), dh = __uint_as_float(d[w] & 0xffff0000u);
+          float el, eh, fl, fh, t0l, t0h, t1l, t1h, u0l, u0h, u1l, u1h, gl, gh, hl, hh, r0, r1;
+          add2(el, eh, bl, bh, -al, -ah);                       // b - a   (upper low-resolution row)
+          add2(fl, fh, dl, dh, -cl, -ch);                       // d - c   (lower row)
+          fma2(t0l, t0h, wx0, wx0, el, eh, al, ah);             // window column 2 cn
+          fma2(t1l, t1h, wx1, wx1, el, eh, al, ah);             // window column 2 cn + 1
+          fma2(u0l, u0h, wx0, wx0, fl, fh, cl, ch);
+          fma2(u1l, u1h, wx1, wx1, fl, fh, cl, ch);
+          add2(gl, gh, u0l, u0h, -t0l, -t0h);
+          add2(hl, hh, u1l, u1h, -t1l, -t1h);
+          fma2(r0, r1, wy0, wy0, gl, gh, t0l, t0h); o00[w] = pack_bf16x2(r0, r1);
+          fma2(r0, r1, wy0, wy0, hl, hh, t1l, t1h); o01[w] = pack_bf16x2(r0, r1);
+          fma2(r0, r1, wy1, wy1, gl, gh, t0l, t0h); o10[w] = pack_bf16x2(r0, r1);
+          fma2(r0, r1, wy1, wy1, hl, hh, t1l, t1h); o11[w] = pack_bf16x2(r0, r1);
+        }
+        const uint32_t q00 = (2 * cm) * P + 2 * cn, q01 = q00 + 1, q10 = q00 + P, q11 = q10 + 1;
+        st_shared_u4(abase + q00 * 128 + ((k ^ (q00 & 7)) << 4), o00[0], o00[1], o00[2], o00[3]);
+        st_shared_u4(abase + q01 * 128 + ((k ^ (q01 & 7)) << 4), o01[0], o01[1], o01[2], o01[3]);
+        st_shared_u4(abase + q10 * 128 + ((k ^ (q10 & 7)) << 4), o10[0], o10[1], o10[2], o10[3]);
+        st_shared_u4(abase + q11 * 128 + ((k ^ (q11 & 7)) << 4), o11[0], o11[1], o11[2], o11[3]);
+      };
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int mt, nt;
+        tile_to_mn<CG>(tile, p.n_ntiles, mt, nt);
+        const int t = mt % p.tiles_per_img;
+        const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
+        // weight of the SECOND low-resolution row / column for window rows / columns (2 c, 2 c + 1): (1/4, 3/4); on the
+        // image edge (first / last cell of a border tile) the pair is a plain copy of (first, second): (0, 1)
+        const int edge_r0 = ty == 0 ? 0 : -1, edge_r1 = ty == p.H / 16 - 1 ? 8 : -1;
+        const int edge_c0 = tx == 0 ? 0 : -1, edge_c1 = tx == p.tiles_x - 1 ? CW - 1 : -1;
+        for (int src = 0; src < p.nsrc; ++src)
+          for (int cb = 0; cb < p.cblk[src]; ++cb) {
+            const bool tail = cb == p.cblk[src] - 1 && p.ctail[src];   // 32 real channels: chunks 0..3 only
+            ptx::mbar_wait_sleep(ptx::smem_u32(&bars.fullL[sl]), pl);         // (polls with a back-off: these warps have slack,
+            ptx::mbar_wait_sleep(ptx::smem_u32(&bars.emptyA[sa]), pa ^ 1);    //  the issue slots belong to the epilogue warps)
+            const uint32_t lbase = l_ring + sl * p.l_bytes, abase = smem_base + sa * p.a_bytes;
+            if (!(p.debug & 64)) {   // (debug bit 64, timing experiments only: windows left stale)
+              // thread = (16-byte channel chunk, cell slot): 8 chunks x 16 slots, or 4 chunks x 32 slots for a half block
+              const uint32_t k = tail ? (t128 & 3) : (t128 & 7);
+              const int slot = tail ? (t128 >> 2) : (t128 >> 3), nslot = tail ? 32 : 16;
+              for (int ci = slot; ci < 9 * CW; ci += nslot) {
+                const int cm = ci / CW, cn = ci - cm * CW;
+                const bool ey = cm == edge_r0 || cm == edge_r1, ex = cn == edge_c0 || cn == edge_c1;
+                blend_cell(lbase, abase, k, cm, cn, ey ? 0.f : 0.25f, ey ? 1.f : 0.75f, ex ? 0.f : 0.25f, ex ? 1.f : 0.75f);
+              }
+            }
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              ptx::mbar_arrive(ptx::smem_u32(&bars.emptyL[sl]));
+              ptx::mbar_arrive_release_rank0(ptx::smem_u32(&bars.fullA[sa]));   // the LEADER's barrier (its MMAs read both windows)
+            }
+            if (++sl == static_cast<uint32_t>(p.l_stages)) { sl = 0; pl ^= 1; }
+            if (++sa == static_cast<uint32_t>(p.a_stages)) { sa = 0; pa ^= 1; }
+          }
+      }
     }
   } else if (warp >= 2 && warp < 2 + EPI_WARPS) {
     // ============================== epilogue (2 groups x 8 warps) ================
@@ -1223,11 +1335,11 @@ static int conv_tc_geo(const ConvGeom& g, int epi) {
   return (g.ksize == 3 && g.stride == 1 && !g.kx_in_n && epi != EPI_EPS && epi != EPI_PLAIN && g.H % 16 == 0) ? 1 : 0;
 }
 
-template <int N, int EPI, int MSUB, int CG, int GEO>
+template <int N, int EPI, int MSUB, int CG, int GEO, int UPS = 0>
 static int set_smem_attr() {
   static bool attr_done = false;
   if (!attr_done) {
-    TCS_CUDA(cudaFuncSetAttribute(conv_tc_kernel<N, EPI, MSUB, CG, GEO>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(TC_SMEM_MAX)));
+    TCS_CUDA(cudaFuncSetAttribute(conv_tc_kernel<N, EPI, MSUB, CG, GEO, UPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(TC_SMEM_MAX)));
     attr_done = true;
   }
   return TCS_OK;
@@ -1235,13 +1347,13 @@ static int set_smem_attr() {
 
 // CTAs of this kernel instance the device can hold at the same time (1 CTA per SM by shared memory; with CTA pairs,
 // whole clusters only: on a partitioned or partly occupied device fewer pairs fit than SMs / 2)
-template <int N, int EPI, int MSUB, int CG, int GEO>
+template <int N, int EPI, int MSUB, int CG, int GEO, int UPS = 0>
 static int max_ctas_t(const ConvTcPlan& pl, int* out) {
-  TCS_CHECK((set_smem_attr<N, EPI, MSUB, CG, GEO>()));
-  auto kern = conv_tc_kernel<N, EPI, MSUB, CG, GEO>;
+  TCS_CHECK((set_smem_attr<N, EPI, MSUB, CG, GEO, UPS>()));
+  auto kern = conv_tc_kernel<N, EPI, MSUB, CG, GEO, UPS>;
   if (CG == 2) {
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(2); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = pl.smem; cfg.stream = nullptr;
+    cfg.gridDim = dim3(2); cfg.blockDim = dim3(TC_THREADS + UPS_EXTRA_THREADS * UPS); cfg.dynamicSmemBytes = pl.smem; cfg.stream = nullptr;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -1259,14 +1371,14 @@ static int max_ctas_t(const ConvTcPlan& pl, int* out) {
   return TCS_OK;
 }
 
-template <int N, int EPI, int MSUB, int CG, int GEO>
+template <int N, int EPI, int MSUB, int CG, int GEO, int UPS = 0>
 static int launch_t(const ConvTcPlan& pl, cudaStream_t st) {
-  auto kern = conv_tc_kernel<N, EPI, MSUB, CG, GEO>;
-  TCS_CHECK((set_smem_attr<N, EPI, MSUB, CG, GEO>()));
+  auto kern = conv_tc_kernel<N, EPI, MSUB, CG, GEO, UPS>;
+  TCS_CHECK((set_smem_attr<N, EPI, MSUB, CG, GEO, UPS>()));
   if (EPI == EPI_GN_FUSED)   // the CTAs of an image group exchange (value, flag) words: flag 0 = not written yet
     TCS_CUDA(cudaMemsetAsync(pl.p.epi.partials, 0, sizeof(unsigned long long) * 16 * pl.p.n_mtiles, st));
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(pl.grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = pl.smem; cfg.stream = st;
+  cfg.gridDim = dim3(pl.grid); cfg.blockDim = dim3(TC_THREADS + UPS_EXTRA_THREADS * UPS); cfg.dynamicSmemBytes = pl.smem; cfg.stream = st;
   cudaLaunchAttribute at[2];
   int na = 0;
   // the CTAs of an image group poll each other's partial sums: the whole grid must be co-resident.  The cooperative
@@ -1295,7 +1407,9 @@ static int conv_tc_max_ctas(const ConvTcPlan& pl, int* out) {
     else return max_ctas_t<NN, EE, MM, 1, 0>(pl, out);                                  \
   }
 #define TCS_TC_GEO1(NN, EE, MM)                                                        \
-  if (pl.geo == 1 && pl.cg == 2 && pl.N == NN && pl.epi == EE && pl.msub == MM) return max_ctas_t<NN, EE, MM, 2, 1>(pl, out);
+  if (pl.geo == 1 && pl.cg == 2 && !pl.ups && pl.N == NN && pl.epi == EE && pl.msub == MM) return max_ctas_t<NN, EE, MM, 2, 1>(pl, out);
+  if (pl.geo == 1 && pl.cg == 2 && pl.ups && pl.epi == EPI_PADDED && pl.N == 96 && pl.msub == 2) return max_ctas_t<96, EPI_PADDED, 2, 2, 1, 1>(pl, out);
+  if (pl.geo == 1 && pl.cg == 2 && pl.ups && pl.epi == EPI_PADDED && pl.N == 192 && pl.msub == 1) return max_ctas_t<192, EPI_PADDED, 1, 2, 1, 1>(pl, out);
   TCS_TC_CASE(96, EPI_RAW_STATS, 2)
   TCS_TC_CASE(96, EPI_PADDED, 2)
   TCS_TC_CASE(96, EPI_PLAIN, 2)
@@ -1324,7 +1438,9 @@ int conv_tc_launch(const ConvTcPlan& pl, cudaStream_t st) {
     else return launch_t<NN, EE, MM, 1, 0>(pl, st);                                     \
   }
 #define TCS_TC_GEO1(NN, EE, MM)                                                        \
-  if (pl.geo == 1 && pl.cg == 2 && pl.N == NN && pl.epi == EE && pl.msub == MM) return launch_t<NN, EE, MM, 2, 1>(pl, st);
+  if (pl.geo == 1 && pl.cg == 2 && !pl.ups && pl.N == NN && pl.epi == EE && pl.msub == MM) return launch_t<NN, EE, MM, 2, 1>(pl, st);
+  if (pl.geo == 1 && pl.cg == 2 && pl.ups && pl.epi == EPI_PADDED && pl.N == 96 && pl.msub == 2) return launch_t<96, EPI_PADDED, 2, 2, 1, 1>(pl, st);
+  if (pl.geo == 1 && pl.cg == 2 && pl.ups && pl.epi == EPI_PADDED && pl.N == 192 && pl.msub == 1) return launch_t<192, EPI_PADDED, 1, 2, 1, 1>(pl, st);
   TCS_TC_CASE(96, EPI_RAW_STATS, 2)
   TCS_TC_CASE(96, EPI_PADDED, 2)
   TCS_TC_CASE(96, EPI_PLAIN, 2)
@@ -1399,6 +1515,8 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, con
   p.geo = pl.geo;
   p.P = p.tiles_x = p.a_stages = p.tb = 0;
   p.a_load_bytes = 0;
+  p.ups = p.l_stages = 0;
+  p.l_bytes = p.l_load_bytes = 0;
   if (pl.geo) {
     // tap-shift geometry: CTA tile = 16 image rows x 8 MSUB pixels; one (16 + 2) x (8 MSUB + 2) pixel window per
     // 64-channel block in a ring of its own, the weights in stages of tb taps (three ky taps of one kx, or single taps
@@ -1413,17 +1531,28 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, con
     p.a_load_bytes = static_cast<uint32_t>(p.WR) * p.P * ROWB;
     p.a_bytes = (p.a_load_bytes + 1023u) & ~1023u;
     p.a_stages = 2;
-    const size_t budget1 = TC_SMEM_MAX - 1024 - EPI_SLAB_BYTES - bias_bytes_of(g.ntot) - EPI_FUSED_BYTES;
+    if (g.ups) {   // low-resolution windows: (8 + 2) rows x (4 MSUB + 2) pixels x 64 channels
+      p.ups = pl.ups = 1;
+      p.l_stages = 2;
+      p.l_load_bytes = 10u * static_cast<uint32_t>(p.P / 2 + 1) * ROWB;
+      p.l_bytes = (p.l_load_bytes + 1023u) & ~1023u;
+    }
+    const size_t budget1 = TC_SMEM_MAX - 1024 - EPI_SLAB_BYTES - bias_bytes_of(g.ntot) - EPI_FUSED_BYTES -
+                           static_cast<size_t>(p.l_stages) * p.l_bytes;
     const size_t rest = budget1 - static_cast<size_t>(p.a_stages) * p.a_bytes;
-    p.tb = (rest / (3u * NB * ROWB) >= 3) ? 3 : 1;
+    p.tb = (rest / (3u * NB * ROWB) >= (g.ups ? 2u : 3u)) ? 3 : 1;   // (ups: two 3-tap stages beat seven 1-tap stages)
     if (getenv("TCS_TB")) p.tb = atoi(getenv("TCS_TB")) == 3 ? 3 : 1;
     p.stage_bytes = (static_cast<uint32_t>(p.tb) * NB * ROWB + 1023u) & ~1023u;
     p.nstage = static_cast<int>(rest / p.stage_bytes);
     if (p.nstage > MAX_STAGES) p.nstage = MAX_STAGES;
+    if (getenv("TCS_NSTAGE") && atoi(getenv("TCS_NSTAGE")) < p.nstage) p.nstage = atoi(getenv("TCS_NSTAGE"));   // experiment
+    if (getenv("TCS_PLAN_LOG")) fprintf(stderr, "[conv_tc plan] H=%d N=%d K=%d ups=%d tb=%d nstage=%d stage_bytes=%u a_bytes=%u l_bytes=%u\n", g.H, pl.N, p.kstages, p.ups, p.tb, p.nstage, p.stage_bytes, p.a_bytes, p.l_bytes);
     if (p.nstage < 2) return fail(TCS_ERR_UNSUPPORTED, "conv_tc: weight stage does not fit shared memory twice");
-    pl.smem = static_cast<size_t>(p.a_stages) * p.a_bytes + static_cast<size_t>(p.nstage) * p.stage_bytes + 1024 +
-              EPI_SLAB_BYTES + bias_bytes_of(g.ntot) + EPI_FUSED_BYTES;
+    pl.smem = static_cast<size_t>(p.a_stages) * p.a_bytes + static_cast<size_t>(p.l_stages) * p.l_bytes +
+              static_cast<size_t>(p.nstage) * p.stage_bytes + 1024 + EPI_SLAB_BYTES + bias_bytes_of(g.ntot) + EPI_FUSED_BYTES;
   }
+  if (g.ups && !(pl.geo == 1 && pl.cg == 2 && epi == EPI_PADDED && g.nsrc == 1 && !g.split3))
+    return fail(TCS_ERR_UNSUPPORTED, "conv_tc: the fused upsample needs a 3x3 stride-1 layer with one padded bf16 source and a padded output");
   p.epi = ea;
   TCS_CHECK(conv_tc_max_ctas(pl, &pl.max_ctas));
   if (getenv("TCS_MAX_CTAS")) pl.max_ctas = atoi(getenv("TCS_MAX_CTAS"));   // test hook: pretend part of the device is taken
@@ -1463,6 +1592,11 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, con
     cuuint32_t box[4] = {KB, static_cast<cuuint32_t>(g.W * g.stride), static_cast<cuuint32_t>(p.WR * g.stride), 1};
     cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(g.stride), static_cast<cuuint32_t>(g.stride), 1};
     if (pl.geo) { box[1] = static_cast<cuuint32_t>(p.P); box[2] = static_cast<cuuint32_t>(p.WR); }
+    if (pl.ups) {   // the half-resolution padded tensor, boxes of (8 + 2) x (4 MSUB + 2) pixels
+      dims[1] = static_cast<cuuint64_t>(g.W / 2 + 2); dims[2] = static_cast<cuuint64_t>(g.H / 2 + 2);
+      strides[1] = C * 2 * dims[1]; strides[2] = strides[1] * dims[2];
+      box[1] = static_cast<cuuint32_t>(p.P / 2 + 1); box[2] = 10;
+    }
     CUresult r = encode(&pl.mapA[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(srcs[s]), dims, strides,
                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

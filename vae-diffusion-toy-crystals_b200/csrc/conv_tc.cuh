@@ -35,6 +35,9 @@ struct ConvTcParams {
   int tiles_x;              // geo 1: CTA tiles per image row
   int a_stages, tb;         // geo 1: A ring depth; taps per weight stage (3 or 1)
   uint32_t a_load_bytes;    // geo 1: bytes one window load delivers (a_bytes is its 1024-byte-aligned slot size)
+  int ups;                  // 1 = fused bilinear x2 upsample (ConvGeom::ups): low-resolution windows in a ring of l_stages slots
+  int l_stages;
+  uint32_t l_bytes, l_load_bytes;
   int debug;                // TCS_DEBUG bits (timing experiments only): 1 = no inter-CTA wait, 2 = no pass-2 stores
   EpiArgs epi;
 };
@@ -45,6 +48,7 @@ struct ConvTcPlan {
   CUtensorMap mapO;   // EPI_PADDED / EPI_GN_FUSED: padded bf16 output, TMA-stored in 32-pixel x 32-channel boxes
   CUtensorMap mapO1;  // geo 1: the same tensor with a one-image-row box (the wrapped copies of rows 0 and H - 1)
   int geo = 0;
+  int ups = 0;
   ConvTcParams p;
   int N;       // N tile (96 or 192)
   int epi;     // Epilogue

@@ -48,6 +48,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (((++spins) & 0x3ff) == 0 && clock64() - t0 > 4000000000LL) __trap();
   }
 }
+// the same for a warp that has slack: sleep between polls instead of competing for issue slots
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(64);
+    if (((++spins) & 0x3ff) == 0 && clock64() - t0 > 4000000000LL) __trap();
+  }
+}
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
                                             int c2, int c3) {
   asm volatile(
@@ -122,6 +132,33 @@ __device__ __forceinline__ void mbar_arrive_rank0(uint32_t bar) {
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
       "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar) : "memory");
+}
+// arrive (release at cluster scope: it publishes shared-memory writes) on CTA 0's copy of this barrier
+__device__ __forceinline__ void mbar_arrive_release_rank0(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar) : "memory");
+}
+// wait with acquire at cluster scope (the arrivals came from both CTAs of a pair and published shared-memory writes)
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (((++spins) & 0x3ff) == 0 && clock64() - t0 > 4000000000LL) __trap();
+  }
 }
 __device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
                                                 int c2, int c3) {

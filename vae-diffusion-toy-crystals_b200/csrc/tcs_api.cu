@@ -100,6 +100,8 @@ struct tcs_handle {
   bool bf16 = false, use_tc = false, fuse_gn = false, fuse_first = true;
   bool fuse_attn = false;   // the attention block as one tcgen05 kernel (attn_tc.cu); TCS_FUSE_ATTN=0 keeps the four launches
   DevBuf attn_wpack;
+  bool fuse_ups = false;    // TCS_FUSE_UPS=1: us1_conv / us2_conv read the half-resolution tensor, the bilinear x2 upsample is blended inside the conv (default: stand-alone kernel)
+  ConvTcPlan plan_us[2];    // [us2_conv, us1_conv] with ConvGeom::ups
   bool split3 = false;   // precision fp32 on the tcgen05 engine: conv operands as bf16 (hi, lo) pairs (kernels_split.cu)
   size_t esz = 4;
   cudaStream_t stream = nullptr;   // internal stream all work runs on
@@ -334,6 +336,21 @@ static int build_plans(tcs_handle* h) {
     }
     TCS_CHECK(conv_tc_make_plan(&h->plan[id], g, w.s0, w.s1, h->wpack[id].as<__nv_bfloat16>(), w.epi, ea, h->sm_count));
   }
+  if (h->fuse_ups) {
+    const int ids[2] = {C_US2, C_US1};
+    const void* lowres[2] = {h->p16_c.p, h->p32_96b.p};
+    for (int k = 0; k < 2; ++k) {
+      const ConvWiring w = wiring(h, ids[k]);
+      ConvGeom g = geom_of(ids[k], h->chunk, w.in_pad);
+      g.ups = 1;
+      EpiArgs ea{};
+      ea.bias = h->dw.at(std::string(kConv[ids[k]].key) + ".bias");
+      ea.out = w.out; ea.partials = h->partials.as<float>(); ea.residual = nullptr; ea.ldo = w.ldo;
+      ea.slots = slots_of(h, ids[k]);
+      ea.overflow = h->status.as<int>();
+      TCS_CHECK(conv_tc_make_plan(&h->plan_us[k], g, lowres[k], nullptr, h->wpack[ids[k]].as<__nv_bfloat16>(), EPI_PADDED, ea, h->sm_count));
+    }
+  }
   // The fused-GroupNorm kernels are launched as CTA pairs WITH the cooperative attribute where the runtime accepts the
   // combination.  Try it once here, outside any stream capture (a refused launch inside a capture would invalidate the
   // captured graph): a full-width grid over a few images of the (uninitialised) workspace.
@@ -495,18 +512,40 @@ static int forward_chunk(tcs_handle* h, const PassArgs& a, cudaStream_t st, TapR
   }
   TAP(1, h->p16_c.p, 16, 16, 192);
   // ---- up2 ---------------------------------------------------------------------------------
-  ++h->launches;
-  TCS_CHECK(launch_upsample2x<T>(h->p16_c.as<T>(), B, 16, 16, 192, h->p32_192a.as<T>(), st));
-  TAP(1, h->p32_192a.p, 32, 32, 192);
-  TCS_CHECK(run_conv<T>(h, C_US2, B, st));
+  // us*_conv: nn.Upsample(x2, bilinear) + 3x3 conv.  Fused: the conv reads the half-resolution tensor and blends the
+  // upsampled window in shared memory; the "us?.up" debug taps need the stand-alone upsample kernel.
+  auto us_conv = [&](int k, int id) -> int {
+    ++h->launches;
+    ConvTcPlan pl = h->plan_us[k];
+    pl.p.n_mtiles = B * pl.p.tiles_per_img;
+    pl.grid = conv_tc_grid(pl, B, h->sm_count);
+    if (h->profiling) TCS_CUDA(cudaEventRecord(h->prof_ev[2 * id], st));
+    TCS_CHECK(conv_tc_launch(pl, st));
+    if (h->profiling) TCS_CUDA(cudaEventRecord(h->prof_ev[2 * id + 1], st));
+    return TCS_OK;
+  };
+  if (h->fuse_ups && sizeof(T) == 2 && !(tap && tap->id == tap_idx)) {
+    ++tap_idx;
+    TCS_CHECK(us_conv(0, C_US2));
+  } else {
+    ++h->launches;
+    TCS_CHECK(launch_upsample2x<T>(h->p16_c.as<T>(), B, 16, 16, 192, h->p32_192a.as<T>(), st));
+    TAP(1, h->p32_192a.p, 32, 32, 192);
+    TCS_CHECK(run_conv<T>(h, C_US2, B, st));
+  }
   TAP(1, h->p32_192b.p, 32, 32, 192);
   CONV_GN(C_U2A, h->raw32.p, 32, 96);
   CONV_GN(C_U2B, h->raw32.p, 32, 96);
   // ---- up1 ---------------------------------------------------------------------------------
-  ++h->launches;
-  TCS_CHECK(launch_upsample2x<T>(h->p32_96b.as<T>(), B, 32, 32, 96, h->p64_a.as<T>(), st));
-  TAP(1, h->p64_a.p, 64, 64, 96);
-  TCS_CHECK(run_conv<T>(h, C_US1, B, st));
+  if (h->fuse_ups && sizeof(T) == 2 && !(tap && tap->id == tap_idx)) {
+    ++tap_idx;
+    TCS_CHECK(us_conv(1, C_US1));
+  } else {
+    ++h->launches;
+    TCS_CHECK(launch_upsample2x<T>(h->p32_96b.as<T>(), B, 32, 32, 96, h->p64_a.as<T>(), st));
+    TAP(1, h->p64_a.p, 64, 64, 96);
+    TCS_CHECK(run_conv<T>(h, C_US1, B, st));
+  }
   TAP(1, h->p64_b.p, 64, 64, 96);
   CONV_GN(C_U1A, h->raw64.p, 64, 96);
   CONV_GN(C_U1B, h->raw64.p, 64, 96);
@@ -837,6 +876,8 @@ int tcs_create(tcs_handle** out, const tcs_config* cfg) {
     const char* e = getenv("TCS_FUSE_GN");   // 0 = keep conv -> raw fp32 -> gn_apply (A/B switch)
     h->fuse_gn = h->use_tc && !h->split3 && cfg->fuse_gn != 0 && !(e && atoi(e) == 0);
     h->fuse_first = !(e && atoi(e) == 0);
+    const char* eu = getenv("TCS_FUSE_UPS");
+    h->fuse_ups = h->use_tc && !h->split3 && eu && atoi(eu) == 1;   // opt-in: measured 1 % slower than the stand-alone kernel
     const char* ea = getenv("TCS_FUSE_ATTN");
     h->fuse_attn = h->use_tc && !h->split3 && !(ea && atoi(ea) == 0);
   }
@@ -1278,7 +1319,7 @@ int tcs_sample(tcs_handle* h, const tcs_sample_args* args, void* stream) {
 template <typename T>
 static int debug_conv_t(bool use_tc, const ConvGeom& g, const float* in0, const float* in1, const float* weight,
                         const float* bias, float* out, float* stats, int epi, cudaStream_t st) {
-  const int B = g.B, Hin = g.H * g.stride, Win = g.W * g.stride;
+  const int B = g.B, Hin = g.ups ? g.H / 2 : g.H * g.stride, Win = g.ups ? g.W / 2 : g.W * g.stride;   // ups: half-resolution source
   const int pad = g.in_pad[0];
   DevBuf s0, s1, wp, db, dout, part;
   const size_t in_elems0 = static_cast<size_t>(B) * (Hin + 2 * pad) * (Win + 2 * pad) * g.csrc[0];
@@ -1437,6 +1478,19 @@ int tcs_debug_conv(int32_t engine, int32_t precision, int32_t B, int32_t H_out, 
   if (eng == TCS_ENGINE_TCGEN05 && !bf16) return debug_conv_split3(g, in0, in1, weight, bias, out, stats, epi, st);
   if (bf16) return debug_conv_t<__nv_bfloat16>(eng == TCS_ENGINE_TCGEN05, g, in0, in1, weight, bias, out, stats, epi, st);
   return debug_conv_t<float>(false, g, in0, in1, weight, bias, out, stats, epi, st);
+}
+
+// 3x3 conv of the bilinear x2 upsample of a half-resolution input, upsample fused into the conv (ConvGeom::ups)
+int tcs_debug_conv_ups(int32_t B, int32_t H_out, int32_t W_out, int32_t cin, int32_t cout, const float* in_lowres,
+                       const float* weight, const float* bias, float* out, void* stream) {
+  if (!in_lowres || !weight || !bias || !out || B < 1) return fail(TCS_ERR_BAD_ARGUMENT, "tcs_debug_conv_ups: bad argument");
+  if (H_out != W_out) return fail(TCS_ERR_UNSUPPORTED, "tcs_debug_conv_ups: square outputs only");
+  ConvGeom g;
+  g.B = B; g.H = H_out; g.W = W_out; g.ksize = 3; g.stride = 1;
+  g.nsrc = 1; g.csrc[0] = g.csrc[1] = cin; g.in_pad[0] = g.in_pad[1] = 1; g.ntot = cout;
+  g.ups = 1;
+  return debug_conv_t<__nv_bfloat16>(true, g, in_lowres, nullptr, weight, bias, out, nullptr, EPI_PADDED,
+                                     static_cast<cudaStream_t>(stream));
 }
 
 // The fused attention block in isolation (halo of the padded output verified like tcs_debug_conv's).
