@@ -344,14 +344,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const CUtensorMap* mapA = ms == 0 ? &mapA0 : (ms == 1 ? &mapA1 : (ms == 2 ? &mapA2 : &mapA3));
         for (int cb = 0; cb < p.cblk[src]; ++cb) {
           if constexpr (UPS) {   // low-resolution window -> its own ring (this CTA's barrier); warps 19..22 fill the A ring
-            ptx::mbar_wait(ptx::smem_u32(&bars.emptyL[sa]), pa ^ 1);
-            if (lane == 0) {
-              const uint32_t full = ptx::smem_u32(&bars.fullL[sa]);
-              ptx::mbar_expect_tx(full, p.l_load_bytes);
-              ptx::tma_load_4d(l_ring + sa * p.l_bytes, mapA, full, cb * KB, tx * 4 * MSUB + p.base_off[src], ty * 8 + p.base_off[src], b);
-            }
-            __syncwarp();
-            if (++sa == static_cast<uint32_t>(p.l_stages)) { sa = 0; pa ^= 1; }
+            // The window of the NEXT block is requested before this block's weights: the weight ring blocks this warp until
+            // the MMAs make progress, and a window that is only requested then arrives (and is blended) too late.
+            auto issue_low = [&](int tl, int cbx) {
+              int mt2, nt2;
+              tile_to_mn<CG>(tl, p.n_ntiles, mt2, nt2);
+              const int b2 = mt2 / p.tiles_per_img, t2 = mt2 - b2 * p.tiles_per_img;
+              const int ty2 = t2 / p.tiles_x, tx2 = t2 - ty2 * p.tiles_x;
+              ptx::mbar_wait(ptx::smem_u32(&bars.emptyL[sa]), pa ^ 1);
+              if (lane == 0) {
+                const uint32_t full = ptx::smem_u32(&bars.fullL[sa]);
+                ptx::mbar_expect_tx(full, p.l_load_bytes);
+                ptx::tma_load_4d(l_ring + sa * p.l_bytes, mapA, full, cbx * KB, tx2 * 4 * MSUB + p.base_off[0], ty2 * 8 + p.base_off[0], b2);
+              }
+              __syncwarp();
+              if (++sa == static_cast<uint32_t>(p.l_stages)) { sa = 0; pa ^= 1; }
+            };
+            if (tile == static_cast<int>(blockIdx.x) && cb == 0) issue_low(tile, 0);
+            int ntile = tile, ncb = cb + 1;
+            if (ncb == p.cblk[0]) { ncb = 0; ntile = tile + static_cast<int>(gridDim.x); }
+            if (ntile < n_tiles) issue_low(ntile, ncb);
           } else {
           ptx::mbar_wait(ptx::smem_u32(&bars.emptyA[sa]), pa ^ 1);
           const bool stale = (p.debug & 8) && (pa || tile != static_cast<int>(blockIdx.x));   // experiment: no TMA

@@ -100,7 +100,7 @@ struct tcs_handle {
   bool bf16 = false, use_tc = false, fuse_gn = false, fuse_first = true;
   bool fuse_attn = false;   // the attention block as one tcgen05 kernel (attn_tc.cu); TCS_FUSE_ATTN=0 keeps the four launches
   DevBuf attn_wpack;
-  bool fuse_ups = false;    // TCS_FUSE_UPS=1: us1_conv / us2_conv read the half-resolution tensor, the bilinear x2 upsample is blended inside the conv (default: stand-alone kernel)
+  bool fuse_ups = false;    // us1_conv / us2_conv read the half-resolution tensor, the bilinear x2 upsample is blended inside the conv (TCS_FUSE_UPS=0: stand-alone kernel)
   ConvTcPlan plan_us[2];    // [us2_conv, us1_conv] with ConvGeom::ups
   bool split3 = false;   // precision fp32 on the tcgen05 engine: conv operands as bf16 (hi, lo) pairs (kernels_split.cu)
   size_t esz = 4;
@@ -348,7 +348,9 @@ static int build_plans(tcs_handle* h) {
       ea.out = w.out; ea.partials = h->partials.as<float>(); ea.residual = nullptr; ea.ldo = w.ldo;
       ea.slots = slots_of(h, ids[k]);
       ea.overflow = h->status.as<int>();
-      TCS_CHECK(conv_tc_make_plan(&h->plan_us[k], g, lowres[k], nullptr, h->wpack[ids[k]].as<__nv_bfloat16>(), EPI_PADDED, ea, h->sm_count));
+      const int rc = conv_tc_make_plan(&h->plan_us[k], g, lowres[k], nullptr, h->wpack[ids[k]].as<__nv_bfloat16>(), EPI_PADDED, ea, h->sm_count);
+      if (rc == TCS_ERR_UNSUPPORTED) { h->fuse_ups = false; break; }   // e.g. TCS_GEO=0 (A/B switch): the stand-alone upsample kernel runs
+      TCS_CHECK(rc);
     }
   }
   // The fused-GroupNorm kernels are launched as CTA pairs WITH the cooperative attribute where the runtime accepts the
@@ -877,7 +879,7 @@ int tcs_create(tcs_handle** out, const tcs_config* cfg) {
     h->fuse_gn = h->use_tc && !h->split3 && cfg->fuse_gn != 0 && !(e && atoi(e) == 0);
     h->fuse_first = !(e && atoi(e) == 0);
     const char* eu = getenv("TCS_FUSE_UPS");
-    h->fuse_ups = h->use_tc && !h->split3 && eu && atoi(eu) == 1;   // opt-in: measured 1 % slower than the stand-alone kernel
+    h->fuse_ups = h->use_tc && !h->split3 && !(eu && atoi(eu) == 0);
     const char* ea = getenv("TCS_FUSE_ATTN");
     h->fuse_attn = h->use_tc && !h->split3 && !(ea && atoi(ea) == 0);
   }
