@@ -758,7 +758,7 @@ def profile_kernels(model, sde, dev, n=1024):
         blk = flops[iq] + flops[ip] + 2e6 * ATTN_SDPA_MMAC * images
         per_layer["attn.block(norm+qkv+sdpa+proj)"] = round(blk / (conv_ms[iq] * 1e-3) / 1e12, 1)
     traffic, traffic_source = None, None   # DRAM bytes of the same 15 launches from the committed `ncu --set full` capture
-    for name in ("r2_conv_ncu_full.json", "r1_conv_ncu_full.json"):
+    for name in ("r2_conv_ncu_full_fused.json", "r2_conv_ncu_full.json", "r1_conv_ncu_full.json"):
         tp = os.path.join(ROOT, "profiles", name)
         if os.path.exists(tp):
             tj = json.load(open(tp))

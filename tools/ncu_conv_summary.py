@@ -30,10 +30,20 @@ def main():
     rep, out = sys.argv[1], sys.argv[2]
     note = sys.argv[3] if len(sys.argv) > 3 else ""
     images = int(sys.argv[4]) if len(sys.argv) > 4 else 256
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if rep.endswith(".csv.gz"):   # the `ncu -i ... --page raw --csv | gzip` dump of a capture
+        import gzip
+        raw = gzip.open(rep, "rt").read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     head, units, data = rows[0], rows[1], rows[2:]
     unit = dict(zip(head, units))
+    global LAYERS
+    tmac = [339.74, 151.00, 169.87, 339.74, 151.00, 84.93, 84.93, 28.31, 9.44, 339.74, 339.74, 84.93, 339.74, 679.48, 339.74]
+    if len(data) == len(LAYERS) - 2:   # fused attention block build: attn.qkv / attn.proj are not conv_tc launches any more
+        keep = [i for i, n in enumerate(LAYERS) if n not in ("attn.qkv", "attn.proj")]
+        tmac = [tmac[i] for i in keep[:-1]]
+        LAYERS = [LAYERS[i] for i in keep]
     if len(data) != len(LAYERS):
         raise SystemExit(f"expected {len(LAYERS)} conv_tc launches (one pass), the report holds {len(data)}")
 
@@ -61,11 +71,11 @@ def main():
         layers.append(e)
         if name != LAYERS[-1]:
             traffic += (rd + wr) * 1e6
-    tmac = [339.74, 151.00, 169.87, 339.74, 151.00, 84.93, 84.93, 28.31, 9.44, 339.74, 339.74, 84.93, 339.74, 679.48, 339.74]
     for e, m in zip(layers[:-1], tmac):
         e["tflops_under_ncu"] = round(2e6 * m * images / (e["us"] * 1e-6) / 1e12, 1)
     res = {"source": (note + "; " if note else "") + rep,
            "images_per_pass": images, "traffic_bytes_per_pass": traffic, "traffic_MB_per_image": traffic / images / 1e6,
+           "conv_launches": len(layers) - 1,
            "conv_family_us": sum(e["us"] for e in layers[:-1]),
            "conv_family_tflops_under_ncu": 2e6 * sum(tmac) * images / (sum(e["us"] for e in layers[:-1]) * 1e-6) / 1e12,
            "algorithmic_MB_per_image_note": "inputs read once + outputs written once in bf16 = about 14.4 MB per image for "
@@ -73,7 +83,7 @@ def main():
                                             "output is still in L2 when the kernel ends",
            "layers": layers[:-1], "eps_conv": layers[-1]}
     json.dump(res, open(out, "w"), indent=1)
-    print(f"{out}: {sum(e['us'] for e in layers[:-1]):.1f} us for the 15 layers, {traffic / images / 1e6:.2f} MB DRAM traffic per image")
+    print(f"{out}: {sum(e['us'] for e in layers[:-1]):.1f} us for the {len(layers) - 1} layers, {traffic / images / 1e6:.2f} MB DRAM traffic per image")
 
 
 if __name__ == "__main__":
