@@ -1312,7 +1312,15 @@ int conv_tc_grid(const ConvTcPlan& pl, int B, int sm_count) {
   const int tiles = (pl.p.pair ? B / 2 : B) * pl.p.tiles_per_img * pl.p.n_ntiles;
   int grid = tiles < sm_count ? tiles : sm_count;
   if (pl.max_ctas > 0 && grid > pl.max_ctas) grid = pl.max_ctas;   // what the device can hold at once (occupancy query)
-  if (pl.epi == EPI_GN_FUSED) grid = grid / pl.p.tiles_per_img * pl.p.tiles_per_img;  // whole image groups only
+  // Fused GroupNorm: the tiles of an image exchange partial sums through L2 words indexed by TILE, not by CTA, so any
+  // co-resident grid is correct and deadlock-free (a tile only ever waits for tiles of its own image, i.e. for tile indices
+  // at most one grid-stride ahead, whose CTAs never wait for anything later).  Whole image groups (grid a multiple of the
+  // tiles per image) keep every image inside one wave; the full grid lets one image in ~9 straddle two waves (its first
+  // tiles' epilogue group waits one tile period, which the other group and the double-buffered accumulators absorb) but
+  // uses all SMs: 148 instead of 144 on the 64x64 and 32x32 layers.  TCS_GN_GROUP_GRID=1 restores the rounded grid.
+  static const bool group_grid = getenv("TCS_GN_GROUP_GRID") && atoi(getenv("TCS_GN_GROUP_GRID")) == 1;
+  if (pl.epi == EPI_GN_FUSED && (group_grid || grid < pl.p.tiles_per_img * 2))
+    grid = grid / pl.p.tiles_per_img * pl.p.tiles_per_img;
   if (pl.cg == 2) grid &= ~1;                                                         // whole CTA pairs
   return grid;
 }
