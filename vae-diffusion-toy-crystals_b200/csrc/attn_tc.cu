@@ -8,10 +8,11 @@
 // stores), so that each CTA holds all 256 keys of the current head.  All MMAs are cta_group::1 (M = 128):
 //   qkv_h [128 x 144] = Xn [128 x 192] . W_h^T        A, B shared memory (K-major SWIZZLE_128B), per head h
 //   S     [128 x 256] = Q'_h [128 x 48] . K_h^T       A = Q' in TENSOR MEMORY (bf16 packed, tcgen05.st), Q' = q log2e/sqrt(48)
-//   O_h   [128 x  48] = P [128 x 256] . V_h           A = P in tensor memory, written IN PLACE over the S columns;
-//                                                     B = V rows (keys) x 48 -> MN-major descriptor
+//   O_h   [128 x  64] = P [128 x 256] . V_h           A = P (fp16) in tensor memory, written IN PLACE over the S columns;
+//                                                     B = V rows (keys) x 64 (fp16: 48 values, a 1, zeros) -> MN-major
+//                                                     descriptor; column 48 of O_h is the softmax denominator
 //   Y     [128 x 192] = O [128 x 192] . Wproj^T       A = normalised O of all heads (shared memory)
-// TMEM columns: [0,256) S / P / Y, [256,400) qkv_h, [400,424) Q' (packed), [424,472) O_h.
+// TMEM columns: [0,256) S / P / Y, [256,400) qkv_h, [400,424) Q' (packed), [424,488) O_h (48 columns + the row sums).
 // Shared memory (214 KB): Xn 48 K | weights of the head 54 K (bulk-copied, pre-swizzled images; Wproj reuses this and the
 // dead Xn region) | K 32 K | V 32 K (128-byte rows, 48 of 64 elements used) | O 48 K.
 // Threads: warp 0 = control (one lane issues the bulk copies and every MMA), warps 1-8 = workers: warp w owns TMEM lane
@@ -62,6 +63,25 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
 }
 __device__ __forceinline__ uint4 pack8(const float* f) {
   return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+}
+// fp16 pair (a in the low half), round to nearest, saturating to the largest finite value
+__device__ __forceinline__ uint32_t pack2_f16(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ uint4 pack8_f16(const float* f) {
+  return make_uint4(pack2_f16(f[0], f[1]), pack2_f16(f[2], f[3]), pack2_f16(f[4], f[5]), pack2_f16(f[6], f[7]));
+}
+// two base-2 exponentials per MUFU operation
+__device__ __forceinline__ uint32_t ex2_f16x2(uint32_t x) {
+  uint32_t y;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+// instruction descriptor for kind::f16 with fp16 A and B (the P V product: P and V are stored as fp16)
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 __device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ int halo_wrap16(int v) { return v == 0 ? 16 : (v == 15 ? -16 : 0); }
@@ -114,7 +134,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AT_THREADS, 1) attn_
   __shared__ float s_part[AT_THREADS][2];
   __shared__ float s_mine[16], s_peer[16];
   __shared__ float s_mean[8], s_rstd[8];
-  __shared__ float s_max[2][AT_TOK], s_sum[2][AT_TOK];
+  __shared__ float s_max[2][AT_TOK];
   __shared__ float s_bqkv[576], s_bproj[192], s_gamma[192], s_beta[192];
 
   cg::cluster_group cluster = cg::this_cluster();
@@ -324,7 +344,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AT_THREADS, 1) attn_
           ptx::mbar_wait(b_vf, ph_vf); ph_vf ^= 1;
           ptx::mbar_expect_tx(b_vf, 16384);
           {
-            const uint32_t idesc = make_idesc(128, 48) | IDESC_B_MN_MAJOR;
+            const uint32_t idesc = make_idesc_f16(128, 64) | IDESC_B_MN_MAJOR;   // columns 48..: the ones column (row sums)
 #pragma unroll
             for (int i = 0; i < 4; ++i) {   // O_h += P V_h for the 64 keys of softmax chunk i, as soon as that chunk is stored
               ptx::mbar_wait(b_p0 + 8 * i, ph_p);
@@ -430,8 +450,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AT_THREADS, 1) attn_
           if (dbg) {
             for (int i = 0; i < 8; ++i) dbg[ATTN_DBG_QKV + static_cast<size_t>(gt) * 576 + 384 + hh * 48 + 24 * hf + j * 8 + i] = g8[i];
           }
-          *reinterpret_cast<uint4*>(sm + V_OFF + sw128(gt, 3 * hf + j)) = pack8(g8);
+          *reinterpret_cast<uint4*>(sm + V_OFF + sw128(gt, 3 * hf + j)) = pack8_f16(g8);
         }
+        // element 48 of every V row is 1: column 48 of P V is then the softmax denominator, summed by the tensor core over
+        // exactly the fp16 P values the product uses (elements 49..63 are zero / never read back)
+        *reinterpret_cast<uint4*>(sm + V_OFF + sw128(gt, 6 + hf)) = hf == 0 ? make_uint4(0x3C00u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
         ptx::fence_proxy_async();
         ptx::tc_fence_before();     // the qkv_h columns have been read: the control lane may issue the next projection
         __syncwarp();
@@ -447,37 +470,43 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AT_THREADS, 1) attn_
         ptx::tc_fence_after();
         const uint32_t sc = lane_addr + S_COL + 128 * hf;
         float m = -INFINITY;
+        {   // pass 1: row maximum, two 32-column loads in flight at a time
+          float sv[2][32];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float sv[32];
-          ptx::tmem_ld32(sc + 32 * i, sv);
-          ptx::tmem_ld_wait();
+          for (int i = 0; i < 4; i += 2) {
+            ptx::tmem_ld32(sc + 32 * i, sv[0]);
+            ptx::tmem_ld32(sc + 32 * i + 32, sv[1]);
+            ptx::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) m = fmaxf(m, sv[j]);
+            for (int j = 0; j < 32; ++j) m = fmaxf(m, fmaxf(sv[0][j], sv[1][j]));
+          }
         }
         s_max[hf][row] = m;
         worker_bar();
         m = fmaxf(s_max[0][row], s_max[1][row]);
-        float l = 0.f;
+        {   // pass 2: P = 2^(S' - m) as fp16 pairs, chunk i + 1 loading and chunk i - 1 draining while chunk i is computed
+          float sv[2][32];
+          ptx::tmem_ld32(sc, sv[0]);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float sv[32];
-          ptx::tmem_ld32(sc + 32 * i, sv);
-          ptx::tmem_ld_wait();
-          uint32_t pk[16];
+          for (int i = 0; i < 4; ++i) {
+            ptx::tmem_ld_wait();
+            if (i < 3) ptx::tmem_ld32(sc + 32 * (i + 1), sv[(i + 1) & 1]);
+            uint32_t pk[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float p0 = ptx::ex2_approx(sv[2 * j] - m), p1 = ptx::ex2_approx(sv[2 * j + 1] - m);
-            l += p0 + p1;
-            pk[j] = pack2(p0, p1);
+            for (int j = 0; j < 16; ++j) pk[j] = ex2_f16x2(pack2_f16(sv[i & 1][2 * j] - m, sv[i & 1][2 * j + 1] - m));
+            if (i > 0) {   // the previous chunk's store has had this chunk's math to complete: publish it
+              ptx::tmem_st_wait();
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive(b_p0 + 8 * (i - 1));
+            }
+            ptx::tmem_st16(sc + 16 * i, pk);
           }
-          ptx::tmem_st16(sc + 16 * i, pk);
           ptx::tmem_st_wait();
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(b_p0 + 8 * i);
+          if (lane == 0) ptx::mbar_arrive(b_p0 + 8 * 3);
         }
-        s_sum[hf][row] = l;
         AT_PROF();   // w: softmax done
         // ---- next head's Q' and K rows (S_h is complete, so Q' and this CTA's K rows may be overwritten) ---------------
         if (h < N_HEADS - 1) convert_qk(h + 1);
@@ -487,11 +516,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AT_THREADS, 1) attn_
         AT_PROF();   // w: O ready
         ptx::tc_fence_after();
         {
-          float o[24];
+          float o[24], lsum;
           ptx::tmem_ld16(lane_addr + O_COL + 24 * hf, o);
           ptx::tmem_ld8(lane_addr + O_COL + 24 * hf + 16, o + 16);
+          ptx::tmem_ld1(lane_addr + O_COL + 48, &lsum);
           ptx::tmem_ld_wait();
-          const float lsum = s_sum[0][row] + s_sum[1][row];
           const float inv = 1.0f / lsum;
           if (dbg && hf == 0) dbg[ATTN_DBG_L + static_cast<size_t>(gt) * 4 + h] = lsum;
 #pragma unroll
