@@ -624,22 +624,33 @@ void attn_tc_pack_weights(const float* qkv_w, const float* proj_w, uint8_t* out)
 int launch_attn_block_tc(const AttnTcParams& p, int sm_count, cudaStream_t st) {
   if (p.B <= 0) return TCS_OK;
   constexpr int smem = AT_SMEM + 1024;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  static int max_clusters = 0;
-  std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(attn_block_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (attr_err != cudaSuccess) return;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(2 * (sm_count / 2)); cfg.blockDim = dim3(AT_THREADS); cfg.dynamicSmemBytes = smem;
-    cudaLaunchAttribute at{};
-    at.id = cudaLaunchAttributeClusterDimension;
-    at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
-    cfg.attrs = &at; cfg.numAttrs = 1;
-    int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, attn_block_tc_kernel, &cfg) == cudaSuccess && n > 0) max_clusters = n;
-    else cudaGetLastError();
-  });
+  // per device (function attributes and cluster occupancy belong to a device; a process may hold handles on several)
+  static std::mutex mu;
+  static int max_clusters_dev[64];
+  static bool done_dev[64] = {};
+  int dev = 0;
+  TCS_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(TCS_ERR_UNSUPPORTED, "attn_tc: device ordinal out of range");
+  cudaError_t attr_err = cudaSuccess;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (!done_dev[dev]) {
+      attr_err = cudaFuncSetAttribute(attn_block_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (attr_err == cudaSuccess) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(2 * (sm_count / 2)); cfg.blockDim = dim3(AT_THREADS); cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute at{};
+        at.id = cudaLaunchAttributeClusterDimension;
+        at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+        cfg.attrs = &at; cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, attn_block_tc_kernel, &cfg) == cudaSuccess && n > 0) max_clusters_dev[dev] = n;
+        else { max_clusters_dev[dev] = 0; cudaGetLastError(); }
+        done_dev[dev] = true;
+      }
+    }
+  }
+  const int max_clusters = max_clusters_dev[dev];
   TCS_CUDA(attr_err);
   int ncl = sm_count / 2;
   if (max_clusters > 0 && max_clusters < ncl) ncl = max_clusters;

@@ -144,7 +144,7 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
 // W == 16: plain per-lane 16-byte stores (the 16x16 layers are small).
 // GEO == 1: the 32 lanes are 4 image rows x 8 pixels (lane = 8 * row + pixel); one TMA store of an 8-pixel x 4-row box,
 // plus a one-row box (mapO1, geo_H = image height) when the block holds image row 0 or H - 1 (the wrapped halo rows).
-template <int GEO = 0>
+template <int GEO = 0, int SB = SLAB_BUFS>
 __device__ __forceinline__ void store_padded_block(const CUtensorMap* mapO, bool use_tma, uint32_t slab, uint32_t& slab_buf,
                                                    int lane, __nv_bfloat16* obase, size_t pix, int wy, int wx, int Wp,
                                                    int ldo, int ch, int img, int y, int x, const uint32_t* pk,
@@ -155,10 +155,10 @@ __device__ __forceinline__ void store_padded_block(const CUtensorMap* mapO, bool
     return;
   }
   long long c0 = tacc ? clock64() : 0;
-  if (lane == 0) ptx::bulk_wait_read<SLAB_BUFS - 1>();   // the staging block about to be overwritten has been read
+  if (lane == 0) ptx::bulk_wait_read<SB - 1>();   // the staging block about to be overwritten has been read
   __syncwarp();
   if (tacc) { const long long c1 = clock64(); tacc[0] += c1 - c0; c0 = c1; }
-  const uint32_t base = slab + (SLAB_BUFS == 2 ? slab_buf * 2048 : 0);
+  const uint32_t base = slab + (SB == 2 ? slab_buf * 2048 : 0);
   const uint32_t dst = base + lane * 64;
   const int sw = (lane >> 1) & 3;
 #pragma unroll
@@ -283,7 +283,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   const uint32_t l_ring = smem_base + (GEO == 1 ? p.a_stages * p.a_bytes : 0u);   // UPS: low-resolution windows after the window ring
   const uint32_t b_ring = l_ring + (UPS ? p.l_stages * p.l_bytes : 0u);           // geo 1: windows first, then weight stages
   const uint32_t slab_base = b_ring + p.nstage * p.stage_bytes;
-  float* bias_s = reinterpret_cast<float*>(smem_raw + (slab_base - ptx::smem_u32(smem_raw)) + EPI_SLAB_BYTES);
+  // UPS kernels stage their outputs in ONE 2 KB block per epilogue warp (measured neutral for the epilogue) and spend the
+  // 32 KB on a third window stage (us1_conv) or a third weight stage (us2_conv)
+  constexpr int SB = UPS ? 1 : SLAB_BUFS;
+  constexpr uint32_t WARP_SLAB = SB * 32 * BLK * 2, SLAB_BYTES = EPI_WARPS * WARP_SLAB;
+  float* bias_s = reinterpret_cast<float*>(smem_raw + (slab_base - ptx::smem_u32(smem_raw)) + SLAB_BYTES);
   for (int i = threadIdx.x; i < p.ntot; i += blockDim.x) bias_s[i] = p.epi.bias[i];
   EpiFusedSmem* fs = reinterpret_cast<EpiFusedSmem*>(reinterpret_cast<uint8_t*>(bias_s) + (GEO == 1 ? bias_bytes_of(p.ntot) : EPI_BIAS_BYTES));
   if constexpr (EPI == EPI_GN_FUSED)
@@ -744,7 +748,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     (void)slab_buf;
     EpiGroupSmem* gsm = &fs->grp[grp];
     (void)gsm;
-    const uint32_t slab = slab_base + static_cast<uint32_t>(e) * EPI_WARP_SLAB;      // this warp's 2 x 2 KB staging halves
+    const uint32_t slab = slab_base + static_cast<uint32_t>(e) * WARP_SLAB;          // this warp's 2 x 2 KB staging halves
     const bool use_tma_out = !(p.debug & 4);
     const int h16 = p.W == 16 ? p.H : 0;       // 16-pixel rows: a 32-lane block spans two image rows
     (void)h16;
@@ -1125,8 +1129,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
               pk[i / 2] = pack_bf16x2(v[i] + b4.x, v[i + 1] + b4.y);
               pk[i / 2 + 1] = pack_bf16x2(v[i + 2] + b4.z, v[i + 3] + b4.w);
             }
-            store_padded_block<GEO>(&mapO, use_tma_out, slab, slab_buf, lane, obase, pix, wy, wx, Wp, p.epi.ldo, n_off + c0, b, y, x, pk,
-                                    nullptr, GEO == 1 ? 0 : h16, &mapO1, p.H);
+            store_padded_block<GEO, SB>(&mapO, use_tma_out, slab, slab_buf, lane, obase, pix, wy, wx, Wp, p.epi.ldo, n_off + c0, b, y, x, pk,
+                                        nullptr, GEO == 1 ? 0 : h16, &mapO1, p.H);
           }
         } else {  // EPI_PLAIN: unpadded bf16 [pixel][ldo] rows; 32 px x 32 ch blocks staged in the warp's slabs and
                   // TMA-stored (a lane-per-row 16-byte store touches 32 different lines per instruction)
@@ -1557,8 +1561,15 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, con
       p.l_load_bytes = 10u * static_cast<uint32_t>(p.P / 2 + 1) * ROWB;
       p.l_bytes = (p.l_load_bytes + 1023u) & ~1023u;
     }
-    const size_t budget1 = TC_SMEM_MAX - 1024 - EPI_SLAB_BYTES - bias_bytes_of(g.ntot) - EPI_FUSED_BYTES -
+    const size_t slab_bytes = g.ups ? EPI_SLAB_BYTES / SLAB_BUFS : EPI_SLAB_BYTES;   // UPS: single-buffered output staging
+    const size_t budget1 = TC_SMEM_MAX - 1024 - slab_bytes - bias_bytes_of(g.ntot) - EPI_FUSED_BYTES -
                            static_cast<size_t>(p.l_stages) * p.l_bytes;
+    // what to do with the 32 KB (measured, profiles/r2_layer_speed_fused_upsample.txt): us1_conv (N = 96, a 64- and a
+    // 32-channel block per tile) gains 2 % from a third window stage (2 weight stages left), us2_conv (N = 192) gains 5 %
+    // from a third weight stage instead
+    const bool want3 = getenv("TCS_UPS_A_STAGES") ? atoi(getenv("TCS_UPS_A_STAGES")) == 3 : pl.msub == 2;
+    if (g.ups && want3 && budget1 >= 3 * static_cast<size_t>(p.a_bytes) + 2 * static_cast<size_t>(3u * NB * ROWB))
+      p.a_stages = 3;
     const size_t rest = budget1 - static_cast<size_t>(p.a_stages) * p.a_bytes;
     p.tb = (rest / (3u * NB * ROWB) >= (g.ups ? 2u : 3u)) ? 3 : 1;   // (ups: two 3-tap stages beat seven 1-tap stages)
     if (getenv("TCS_TB")) p.tb = atoi(getenv("TCS_TB")) == 3 ? 3 : 1;
@@ -1569,7 +1580,7 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, con
     if (getenv("TCS_PLAN_LOG")) fprintf(stderr, "[conv_tc plan] H=%d N=%d K=%d ups=%d tb=%d nstage=%d stage_bytes=%u a_bytes=%u l_bytes=%u\n", g.H, pl.N, p.kstages, p.ups, p.tb, p.nstage, p.stage_bytes, p.a_bytes, p.l_bytes);
     if (p.nstage < 2) return fail(TCS_ERR_UNSUPPORTED, "conv_tc: weight stage does not fit shared memory twice");
     pl.smem = static_cast<size_t>(p.a_stages) * p.a_bytes + static_cast<size_t>(p.l_stages) * p.l_bytes +
-              static_cast<size_t>(p.nstage) * p.stage_bytes + 1024 + EPI_SLAB_BYTES + bias_bytes_of(g.ntot) + EPI_FUSED_BYTES;
+              static_cast<size_t>(p.nstage) * p.stage_bytes + 1024 + slab_bytes + bias_bytes_of(g.ntot) + EPI_FUSED_BYTES;
   }
   if (g.ups && !(pl.geo == 1 && pl.cg == 2 && epi == EPI_PADDED && g.nsrc == 1 && !g.split3))
     return fail(TCS_ERR_UNSUPPORTED, "conv_tc: the fused upsample needs a 3x3 stride-1 layer with one padded bf16 source and a padded output");
