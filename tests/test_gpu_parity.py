@@ -502,6 +502,39 @@ def test_tma_store_epilogues_match_per_lane_stores(monkeypatch):
     assert torch.equal(outs[0], outs[4]), "weight stages of one tap differ from stages of three taps"
 
 
+def test_fused_blocks_agree_with_their_unfused_forms(monkeypatch):
+    """The fused attention block (attn_tc.cu) and the upsample fused into us1_conv / us2_conv against the same network with
+    the four-launch attention / the stand-alone upsample kernel (TCS_FUSE_ATTN=0, TCS_FUSE_UPS=0): one CFG evaluation of
+    5 samples.  The fused upsample performs the same fp32 blend and the same single rounding, so it may only move bf16
+    roundings (measured: bit-identical eps); the fused attention rounds q, k, v, P differently (fp16 P and V): measured
+    5.5e-3 on eps, both forms are equally far (~9e-3) from the oracle."""
+    import toycrystals_oracle as orc
+    from toycrystals_b200.models import sde_score_model as shim
+    sd = orc.default_init_state_dict(1)
+    y_cat, y_cont = (t.cuda() for t in orc.condition_grid(5, 4, 4))
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn((5, 1, 64, 64), generator=g).cuda()
+    t = torch.full((5,), 0.4).cuda()
+    outs = {}
+    for name, env in (("fused", {}), ("ups_off", {"TCS_FUSE_UPS": "0"}), ("attn_off", {"TCS_FUSE_ATTN": "0"})):
+        for k in ("TCS_FUSE_UPS", "TCS_FUSE_ATTN"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        m = shim.CondUNetTiny(**orc.DEFAULT_CFG, precision="bf16", chunk=64)
+        m.load_state_dict(sd)
+        m = m.to("cuda").eval()
+        outs[name] = shim.predict_eps_cfg(m, x, t, y_cat, y_cont, 1.5).clone()
+        n_launch = m.launch_count()
+        del m
+        outs[name + "_launches"] = n_launch
+    e_ups, e_att = orc.rel_l2(outs["fused"], outs["ups_off"]), orc.rel_l2(outs["fused"], outs["attn_off"])
+    print(f"fused vs stand-alone upsample: eps rel-L2 {e_ups:.2e}; fused vs four-launch attention: {e_att:.2e}; "
+          f"launches {outs['fused_launches']} / {outs['ups_off_launches']} / {outs['attn_off_launches']}")
+    assert e_ups < 5e-3 and e_att < 1e-2, (e_ups, e_att)
+    assert outs["ups_off_launches"] == outs["fused_launches"] + 2 and outs["attn_off_launches"] == outs["fused_launches"] + 3
+
+
 # ---- round 2: gaps named by the round-1 review ----------------------------------------------------------
 def _oracle_on_cuda():
     """The oracle evaluated by PyTorch on the GPU in IEEE fp32 (TF32 off): seconds instead of minutes at n = 1024."""
