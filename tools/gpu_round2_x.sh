@@ -1,6 +1,10 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/r2_bench_q.json 2> gpurun_out/r2_bench_q.err; echo "bench exit $?"
-tail -c 2500 gpurun_out/r2_bench_q.json
-TCS_EXCHANGE_TIMEOUT=400000000000 timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 520 --csv --log-file gpurun_out/r2d_launches_bench.csv python bench.py --steps 1 --warmup 3 --no-extra --no-cpu-baseline --skip-e2e > gpurun_out/r2_ncu_bench3.log 2>&1
-python tools/launch_summary.py gpurun_out/r2d_launches_bench.csv
+timeout 900 python bench.py > gpurun_out/r2_bench_final.json 2> gpurun_out/r2_bench_final.err; echo "bench exit $?"
+python - <<'P'
+import json
+d=json.loads(open('gpurun_out/r2_bench_final.json').read().strip().splitlines()[-1])
+print(d['value'], d['e2e']['value'], d['clocks'], d['gpu_launches'], d['roofline']['achieved'], d['roofline']['frac'], d['roofline']['pass_ms'], d['whole_job']['frac'])
+print(d['roofline']['per_layer_tflops'])
+print({k:(v.get('value') if isinstance(v,dict) else v) for k,v in d['extra'].items()})
+P
