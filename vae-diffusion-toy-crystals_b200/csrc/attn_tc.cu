@@ -1,11 +1,12 @@
 // attn_tc.cu — SelfAttention2d (sde_score_model.py:136-167) of a 16x16x192 image as ONE tcgen05 kernel:
 //   GroupNorm(8 groups) -> qkv 1x1 conv -> per head softmax(q k^T / sqrt(48)) v -> proj 1x1 conv -> + x
 // q, k, v, the scores and the attention output never leave the SM (shared / tensor memory).  It replaces four
-// launches (gn_image16, conv_tc<attn.qkv>, attention_mma_kernel on mma.sync, conv_tc<attn.proj>).
+// launches of round 1 (gn_image16, conv_tc<attn.qkv>, an mma.sync attention kernel, conv_tc<attn.proj>).
 //
 // Work split: an image (256 tokens) is a CLUSTER OF TWO CTAs, each owning 128 tokens = the 128 TMEM lanes = one M tile.
-// Every CTA projects q, k, v of its own tokens; the k and v rows are written into BOTH CTAs' shared memory (DSMEM
-// stores), so that each CTA holds all 256 keys of the current head.  All MMAs are cta_group::1 (M = 128):
+// Every CTA projects q, k, v of its own tokens and pushes its 128 k / v rows into the peer's shared memory (one bulk
+// shared::cluster copy per operand, completing on the peer's mbarrier), so that each CTA holds all 256 keys of the
+// current head.  All MMAs are cta_group::1 (M = 128):
 //   qkv_h [128 x 144] = Xn [128 x 192] . W_h^T        A, B shared memory (K-major SWIZZLE_128B), per head h
 //   S     [128 x 256] = Q'_h [128 x 48] . K_h^T       A = Q' in TENSOR MEMORY (bf16 packed, tcgen05.st), Q' = q log2e/sqrt(48)
 //   O_h   [128 x  64] = P [128 x 256] . V_h           A = P (fp16) in tensor memory, written IN PLACE over the S columns;
@@ -17,7 +18,10 @@
 // dead Xn region) | K 32 K | V 32 K (128-byte rows, 48 of 64 elements used) | O 48 K.
 // Threads: warp 0 = control (one lane issues the bulk copies and every MMA), warps 1-8 = workers: warp w owns TMEM lane
 // quarter w % 4 (32 tokens) and column half (w - 1) / 4 of whatever is being read, so a softmax row is shared by two
-// threads (max and sum are combined through shared memory).
+// threads (the row maximum is combined through shared memory, the row sum comes out of the P V product).
+// Protocol: mbarriers only (struct AttnBars); the control lane issues the next head's projection right after S_h and the
+// P V product chunk by chunk behind the softmax; the workers convert the next head's q, k / v while the tensor core works.
+// The one cluster-wide barrier per image is the GroupNorm statistics exchange.
 // The building blocks (A operand in tensor memory, MN-major partial atom, DSMEM-written operands, 1-D bulk copies)
 // were probed on B200 first: tools/umma_attn_probe.cu, profiles/r2_attn_probe.txt.
 #include <cooperative_groups.h>
