@@ -20,7 +20,7 @@ def main():
     for line in names.splitlines():
         m = re.search(r"Function : (.*)", line)
         if m:
-            cur = re.sub(r"\(.*", "", m.group(1)).strip()
+            cur = re.sub(r"\(.*", "", m.group(1).replace("(anonymous namespace)::", "")).strip()
             per[cur] = collections.Counter()
             continue
         if cur is None:
