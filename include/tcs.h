@@ -180,6 +180,12 @@ int tcs_debug_conv(int32_t engine, int32_t precision, int32_t B, int32_t H_out, 
 int tcs_debug_conv_ups(int32_t B, int32_t H_out, int32_t W_out, int32_t cin, int32_t cout, const float* in_lowres,
                        const float* weight, const float* bias, float* out, void* stream);
 
+/* Host-only helper of the tests: the byte image of the attention block's weights as attn_block_tc_kernel copies it into
+ * shared memory (host pointers: qkv_w [576,192], proj_w [192,192]): per head [3 blocks of 64 input channels][144 rows =
+ * q | k | v rows of the head][128 B], then the projection [3][192 rows][128 B]; bf16, every 128-byte row with its 16-byte
+ * chunks at (chunk ^ (row & 7)) = SWIZZLE_128B.  out == NULL returns the size in bytes. */
+int64_t tcs_debug_attn_pack(const float* qkv_w, const float* proj_w, uint8_t* out, int64_t capacity);
+
 /* Run the fused attention block (csrc/attn_tc.cu: GroupNorm -> qkv -> softmax(q k^T / sqrt(48)) v -> proj -> + x,
  * SelfAttention2d.forward, sde_score_model.py:136-167) in isolation, bf16 / tcgen05.  Device fp32 pointers:
  *   x, out  : NHWC [B,16,16,192];  gn_w, gn_b [192];  qkv_w [576,192], qkv_b [576];  proj_w [192,192], proj_b [192]

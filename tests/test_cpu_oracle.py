@@ -276,3 +276,36 @@ def test_staged_reference_is_the_unmodified_module_and_runs():
     with torch.no_grad():
         tr = orc.sample(sd, orc.DEFAULT_CFG, orc.Schedule(0.1, 30.0), y_cat, y_cont, x0, "sde", 1, 1.5, 0.005, [z])
     assert torch.equal(img, tr.image)
+
+
+def test_attention_weight_image_layout():
+    """Host logic of the fused attention block (csrc/attn_tc.cu): the byte image the kernel bulk-copies into shared memory.
+    Per head [3 blocks of 64 input channels][144 rows = q | k | v rows of that head][128 B], then the projection
+    [3][192 rows][128 B]; bf16; the 16-byte chunk c of row r sits at chunk position c ^ (r & 7) (SWIZZLE_128B, which the UMMA
+    descriptors of the kernel assume).  Rows follow torch.chunk(qkv, 3) and the head split of SelfAttention2d.forward
+    (sde_score_model.py:149-155).  No GPU needed."""
+    L = _cabi.lib()
+    g = torch.Generator().manual_seed(3)
+    qkv_w = torch.randn((576, 192), generator=g)
+    proj_w = torch.randn((192, 192), generator=g)
+    need = int(L.tcs_debug_attn_pack(None, None, None, 0))
+    assert need == 4 * 3 * 144 * 128 + 3 * 192 * 128
+    buf = np.zeros(need, dtype=np.uint8)
+    got = L.tcs_debug_attn_pack(qkv_w.numpy().ctypes.data, proj_w.numpy().ctypes.data, buf.ctypes.data, need)
+    assert got == need
+    words = torch.from_numpy(buf.view(np.int16).copy()).view(torch.bfloat16).float()
+
+    def unpack(base_bytes, rows):   # [3 blocks][rows][64] -> [rows, 192]
+        out = torch.empty((rows, 192))
+        blk = words[base_bytes // 2: base_bytes // 2 + 3 * rows * 64].reshape(3, rows, 8, 8)   # [block][row][chunk position][8]
+        for r in range(rows):
+            pos = torch.tensor([c ^ (r & 7) for c in range(8)])
+            out[r] = blk[:, r, pos, :].reshape(192)
+        return out
+
+    for h in range(4):
+        w = unpack(h * 3 * 144 * 128, 144)
+        for kind in range(3):   # q, k, v rows of head h
+            want = qkv_w[kind * 192 + h * 48: kind * 192 + (h + 1) * 48].bfloat16().float()
+            assert torch.equal(w[kind * 48:(kind + 1) * 48], want), (h, kind)
+    assert torch.equal(unpack(4 * 3 * 144 * 128, 192), proj_w.bfloat16().float())

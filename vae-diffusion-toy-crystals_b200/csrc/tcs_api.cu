@@ -1495,6 +1495,15 @@ int tcs_debug_conv_ups(int32_t B, int32_t H_out, int32_t W_out, int32_t cin, int
                                      static_cast<cudaStream_t>(stream));
 }
 
+// Host-only: the weight image attn_block_tc_kernel bulk-copies (no device needed; tests check the layout on the CPU).
+int64_t tcs_debug_attn_pack(const float* qkv_w, const float* proj_w, uint8_t* out, int64_t capacity) {
+  const int64_t need = static_cast<int64_t>(attn_tc_wpack_bytes());
+  if (!out) return need;
+  if (!qkv_w || !proj_w || capacity < need) return fail(TCS_ERR_BAD_ARGUMENT, "tcs_debug_attn_pack: bad argument");
+  attn_tc_pack_weights(qkv_w, proj_w, out);
+  return need;
+}
+
 // The fused attention block in isolation (halo of the padded output verified like tcs_debug_conv's).
 int tcs_debug_attn_block(int32_t B, const float* x, const float* gn_w, const float* gn_b, const float* qkv_w,
                          const float* qkv_b, const float* proj_w, const float* proj_b, float* out, float* dbg,

@@ -104,6 +104,7 @@ SIGNATURES = {
                                  C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "tcs_debug_attn_block": (C.c_int, [C.c_int32] + [C.c_void_p] * 10),
     "tcs_debug_conv_ups": (C.c_int, [C.c_int32] * 5 + [C.c_void_p] * 5),
+    "tcs_debug_attn_pack": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
 }
 
 _lib: Optional[C.CDLL] = None
