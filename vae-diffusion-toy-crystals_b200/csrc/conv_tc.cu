@@ -659,12 +659,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       uint32_t sa = 0, pa = 0, sl = 0, pl = 0;
       // blend one cell (packed fp32x2 math: t = a + w (b - a), so that w = 0 / 1 copy a / b): chunk k of cell (cm, cn)
       auto blend_cell = [&](uint32_t lbase, uint32_t abase, uint32_t k, int cm, int cn, float wy0, float wy1, float wx0, float wx1) {
-        const uint32_t pA = cm * LP + cn, pB = pA + 1, pC = pA + LP, pD = pC + 1;
+        // the low-resolution window is NOT swizzled (its tensor map says so): the eight lanes of a cell read one pixel's
+        // 128 contiguous bytes, which is conflict-free as it is, and the four corners are constant offsets from one address
+        const uint32_t pa = lbase + (cm * LP + cn) * 128 + (k << 4);
         uint32_t a[4], bq[4], c[4], d[4];
-        ld_shared_u4(lbase + pA * 128 + ((k ^ (pA & 7)) << 4), a[0], a[1], a[2], a[3]);
-        ld_shared_u4(lbase + pB * 128 + ((k ^ (pB & 7)) << 4), bq[0], bq[1], bq[2], bq[3]);
-        ld_shared_u4(lbase + pC * 128 + ((k ^ (pC & 7)) << 4), c[0], c[1], c[2], c[3]);
-        ld_shared_u4(lbase + pD * 128 + ((k ^ (pD & 7)) << 4), d[0], d[1], d[2], d[3]);
+        ld_shared_u4(pa, a[0], a[1], a[2], a[3]);
+        ld_shared_u4(pa + 128, bq[0], bq[1], bq[2], bq[3]);
+        ld_shared_u4(pa + LP * 128, c[0], c[1], c[2], c[3]);
+        ld_shared_u4(pa + LP * 128 + 128, d[0], d[1], d[2], d[3]);
         uint32_t o00[4], o01[4], o10[4], o11[4];
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
@@ -1629,7 +1631,7 @@ int conv_tc_make_plan(ConvTcPlan* plan, const ConvGeom& g, const void* src0, con
       box[1] = static_cast<cuuint32_t>(p.P / 2 + 1); box[2] = 10;
     }
     CUresult r = encode(&pl.mapA[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(srcs[s]), dims, strides,
-                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, pl.ups ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(TCS_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed: " + std::to_string(r));
   }
